@@ -1,0 +1,722 @@
+// smj_api.cu -- the C-ABI of libsmj.so (include/smj.h): contexts, workspace arena, error reporting and the
+// single-GPU stage entry points smj_select / smj_sort / smj_merge / smj_join / smj_run.
+//
+// Stage order and semantics follow sort-merge-join/app.c:main (select :221-307, sort :315-373,
+// merge :413-547, join :585-688) and cpu_app.c:336-344.  There is no CPU fallback: every entry point
+// needs a CUDA device and returns SMJ_ENODEVICE without one.
+#include "smj_internal.h"
+#include "../../include/user.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_errbuf[512] = "";
+
+int smj_set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_errbuf, sizeof g_errbuf, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int smj_cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    const char *base = strrchr(file, '/');
+    snprintf(g_errbuf, sizeof g_errbuf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e),
+             base ? base + 1 : file, line, what);
+    if (e == cudaErrorMemoryAllocation) return SMJ_ENOMEM;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return SMJ_ENODEVICE;
+    return SMJ_ECUDA;
+}
+
+extern "C" const char *smj_strerror(int code)
+{
+    switch (code) {
+    case SMJ_OK: return "success";
+    case SMJ_EINVAL: return "invalid argument";
+    case SMJ_ENODEVICE: return "no CUDA device / library not initialised";
+    case SMJ_ECUDA: return "CUDA runtime error";
+    case SMJ_ENOMEM: return "out of memory";
+    case SMJ_ETOOBIG: return "input exceeds the supported row count";
+    case SMJ_ENCCL: return "NCCL error";
+    case SMJ_EINTERNAL: return "device-side consistency check failed";
+    default: return "unknown error";
+    }
+}
+extern "C" const char *smj_last_error(void) { return g_errbuf; }
+
+// ------------------------------------------------------------------ global state
+SmjCtx *g_ctx[8] = {};
+int g_nctx = 0;
+smj_config_t g_cfg;
+static bool g_inited = false;
+
+extern "C" void smj_config_default(smj_config_t *cfg)
+{
+    memset(cfg, 0, sizeof *cfg);
+    cfg->nr_gpus = NR_GPUS;
+    cfg->select_col1 = SELECT_COL1; cfg->select_val1 = SELECT_VAL1;
+    cfg->select_col2 = SELECT_COL2; cfg->select_val2 = SELECT_VAL2;
+    cfg->join_key1 = JOIN_KEY1; cfg->join_key2 = JOIN_KEY2;
+    cfg->join_mode = SMJ_JOIN_ZIP;
+#ifdef DEBUG
+    cfg->debug = 1;
+#endif
+}
+
+static int ctx_create(int device, SmjCtx **out)
+{
+    CUDA_TRY(cudaSetDevice(device));
+    SmjCtx *c = new SmjCtx();
+    c->device = device;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc(&c->d_err, 256));
+    CUDA_TRY(cudaMemset(c->d_err, 0, 256));
+    c->h_pinned_bytes = 1 << 16;
+    CUDA_TRY(cudaMallocHost(&c->h_pinned, c->h_pinned_bytes));
+    for (auto &e : c->ev) CUDA_TRY(cudaEventCreate(&e));
+    for (auto &e : c->pass_ev) CUDA_TRY(cudaEventCreate(&e));
+    // keep freed output buffers cached in the stream-ordered pool
+    cudaMemPool_t pool;
+    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;
+    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    *out = c;
+    return SMJ_OK;
+}
+
+static void ctx_destroy(SmjCtx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < SmjCtx::kSlots; i++) if (c->slot[i]) cudaFree(c->slot[i]);
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : c->pass_ev) if (e) cudaEventDestroy(e);
+    if (c->d_err) cudaFree(c->d_err);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+void *smj_ws(SmjCtx *c, int slot, size_t bytes)
+{
+    if (bytes == 0) bytes = 256;
+    if (c->slot_bytes[slot] >= bytes) return c->slot[slot];
+    if (c->slot[slot]) { cudaStreamSynchronize(c->stream); cudaFree(c->slot[slot]); c->slot[slot] = nullptr; c->slot_bytes[slot] = 0; }
+    const size_t want = align_up(bytes + bytes / 16, 1 << 20);   // a little slack so near-equal sizes do not realloc
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { smj_cuda_fail(e, "workspace cudaMalloc", __FILE__, __LINE__); return nullptr; }
+    c->slot[slot] = p;
+    c->slot_bytes[slot] = want;
+    return p;
+}
+#define WS_TRY(var, type, c, slot, bytes) type var = (type)smj_ws(c, slot, bytes); if (!var) return SMJ_ENOMEM
+
+extern "C" int smj_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" int smj_version(void) { return SMJ_VERSION; }
+
+extern "C" int smj_init(const smj_config_t *cfg)
+{
+    if (g_inited) {
+        if (cfg) {
+            if (cfg->nr_gpus > g_nctx) { smj_shutdown(); }
+            else { g_cfg = *cfg; return SMJ_OK; }
+        } else return SMJ_OK;
+    }
+    if (cfg) g_cfg = *cfg; else smj_config_default(&g_cfg);
+    if (g_cfg.nr_gpus < 1) g_cfg.nr_gpus = 1;
+    const int ndev = smj_device_count();
+    if (ndev < 1) return smj_set_error(SMJ_ENODEVICE, "no CUDA device visible (libsmj has no CPU fallback)");
+    if (g_cfg.nr_gpus > ndev || g_cfg.nr_gpus > 8)
+        return smj_set_error(SMJ_EINVAL, "nr_gpus=%d but %d CUDA devices visible (max 8)", g_cfg.nr_gpus, ndev);
+    for (int g = 0; g < g_cfg.nr_gpus; g++) {
+        int r = ctx_create(g, &g_ctx[g]);
+        if (r != SMJ_OK) { smj_shutdown(); return r; }
+        g_nctx = g + 1;
+    }
+    cudaSetDevice(g_ctx[0]->device);
+    g_inited = true;
+    return SMJ_OK;
+}
+
+int smj_dist_shutdown(void);
+static void pinned_clear(void);
+
+extern "C" void smj_shutdown(void)
+{
+    smj_dist_shutdown();
+    pinned_clear();
+    for (int g = 0; g < 8; g++) { ctx_destroy(g_ctx[g]); g_ctx[g] = nullptr; }
+    g_nctx = 0;
+    g_inited = false;
+}
+
+int smj_ensure_init(void)
+{
+    if (g_inited) return SMJ_OK;
+    return smj_init(nullptr);
+}
+
+extern "C" int64_t smj_kernel_launches(void)
+{
+    int64_t n = 0;
+    for (int g = 0; g < g_nctx; g++) n += g_ctx[g]->launches;
+    return n;
+}
+
+// ------------------------------------------------------------------ memory helpers
+extern "C" int smj_host_alloc(void **p, size_t bytes)
+{
+    SMJ_TRY(smj_ensure_init());
+    CUDA_TRY(cudaMallocHost(p, bytes ? bytes : 1));
+    return SMJ_OK;
+}
+extern "C" void smj_host_free(void *p) { if (p) cudaFreeHost(p); }
+extern "C" int smj_device_alloc(void **p, size_t bytes)
+{
+    SMJ_TRY(smj_ensure_init());
+    CUDA_TRY(cudaSetDevice(g_ctx[0]->device));
+    CUDA_TRY(cudaMalloc(p, bytes ? bytes : 1));
+    return SMJ_OK;
+}
+extern "C" void smj_device_free(void *p) { if (p) cudaFree(p); }
+extern "C" int smj_memcpy_h2d(void *dst, const void *src, size_t bytes)
+{
+    SMJ_TRY(smj_ensure_init());
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_ctx[0]->stream));
+    CUDA_TRY(cudaStreamSynchronize(g_ctx[0]->stream));
+    return SMJ_OK;
+}
+extern "C" int smj_memcpy_d2h(void *dst, const void *src, size_t bytes)
+{
+    SMJ_TRY(smj_ensure_init());
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_ctx[0]->stream));
+    CUDA_TRY(cudaStreamSynchronize(g_ctx[0]->stream));
+    return SMJ_OK;
+}
+extern "C" int smj_device_sync(void)
+{
+    SMJ_TRY(smj_ensure_init());
+    for (int g = 0; g < g_nctx; g++) {
+        CUDA_TRY(cudaSetDevice(g_ctx[g]->device));
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
+    CUDA_TRY(cudaSetDevice(g_ctx[0]->device));
+    return SMJ_OK;
+}
+
+extern "C" int smj_synth_table(int32_t *dev_out, int64_t row0, int64_t rows, int64_t total_rows, int cols, int key_col,
+                               uint64_t seed, int kind, int64_t key_domain)
+{
+    SMJ_TRY(smj_ensure_init());
+    SmjCtx *c = g_ctx[0];
+    SMJ_TRY(smj_launch_synth(c, dev_out, row0, rows, total_rows, cols, key_col, seed, kind, key_domain));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SMJ_OK;
+}
+
+// ------------------------------------------------------------------ table staging
+static int check_table(const smj_table_t *t, const char *name)
+{
+    if (!t) return smj_set_error(SMJ_EINVAL, "%s: null table", name);
+    if (t->cols < 1 || t->rows < 0) return smj_set_error(SMJ_EINVAL, "%s: bad shape %lld x %d", name, (long long)t->rows, t->cols);
+    if (t->rows > 0 && !t->data) return smj_set_error(SMJ_EINVAL, "%s: null data", name);
+    if (t->rows > 0xffffffffll) return smj_set_error(SMJ_ETOOBIG, "%s: %lld rows exceed 32-bit row ids", name, (long long)t->rows);
+    return SMJ_OK;
+}
+
+// Device view of an input table: the caller's pointer when it already lives in HBM, else an async H2D copy
+// into a workspace slot (the analogue of dpu_prepare_xfer + dpu_push_xfer, app.c:222-243).
+int smj_stage_in(SmjCtx *c, const smj_table_t *t, int slot, const int32_t **d)
+{
+    if (t->on_device || t->rows == 0) { *d = t->data; return SMJ_OK; }
+    const size_t bytes = (size_t)t->rows * t->cols * sizeof(int32_t);
+    WS_TRY(p, int32_t *, c, slot, bytes);
+    CUDA_TRY(cudaMemcpyAsync(p, t->data, bytes, cudaMemcpyHostToDevice, c->stream));
+    *d = p;
+    return SMJ_OK;
+}
+
+// Pinned host buffers for host-side outputs are recycled: cudaMallocHost costs milliseconds per call,
+// which would dominate the GPU->CPU leg (app.c timer 2) of a sub-millisecond pipeline.
+struct PinnedEntry { void *p; size_t bytes; bool used; };
+static PinnedEntry g_pinned[16];
+
+static int pinned_get(void **out, size_t bytes)
+{
+    int best = -1, spare = -1;
+    for (int i = 0; i < 16; i++) {
+        if (g_pinned[i].p && !g_pinned[i].used && g_pinned[i].bytes >= bytes &&
+            (best < 0 || g_pinned[i].bytes < g_pinned[best].bytes)) best = i;
+        if (!g_pinned[i].p && spare < 0) spare = i;
+    }
+    if (best >= 0 && g_pinned[best].bytes <= 4 * bytes + (1 << 20)) { g_pinned[best].used = true; *out = g_pinned[best].p; return SMJ_OK; }
+    if (spare < 0)
+        for (int i = 0; i < 16; i++)
+            if (!g_pinned[i].used) { cudaFreeHost(g_pinned[i].p); g_pinned[i].p = nullptr; spare = i; break; }
+    void *p = nullptr;
+    CUDA_TRY(cudaMallocHost(&p, bytes));
+    if (spare >= 0) g_pinned[spare] = {p, bytes, true};
+    *out = p;
+    return SMJ_OK;
+}
+static void pinned_put(void *p)
+{
+    for (int i = 0; i < 16; i++)
+        if (g_pinned[i].p == p) { g_pinned[i].used = false; return; }
+    cudaFreeHost(p);
+}
+static void pinned_clear(void)
+{
+    for (int i = 0; i < 16; i++) { if (g_pinned[i].p) cudaFreeHost(g_pinned[i].p); g_pinned[i] = {nullptr, 0, false}; }
+}
+
+// Output allocation: device memory from the stream-ordered pool, or (recycled) pinned host memory.
+int smj_alloc_out(SmjCtx *c, smj_table_t *out, int64_t rows, int cols)
+{
+    const int on_device = out->on_device;
+    out->rows = rows; out->cols = cols; out->data = nullptr;
+    const size_t bytes = (size_t)rows * cols * sizeof(int32_t);
+    if (bytes == 0) return SMJ_OK;
+    if (on_device) CUDA_TRY(cudaMallocAsync((void **)&out->data, bytes, c->stream));
+    else SMJ_TRY(pinned_get((void **)&out->data, bytes));
+    return SMJ_OK;
+}
+
+extern "C" void smj_table_free(smj_table_t *t)
+{
+    if (!t || !t->data) return;
+    if (t->on_device) {
+        cudaPointerAttributes at;
+        SmjCtx *c = g_nctx > 0 ? g_ctx[0] : nullptr;
+        if (cudaPointerGetAttributes(&at, t->data) == cudaSuccess)
+            for (int g = 0; g < g_nctx; g++) if (g_ctx[g]->device == at.device) c = g_ctx[g];
+        if (c) { cudaSetDevice(c->device); cudaFreeAsync(t->data, c->stream); cudaSetDevice(g_ctx[0]->device); }
+        else cudaFree(t->data);
+    } else pinned_put(t->data);
+    t->data = nullptr; t->rows = 0;
+}
+
+// Produces the output table from a device buffer of rows (device->device copy is avoided by allocating the
+// final buffer up front when the destination is the device).
+static int emit_out_from_device(SmjCtx *c, smj_table_t *out, const int32_t *d_rows, int64_t rows, int cols)
+{
+    SMJ_TRY(smj_alloc_out(c, out, rows, cols));
+    const size_t bytes = (size_t)rows * cols * sizeof(int32_t);
+    if (bytes)
+        CUDA_TRY(cudaMemcpyAsync(out->data, d_rows, bytes, out->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                 c->stream));
+    return SMJ_OK;
+}
+
+int smj_check_device_flag(SmjCtx *c)
+{
+    u32 *h = (u32 *)((char *)c->h_pinned + c->h_pinned_bytes - 64);
+    CUDA_TRY(cudaMemcpyAsync(h, c->d_err, 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (*h) {
+        const u32 code = *h;
+        cudaMemsetAsync(c->d_err, 0, 4, c->stream);
+        return smj_set_error(SMJ_EINTERNAL, "device-side check failed (code %u: look-back spin limit in %s)", code,
+                             code == 1 ? "select" : code == 2 ? "radix sort" : "join");
+    }
+    return SMJ_OK;
+}
+
+// Scratch header, zeroed at the start of every call that uses it.
+struct ScratchHeader {
+    u32 hist[2][SMJ_KEY_PASSES * SMJ_RADIX];
+    u64 count[2];
+    u64 jcount;
+    u64 pad0;
+    u32 counter[16];     // 0,1: select tickets; 2: join ticket
+};
+
+// (key,rowid) pairs of every row of a device table (no predicate): used by sort / merge / join entry points.
+static int pairs_of_table(SmjCtx *c, const int32_t *d_t, int64_t rows, int cols, int key_col, u32 rowid_base, u64 *d_pairs,
+                          char *scratch_status, u32 *d_counter, u32 *d_hist, u64 *d_count)
+{
+    return smj_launch_select_pairs(c, d_t, rows, cols, key_col, 0, /*select_all=*/1, key_col, rowid_base, d_pairs,
+                                   (u64 *)scratch_status, d_counter, d_hist, d_count);
+}
+
+// ------------------------------------------------------------------ smj_select
+extern "C" int smj_select(const smj_table_t *in, int col, int64_t val, smj_table_t *out)
+{
+    SMJ_TRY(smj_ensure_init());
+    SMJ_TRY(check_table(in, "smj_select"));
+    if (!out) return smj_set_error(SMJ_EINVAL, "smj_select: null out");
+    if (col < 0 || col >= in->cols) return smj_set_error(SMJ_EINVAL, "smj_select: column %d out of range", col);
+    SmjCtx *c = g_ctx[0];
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int64_t n = in->rows;
+    const int32_t *d_in;
+    SMJ_TRY(smj_stage_in(c, in, WS_T1, &d_in));
+    const size_t tiles = smj_select_num_tiles(n);
+    const size_t sbytes = sizeof(ScratchHeader) + tiles * 8;
+    WS_TRY(scr, char *, c, WS_SCRATCH, sbytes);
+    CUDA_TRY(cudaMemsetAsync(scr, 0, sbytes, c->stream));
+    ScratchHeader *h = (ScratchHeader *)scr;
+    WS_TRY(pairs, u64 *, c, WS_PAIRS_A1, (size_t)n * 8);
+    SMJ_TRY(smj_launch_select_pairs(c, d_in, n, in->cols, col, val, 0, col, 0, pairs, (u64 *)(scr + sizeof(ScratchHeader)),
+                                    &h->counter[0], nullptr, &h->count[0]));
+    u64 *hm = (u64 *)c->h_pinned;
+    CUDA_TRY(cudaMemcpyAsync(hm, &h->count[0], 8, cudaMemcpyDeviceToHost, c->stream));
+    SMJ_TRY(smj_check_device_flag(c));
+    const int64_t m = (int64_t)hm[0];
+    if (out->on_device) {
+        SMJ_TRY(smj_alloc_out(c, out, m, in->cols));
+        SMJ_TRY(smj_launch_gather_rows(c, pairs, m, d_in, in->cols, out->data));
+    } else {
+        WS_TRY(tmp, int32_t *, c, WS_TMP_ROWS, (size_t)m * in->cols * 4);
+        SMJ_TRY(smj_launch_gather_rows(c, pairs, m, d_in, in->cols, tmp));
+        SMJ_TRY(emit_out_from_device(c, out, tmp, m, in->cols));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SMJ_OK;
+}
+
+// ------------------------------------------------------------------ smj_sort
+// Sorts the n pairs in `pairs` (ping buffer) using `pong`; d_hist must hold their digit histogram.
+static int sort_pairs_with_hist(SmjCtx *c, u64 *pairs, u64 *pong, u32 n, const u32 *d_hist, int scratch_slot, u64 **sorted)
+{
+    u32 *hh = (u32 *)c->h_pinned;
+    CUDA_TRY(cudaMemcpyAsync(hh, d_hist, SMJ_KEY_PASSES * SMJ_RADIX * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const size_t rbytes = smj_radix_scratch_bytes(n);
+    WS_TRY(rs, u32 *, c, scratch_slot, rbytes);
+    CUDA_TRY(cudaMemsetAsync(rs, 0, rbytes, c->stream));
+    return smj_radix_sort_pairs(c, pairs, pong, n, d_hist, hh, rs, sorted);
+}
+
+extern "C" int smj_sort(smj_table_t *inout, int key_col)
+{
+    SMJ_TRY(smj_ensure_init());
+    SMJ_TRY(check_table(inout, "smj_sort"));
+    if (key_col < 0 || key_col >= inout->cols) return smj_set_error(SMJ_EINVAL, "smj_sort: column %d out of range", key_col);
+    SmjCtx *c = g_ctx[0];
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int64_t n = inout->rows;
+    if (n < 2) return SMJ_OK;
+    if (n > SMJ_MAX_SORT_ROWS) return smj_set_error(SMJ_ETOOBIG, "smj_sort: %lld rows exceed 2^30 - 1", (long long)n);
+    const int32_t *d_in;
+    SMJ_TRY(smj_stage_in(c, inout, WS_T1, &d_in));
+    const size_t tiles = smj_select_num_tiles(n);
+    const size_t sbytes = sizeof(ScratchHeader) + tiles * 8;
+    WS_TRY(scr, char *, c, WS_SCRATCH, sbytes);
+    CUDA_TRY(cudaMemsetAsync(scr, 0, sbytes, c->stream));
+    ScratchHeader *h = (ScratchHeader *)scr;
+    WS_TRY(ping, u64 *, c, WS_PAIRS_A1, (size_t)n * 8);
+    WS_TRY(pong, u64 *, c, WS_PAIRS_B1, (size_t)n * 8);
+    SMJ_TRY(pairs_of_table(c, d_in, n, inout->cols, key_col, 0, ping, scr + sizeof(ScratchHeader), &h->counter[0],
+                           h->hist[0], &h->count[0]));
+    u64 *sorted;
+    c->pass_count = 0;
+    SMJ_TRY(sort_pairs_with_hist(c, ping, pong, (u32)n, h->hist[0], WS_RADIX, &sorted));
+    const size_t bytes = (size_t)n * inout->cols * 4;
+    WS_TRY(tmp, int32_t *, c, WS_TMP_ROWS, bytes);
+    SMJ_TRY(smj_launch_gather_rows(c, sorted, n, d_in, inout->cols, tmp));
+    CUDA_TRY(cudaMemcpyAsync(inout->data, tmp, bytes, inout->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                             c->stream));
+    SMJ_TRY(smj_check_device_flag(c));
+    return SMJ_OK;
+}
+
+// ------------------------------------------------------------------ smj_merge
+extern "C" int smj_merge(const smj_table_t *a, const smj_table_t *b, int key_col, smj_table_t *out)
+{
+    SMJ_TRY(smj_ensure_init());
+    SMJ_TRY(check_table(a, "smj_merge(a)"));
+    SMJ_TRY(check_table(b, "smj_merge(b)"));
+    if (!out) return smj_set_error(SMJ_EINVAL, "smj_merge: null out");
+    if (a->cols != b->cols) return smj_set_error(SMJ_EINVAL, "smj_merge: runs of one table must have equal column counts");
+    if (key_col < 0 || key_col >= a->cols) return smj_set_error(SMJ_EINVAL, "smj_merge: column %d out of range", key_col);
+    const int64_t total = a->rows + b->rows;
+    if (total > SMJ_MAX_SORT_ROWS) return smj_set_error(SMJ_ETOOBIG, "smj_merge: %lld rows exceed 2^30 - 1", (long long)total);
+    SmjCtx *c = g_ctx[0];
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int cols = a->cols;
+    const int32_t *d_a, *d_b;
+    SMJ_TRY(smj_stage_in(c, a, WS_T1, &d_a));
+    SMJ_TRY(smj_stage_in(c, b, WS_T2, &d_b));
+    const size_t ta = smj_select_num_tiles(a->rows), tb = smj_select_num_tiles(b->rows);
+    const size_t sbytes = sizeof(ScratchHeader) + (ta + tb) * 8;
+    WS_TRY(scr, char *, c, WS_SCRATCH, sbytes);
+    CUDA_TRY(cudaMemsetAsync(scr, 0, sbytes, c->stream));
+    ScratchHeader *h = (ScratchHeader *)scr;
+    WS_TRY(pa, u64 *, c, WS_PAIRS_A1, (size_t)a->rows * 8);
+    WS_TRY(pb, u64 *, c, WS_PAIRS_A2, (size_t)b->rows * 8);
+    WS_TRY(pm, u64 *, c, WS_PAIRS_B1, (size_t)total * 8);
+    SMJ_TRY(pairs_of_table(c, d_a, a->rows, cols, key_col, 0, pa, scr + sizeof(ScratchHeader), &h->counter[0], nullptr, &h->count[0]));
+    SMJ_TRY(pairs_of_table(c, d_b, b->rows, cols, key_col, (u32)a->rows, pb, scr + sizeof(ScratchHeader) + ta * 8,
+                           &h->counter[1], nullptr, &h->count[1]));
+    WS_TRY(part, u32 *, c, WS_PART, (smj_merge_num_tiles((u64)total) + 2) * 4);
+    SMJ_TRY(smj_launch_merge_pairs(c, pa, (u32)a->rows, pb, (u32)b->rows, pm, part));
+    if (out->on_device) {
+        SMJ_TRY(smj_alloc_out(c, out, total, cols));
+        SMJ_TRY(smj_launch_gather_rows2(c, pm, total, d_a, d_b, (u32)a->rows, cols, out->data));
+    } else {
+        WS_TRY(tmp, int32_t *, c, WS_TMP_ROWS, (size_t)total * cols * 4);
+        SMJ_TRY(smj_launch_gather_rows2(c, pm, total, d_a, d_b, (u32)a->rows, cols, tmp));
+        SMJ_TRY(emit_out_from_device(c, out, tmp, total, cols));
+    }
+    SMJ_TRY(smj_check_device_flag(c));
+    return SMJ_OK;
+}
+
+// ------------------------------------------------------------------ smj_join
+static int join_sorted_pairs(SmjCtx *c, const u64 *pl, u32 m1, const u64 *pr, u32 m2, int mode, bool count_only,
+                             const int32_t *d_t1, int c1, const int32_t *d_t2, int c2, int key2, smj_table_t *out,
+                             int64_t *rows_out)
+{
+    // scratch for the join lives in WS_PART: [jcount u64][ticket u32 + pad][status tiles*8][part 2*(tiles+1) u32]
+    const size_t tiles = smj_join_num_tiles((u64)m1 + m2);
+    const size_t sbytes = 64 + tiles * 8 + (tiles + 1) * 2 * 4;
+    WS_TRY(js, char *, c, WS_PART, sbytes);
+    CUDA_TRY(cudaMemsetAsync(js, 0, 64 + tiles * 8, c->stream));
+    u64 *d_jcount = (u64 *)js;
+    u32 *d_ticket = (u32 *)(js + 16);
+    u64 *d_status = (u64 *)(js + 64);
+    u32 *d_part = (u32 *)(js + 64 + tiles * 8);
+    const u32 mmin = m1 < m2 ? m1 : m2;
+    uint2 *d_matches = nullptr;
+    if (mode == SMJ_JOIN_ZIP) { WS_TRY(mm, uint2 *, c, WS_MATCH, (size_t)mmin * 8); d_matches = mm; }
+    else if (!count_only) return smj_set_error(SMJ_EINVAL, "SMJ_JOIN_MANY materialisation is not available in this build; use smj_join_count");
+    SMJ_TRY(smj_launch_join_match(c, pl, m1, pr, m2, mode, d_part, d_status, d_ticket, d_matches, d_jcount));
+    u64 *hm = (u64 *)c->h_pinned;
+    CUDA_TRY(cudaMemcpyAsync(hm, d_jcount, 8, cudaMemcpyDeviceToHost, c->stream));
+    SMJ_TRY(smj_check_device_flag(c));
+    const int64_t j = (int64_t)hm[0];
+    *rows_out = j;
+    if (count_only) return SMJ_OK;
+    const int c_out = c1 + c2 - 1;
+    if (out->on_device) {
+        SMJ_TRY(smj_alloc_out(c, out, j, c_out));
+        SMJ_TRY(smj_launch_join_materialize(c, d_matches, j, d_t1, c1, d_t2, c2, key2, out->data));
+    } else {
+        WS_TRY(tmp, int32_t *, c, WS_TMP_ROWS, (size_t)j * c_out * 4);
+        SMJ_TRY(smj_launch_join_materialize(c, d_matches, j, d_t1, c1, d_t2, c2, key2, tmp));
+        SMJ_TRY(emit_out_from_device(c, out, tmp, j, c_out));
+    }
+    return SMJ_OK;
+}
+
+static int join_tables(const smj_table_t *l, const smj_table_t *r, int key1, int key2, int mode, bool count_only,
+                       smj_table_t *out, int64_t *rows_out)
+{
+    SMJ_TRY(smj_ensure_init());
+    SMJ_TRY(check_table(l, "smj_join(l)"));
+    SMJ_TRY(check_table(r, "smj_join(r)"));
+    if (key1 < 0 || key1 >= l->cols || key2 < 0 || key2 >= r->cols) return smj_set_error(SMJ_EINVAL, "smj_join: key column out of range");
+    if (mode != SMJ_JOIN_ZIP && mode != SMJ_JOIN_MANY) return smj_set_error(SMJ_EINVAL, "smj_join: bad mode %d", mode);
+    if (l->rows > SMJ_MAX_SORT_ROWS || r->rows > SMJ_MAX_SORT_ROWS) return smj_set_error(SMJ_ETOOBIG, "smj_join: more than 2^30 - 1 rows");
+    SmjCtx *c = g_ctx[0];
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int32_t *d_l, *d_r;
+    SMJ_TRY(smj_stage_in(c, l, WS_T1, &d_l));
+    SMJ_TRY(smj_stage_in(c, r, WS_T2, &d_r));
+    const size_t tl = smj_select_num_tiles(l->rows), tr = smj_select_num_tiles(r->rows);
+    const size_t sbytes = sizeof(ScratchHeader) + (tl + tr) * 8;
+    WS_TRY(scr, char *, c, WS_SCRATCH, sbytes);
+    CUDA_TRY(cudaMemsetAsync(scr, 0, sbytes, c->stream));
+    ScratchHeader *h = (ScratchHeader *)scr;
+    WS_TRY(pl, u64 *, c, WS_PAIRS_A1, (size_t)l->rows * 8);
+    WS_TRY(pr, u64 *, c, WS_PAIRS_A2, (size_t)r->rows * 8);
+    SMJ_TRY(pairs_of_table(c, d_l, l->rows, l->cols, key1, 0, pl, scr + sizeof(ScratchHeader), &h->counter[0], nullptr, &h->count[0]));
+    SMJ_TRY(pairs_of_table(c, d_r, r->rows, r->cols, key2, 0, pr, scr + sizeof(ScratchHeader) + tl * 8, &h->counter[1], nullptr,
+                           &h->count[1]));
+    SMJ_TRY(join_sorted_pairs(c, pl, (u32)l->rows, pr, (u32)r->rows, mode, count_only, d_l, l->cols, d_r, r->cols, key2, out, rows_out));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SMJ_OK;
+}
+
+extern "C" int smj_join(const smj_table_t *l, const smj_table_t *r, int key1, int key2, int mode, smj_table_t *out)
+{
+    if (!out) return smj_set_error(SMJ_EINVAL, "smj_join: null out");
+    int64_t rows;
+    return join_tables(l, r, key1, key2, mode, false, out, &rows);
+}
+
+extern "C" int smj_join_count(const smj_table_t *l, const smj_table_t *r, int key1, int key2, int mode, int64_t *rows)
+{
+    if (!rows) return smj_set_error(SMJ_EINVAL, "smj_join_count: null rows");
+    return join_tables(l, r, key1, key2, mode, true, nullptr, rows);
+}
+
+// ------------------------------------------------------------------ smj_run (single GPU)
+// SURVEY.md section 8d algorithmic-bytes model (w = 4, P = 4 radix passes).
+static double bytes_model(const int64_t n[2], const int c[2], const int64_t m[2], int64_t j)
+{
+    double b = 0;
+    for (int t = 0; t < 2; t++)
+        b += (double)n[t] * c[t] * 4 + 8.0 * m[t] + 8.0 * m[t] + 16.0 * SMJ_KEY_PASSES * m[t] + 4.0 * m[t] + 2.0 * m[t] * c[t] * 4;
+    b += 8.0 * (m[0] + m[1]) + (double)j * (c[0] + c[1] + (c[0] + c[1] - 1)) * 4;
+    return b;
+}
+
+static float ev_ms(cudaEvent_t a, cudaEvent_t b)
+{
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return ms;
+}
+
+int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, smj_table_t *out,
+                   smj_stats_t *stats)
+{
+    CUDA_TRY(cudaSetDevice(c->device));
+    const smj_table_t *tb[2] = {t1, t2};
+    const int sel_col[2] = {cfg->select_col1, cfg->select_col2};
+    const int64_t sel_val[2] = {cfg->select_val1, cfg->select_val2};
+    const int key[2] = {cfg->join_key1, cfg->join_key2};
+    for (int t = 0; t < 2; t++) {
+        if (sel_col[t] < 0 || sel_col[t] >= tb[t]->cols) return smj_set_error(SMJ_EINVAL, "SELECT_COL%d=%d out of range", t + 1, sel_col[t]);
+        if (key[t] < 0 || key[t] >= tb[t]->cols) return smj_set_error(SMJ_EINVAL, "JOIN_KEY%d=%d out of range", t + 1, key[t]);
+    }
+    if (cfg->join_mode != SMJ_JOIN_ZIP) return smj_set_error(SMJ_EINVAL, "smj_run materialises SMJ_JOIN_ZIP only (the reference semantics)");
+    const int64_t launches0 = c->launches;
+    c->pass_count = 0;
+    enum { E_START, E_H2D, E_SELECT, E_SORT, E_JOIN, E_D2H };
+
+    // ---- CPU -> GPU (app.c timer 0)
+    CUDA_TRY(cudaEventRecord(c->ev[E_START], c->stream));
+    const int32_t *d_t[2];
+    SMJ_TRY(smj_stage_in(c, t1, WS_T1, &d_t[0]));
+    SMJ_TRY(smj_stage_in(c, t2, WS_T2, &d_t[1]));
+    const int64_t n[2] = {t1->rows, t2->rows};
+    const int cc[2] = {t1->cols, t2->cols};
+    const size_t tiles[2] = {smj_select_num_tiles(n[0]), smj_select_num_tiles(n[1])};
+    const size_t sbytes = sizeof(ScratchHeader) + (tiles[0] + tiles[1]) * 8;
+    WS_TRY(scr, char *, c, WS_SCRATCH, sbytes);
+    WS_TRY(ping0, u64 *, c, WS_PAIRS_A1, (size_t)n[0] * 8);
+    WS_TRY(ping1, u64 *, c, WS_PAIRS_A2, (size_t)n[1] * 8);
+    u64 *ping[2] = {ping0, ping1};
+    CUDA_TRY(cudaEventRecord(c->ev[E_H2D], c->stream));
+
+    // ---- select (+ digit histograms), both tables, then one host round trip for the survivor counts
+    CUDA_TRY(cudaMemsetAsync(scr, 0, sbytes, c->stream));
+    ScratchHeader *h = (ScratchHeader *)scr;
+    char *st = scr + sizeof(ScratchHeader);
+    for (int t = 0; t < 2; t++)
+        SMJ_TRY(smj_launch_select_pairs(c, d_t[t], n[t], cc[t], sel_col[t], sel_val[t], 0, key[t], 0, ping[t],
+                                        (u64 *)(st + (t ? tiles[0] * 8 : 0)), &h->counter[t], h->hist[t], &h->count[t]));
+    CUDA_TRY(cudaEventRecord(c->ev[E_SELECT], c->stream));
+    ScratchHeader *hh = (ScratchHeader *)c->h_pinned;
+    CUDA_TRY(cudaMemcpyAsync(hh, h, sizeof(ScratchHeader), cudaMemcpyDeviceToHost, c->stream));
+    SMJ_TRY(smj_check_device_flag(c));
+    const int64_t m[2] = {(int64_t)hh->count[0], (int64_t)hh->count[1]};
+    if (m[0] > SMJ_MAX_SORT_ROWS || m[1] > SMJ_MAX_SORT_ROWS)
+        return smj_set_error(SMJ_ETOOBIG, "selected %lld / %lld rows; this build sorts at most 2^30 - 1 per table per GPU",
+                             (long long)m[0], (long long)m[1]);
+    if (cfg->debug) {   // app.c:294-305 prints one "select" line per DPU; one GPU here
+        printf("==================\n#    select.cu   #\n==================\n");
+        for (int t = 0; t < 2; t++) printf("Table %d : select %lld rows\n", t, (long long)m[t]);
+        printf("####################\n\n");
+    }
+
+    // ---- sort
+    u32 host_hist[2][SMJ_KEY_PASSES * SMJ_RADIX];
+    memcpy(host_hist, hh->hist, sizeof host_hist);
+    u64 *sorted[2];
+    WS_TRY(pong0, u64 *, c, WS_PAIRS_B1, (size_t)m[0] * 8);
+    WS_TRY(pong1, u64 *, c, WS_PAIRS_B2, (size_t)m[1] * 8);
+    u64 *pong[2] = {pong0, pong1};
+    const size_t rb[2] = {align_up(smj_radix_scratch_bytes((u32)m[0]), 256), align_up(smj_radix_scratch_bytes((u32)m[1]), 256)};
+    WS_TRY(rs, char *, c, WS_RADIX, rb[0] + rb[1]);
+    CUDA_TRY(cudaMemsetAsync(rs, 0, rb[0] + rb[1], c->stream));
+    for (int t = 0; t < 2; t++)
+        SMJ_TRY(smj_radix_sort_pairs(c, ping[t], pong[t], (u32)m[t], h->hist[t], host_hist[t], (u32 *)(rs + (t ? rb[0] : 0)), &sorted[t]));
+    CUDA_TRY(cudaEventRecord(c->ev[E_SORT], c->stream));
+    if (cfg->debug) {
+        printf("==================\n#     sort.cu    #\n==================\n");
+        for (int t = 0; t < 2; t++) printf("Table %d - GPU %d sort %lld rows\n", t, c->device, (long long)m[t]);
+        printf("####################\n\n");
+    }
+
+    // ---- join: co-rank, count, scan, write matches; then materialise rows straight from the input tables
+    int64_t j = 0;
+    smj_table_t dev_out = {nullptr, 0, cc[0] + cc[1] - 1, 1};
+    const int c_out = cc[0] + cc[1] - 1;
+    {
+        const size_t jt = smj_join_num_tiles((u64)m[0] + m[1]);
+        const size_t jbytes = 64 + jt * 8 + (jt + 1) * 2 * 4;
+        WS_TRY(js, char *, c, WS_PART, jbytes);
+        CUDA_TRY(cudaMemsetAsync(js, 0, 64 + jt * 8, c->stream));
+        const u32 mmin = (u32)(m[0] < m[1] ? m[0] : m[1]);
+        WS_TRY(mm, uint2 *, c, WS_MATCH, (size_t)mmin * 8);
+        SMJ_TRY(smj_launch_join_match(c, sorted[0], (u32)m[0], sorted[1], (u32)m[1], SMJ_JOIN_ZIP, (u32 *)(js + 64 + jt * 8),
+                                      (u64 *)(js + 64), (u32 *)(js + 16), mm, (u64 *)js));
+        u64 *hm = (u64 *)c->h_pinned;
+        CUDA_TRY(cudaMemcpyAsync(hm, js, 8, cudaMemcpyDeviceToHost, c->stream));
+        SMJ_TRY(smj_check_device_flag(c));
+        j = (int64_t)hm[0];
+        SMJ_TRY(smj_alloc_out(c, &dev_out, j, c_out));
+        SMJ_TRY(smj_launch_join_materialize(c, mm, j, d_t[0], cc[0], d_t[1], cc[1], key[1], dev_out.data));
+    }
+    CUDA_TRY(cudaEventRecord(c->ev[E_JOIN], c->stream));
+
+    // ---- GPU -> CPU (app.c timer 2)
+    if (out->on_device) {
+        *out = dev_out;
+    } else {
+        SMJ_TRY(smj_alloc_out(c, out, j, c_out));
+        if (j) CUDA_TRY(cudaMemcpyAsync(out->data, dev_out.data, (size_t)j * c_out * 4, cudaMemcpyDeviceToHost, c->stream));
+        smj_table_free(&dev_out);
+    }
+    CUDA_TRY(cudaEventRecord(c->ev[E_D2H], c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (cfg->debug) {
+        printf("==================\n#     join.cu    #\n==================\n");
+        printf("Rows: %lld\nCOL NUM 1: %d / COL NUM 2: %d\n", (long long)j, cc[0], cc[1]);
+        printf("GPU %d results: %lld rows\n####################\n\n", c->device, (long long)j);
+    }
+
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->h2d_ms = ev_ms(c->ev[E_START], c->ev[E_H2D]);
+        stats->select_ms = ev_ms(c->ev[E_H2D], c->ev[E_SELECT]);
+        stats->sort_ms = ev_ms(c->ev[E_SELECT], c->ev[E_SORT]);
+        stats->join_ms = ev_ms(c->ev[E_SORT], c->ev[E_JOIN]);
+        stats->d2h_ms = ev_ms(c->ev[E_JOIN], c->ev[E_D2H]);
+        stats->total_device_ms = ev_ms(c->ev[E_H2D], c->ev[E_JOIN]);
+        for (int t = 0; t < 2; t++) { stats->rows_in[t] = n[t]; stats->rows_selected[t] = m[t]; }
+        stats->rows_joined = j;
+        stats->bytes_model = bytes_model(n, cc, m, j);
+        stats->kernel_launches = c->launches - launches0;
+        double sum = 0;
+        for (int p = 0; p < c->pass_count; p++) sum += ev_ms(c->pass_ev[2 * p], c->pass_ev[2 * p + 1]);
+        stats->sort_passes = c->pass_count;
+        stats->sort_pass_ms_avg = c->pass_count ? sum / c->pass_count : 0;
+    }
+    return SMJ_OK;
+}
+
+int smj_run_multi(const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, smj_table_t *out, smj_stats_t *stats);
+bool smj_dist_active(void);
+
+extern "C" int smj_run(const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, smj_table_t *out,
+                       smj_stats_t *stats)
+{
+    smj_config_t local;
+    if (!cfg) { smj_config_default(&local); cfg = &local; }
+    if (!g_inited || (cfg->nr_gpus > g_nctx && !smj_dist_active())) SMJ_TRY(smj_init(cfg));
+    SMJ_TRY(check_table(t1, "smj_run(t1)"));
+    SMJ_TRY(check_table(t2, "smj_run(t2)"));
+    if (!out) return smj_set_error(SMJ_EINVAL, "smj_run: null out");
+    if (smj_dist_active() || cfg->nr_gpus > 1) return smj_run_multi(cfg, t1, t2, out, stats);
+    return smj_run_single(g_ctx[0], cfg, t1, t2, out, stats);
+}

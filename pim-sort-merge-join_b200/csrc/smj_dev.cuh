@@ -1,0 +1,144 @@
+// smj_dev.cuh -- device-side primitives shared by the kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+#define FULL_MASK 0xffffffffu
+// Bounded spin for every decoupled look-back: a bug must surface as SMJ_EINTERNAL, never as a hung GPU.
+#define SMJ_SPIN_LIMIT (1u << 24)
+#define SMJ_ERR_SPIN_SELECT 1u
+#define SMJ_ERR_SPIN_RADIX  2u
+#define SMJ_ERR_SPIN_JOIN   3u
+
+__device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ u32 lanemask_lt()
+{
+    u32 m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// Look-back status words carry flag and value in ONE word, so relaxed gpu-scope accesses are sufficient:
+// a reader either sees the old word (flag 0) or the complete new one.
+__device__ __forceinline__ u32 ld_relaxed(const u32 *p)
+{
+    u32 v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(u32 *p, u32 v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ u64 ld_relaxed(const u64 *p)
+{
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(u64 *p, u64 v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ u32 warp_incl_scan(u32 v)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(FULL_MASK, v, o);
+        if (lane_id() >= (u32)o) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ u64 warp_sum(u64 v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+
+// (flipped key << 32) | rowid.  Flipping the sign bit makes signed int32 order == unsigned order.
+__device__ __forceinline__ u64 make_pair(int32_t key, u32 rowid) { return ((u64)((u32)key ^ 0x80000000u) << 32) | rowid; }
+__device__ __forceinline__ u32 pair_key(u64 p) { return (u32)(p >> 32); }
+__device__ __forceinline__ u32 pair_row(u64 p) { return (u32)p; }
+
+// ---- searches over key-sorted pair arrays (global or shared memory)
+// Elements taken from A among the first `diag` of merge(A,B), A first on equal keys.
+__device__ __forceinline__ u32 merge_path(const u64 *A, u32 na, const u64 *B, u32 nb, u32 diag)
+{
+    u32 lo = diag > nb ? diag - nb : 0u, hi = diag < na ? diag : na;
+    while (lo < hi) {
+        const u32 mid = (lo + hi) >> 1;
+        if (pair_key(A[mid]) <= pair_key(B[diag - 1 - mid])) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ u32 lower_bound_key(const u64 *A, u32 lo, u32 hi, u32 k)
+{
+    while (lo < hi) {
+        const u32 mid = (lo + hi) >> 1;
+        if (pair_key(A[mid]) < k) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ u32 upper_bound_key(const u64 *A, u32 lo, u32 hi, u32 k)
+{
+    while (lo < hi) {
+        const u32 mid = (lo + hi) >> 1;
+        if (pair_key(A[mid]) <= k) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+
+// ---- 64-bit tile status for scans with one value per tile (select, join): flag in the top 2 bits.
+#define ST64_EMPTY 0ull
+#define ST64_LOCAL (1ull << 62)
+#define ST64_INCL  (2ull << 62)
+#define ST64_VAL(x) ((x) & ((1ull << 62) - 1))
+#define ST64_FLAG(x) ((x) >> 62)
+
+// Warp-parallel decoupled look-back (one warp of the CTA calls this; all 32 lanes).
+// Publishes this tile's aggregate, returns the exclusive prefix of all earlier tiles and publishes the
+// inclusive prefix.  status[] must have been zeroed.  Tiles are numbered by an atomic ticket so every
+// predecessor is already resident or finished (forward progress without relying on block scheduling order).
+__device__ __forceinline__ u64 lookback_warp(u64 *status, u32 tile, u64 aggregate, u32 *err, u32 err_code)
+{
+    const u32 lane = lane_id();
+    if (tile == 0) {
+        if (lane == 0) st_relaxed(&status[0], ST64_INCL | aggregate);
+        return 0;
+    }
+    if (lane == 0) st_relaxed(&status[tile], ST64_LOCAL | aggregate);
+    u64 excl = 0;
+    int look = (int)tile - 1;
+    u32 spins = 0;
+    bool bail = false;
+    while (!bail) {
+        int idx = look - (int)lane;
+        u64 st = (idx >= 0) ? ld_relaxed(&status[idx]) : ST64_INCL;
+        while (__any_sync(FULL_MASK, ST64_FLAG(st) == 0)) {
+            if (ST64_FLAG(st) == 0) st = ld_relaxed(&status[idx]);
+            if (++spins > SMJ_SPIN_LIMIT) {   // warp-uniform: every lane counts the same iterations
+                if (lane == 0) atomicExch(err, err_code);
+                bail = true;                   // still publish below so successors do not cascade the wait
+                break;
+            }
+        }
+        if (bail) break;
+        u32 incl_mask = __ballot_sync(FULL_MASK, ST64_FLAG(st) == 2);
+        int first = incl_mask ? (__ffs(incl_mask) - 1) : 31;
+        u64 v = ((int)lane <= first) ? ST64_VAL(st) : 0ull;
+        excl += warp_sum(v);
+        if (incl_mask) break;
+        look -= 32;
+    }
+    if (lane == 0) st_relaxed(&status[tile], ST64_INCL | (excl + aggregate));
+    return excl;
+}

@@ -1,0 +1,109 @@
+// smj_internal.h -- host-side internals shared by the .cu translation units of libsmj.so.
+// Nothing here crosses the C-ABI (include/smj.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/smj.h"
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+#define SMJ_RADIX_BITS 8
+#define SMJ_RADIX 256
+#define SMJ_KEY_PASSES 4            // 32-bit keys, 8-bit digits
+#define SMJ_MAX_SORT_ROWS ((1u << 30) - 1) // look-back status words keep 30-bit counts
+
+// One per GPU driven by this process.
+struct SmjCtx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    u32 *d_err = nullptr;            // device-side consistency flag (bounded spins, bad partitions)
+    void *h_pinned = nullptr;        // small pinned mailbox for counts / histograms
+    size_t h_pinned_bytes = 0;
+    int64_t launches = 0;
+    // grow-only workspace slots (no cudaMalloc in steady state)
+    static const int kSlots = 24;
+    void *slot[kSlots] = {};
+    size_t slot_bytes[kSlots] = {};
+    cudaEvent_t ev[16] = {};
+    // per-run accounting of the dominant kernel (radix scatter pass): events bracket every pass launch
+    static const int kMaxTimedPasses = 16;
+    cudaEvent_t pass_ev[2 * kMaxTimedPasses] = {};
+    u32 pass_items[kMaxTimedPasses] = {};
+    int pass_count = 0;
+    bool radix_attr_set = false;
+};
+
+enum SmjSlot {
+    WS_T1 = 0, WS_T2,                // device copies of host input tables
+    WS_PAIRS_A1, WS_PAIRS_B1,        // ping-pong (key,rowid) buffers, table 1
+    WS_PAIRS_A2, WS_PAIRS_B2,        // table 2
+    WS_SCRATCH,                      // zeroed per run: tile status words, tile counters, histograms, counts
+    WS_PART,                         // merge-path partitions + run starts
+    WS_MATCH,                        // matched (left rowid, right rowid)
+    WS_TMP_ROWS, WS_TMP_ROWS2,       // staging for in-place sort / host outputs
+    WS_XCHG_SEND1, WS_XCHG_SEND2, WS_XCHG_RECV1, WS_XCHG_RECV2, WS_SAMPLES,
+    WS_MERGE_A, WS_MERGE_B, WS_RADIX,
+};
+
+int   smj_set_error(int code, const char *fmt, ...);
+int   smj_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+void *smj_ws(SmjCtx *c, int slot, size_t bytes);     // nullptr on failure (error already set)
+
+#define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return smj_cuda_fail(e_, #x, __FILE__, __LINE__); } while (0)
+#define SMJ_TRY(x)  do { int r_ = (x); if (r_ != SMJ_OK) return r_; } while (0)
+#define KERNEL_CHECK(c) do { (c)->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return smj_cuda_fail(e_, "kernel launch", __FILE__, __LINE__); } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------ select (smj_select.cu)
+// Scratch layout helpers: all tile-status arrays must be zero before the launch.
+size_t smj_select_num_tiles(int64_t n);
+// Evaluates `cell[sel_col] > sel_val` (or everything when select_all) over n rows of a row-major table,
+// writes order-preserving (flipped key << 32 | rowid_base + row) pairs, the selected count, and (optionally)
+// the 4 x 256 digit histogram of the flipped keys.
+int smj_launch_select_pairs(SmjCtx *c, const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val,
+                            int select_all, int key_col, u32 rowid_base, u64 *d_pairs,
+                            u64 *d_status /*[tiles], zero*/, u32 *d_tile_counter /*zero*/,
+                            u32 *d_hist /*[4*256] zero, may be null*/, u64 *d_count /*out*/);
+
+// ------------------------------------------------------------------ radix sort (smj_radix.cu)
+size_t smj_radix_num_tiles(u32 n);
+size_t smj_radix_status_words(u32 n);          // per pass
+int smj_launch_radix_hist(SmjCtx *c, const u64 *d_pairs, u32 n, u32 *d_hist /*[4*256], zero*/);
+int smj_launch_radix_scan(SmjCtx *c, const u32 *d_hist, u32 *d_bases /*[4*256]*/);
+int smj_launch_radix_pass(SmjCtx *c, const u64 *d_in, u64 *d_out, u32 n, int pass, const u32 *d_bases_pass,
+                          u32 *d_status /*zero*/, u32 *d_tile_counter /*zero*/);
+// Full LSD sort of n pairs by their high 32 bits (stable). Result pointer in *d_sorted (either buf_a or buf_b).
+// h_hist: host copy of the 4x256 histogram (to skip trivial passes); d_hist on device.
+int smj_radix_sort_pairs(SmjCtx *c, u64 *buf_a, u64 *buf_b, u32 n, const u32 *d_hist, const u32 *h_hist,
+                         u32 *d_scratch /*smj_radix_scratch_bytes(n), zero*/, u64 **d_sorted);
+size_t smj_radix_scratch_bytes(u32 n);         // bases + status(4 passes) + counters, all zero-initialised by caller
+
+// ------------------------------------------------------------------ gather (smj_gather.cu)
+// out[i][:] = in[lo32(pairs[i])][:]
+int smj_launch_gather_rows(SmjCtx *c, const u64 *d_pairs, int64_t m, const int32_t *d_in, int cols, int32_t *d_out);
+// two-source variant for smj_merge: rowid < split -> a[rowid], else b[rowid - split]
+int smj_launch_gather_rows2(SmjCtx *c, const u64 *d_pairs, int64_t m, const int32_t *d_a, const int32_t *d_b,
+                            u32 split, int cols, int32_t *d_out);
+
+// ------------------------------------------------------------------ merge (smj_merge.cu)
+size_t smj_merge_num_tiles(u64 total);
+// merge two key-sorted pair arrays, a before b on equal keys
+int smj_launch_merge_pairs(SmjCtx *c, const u64 *d_a, u32 na, const u64 *d_b, u32 nb, u64 *d_out, u32 *d_part);
+
+// ------------------------------------------------------------------ join (smj_join.cu)
+size_t smj_join_num_tiles(u64 total);
+// zip mode: matches[i] = (left rowid, right rowid) in (key, left position) order; *d_count = number of matches.
+// many mode with d_matches == nullptr: *d_count = sum over left rows of the right run length (count only).
+int smj_launch_join_match(SmjCtx *c, const u64 *d_l, u32 m1, const u64 *d_r, u32 m2, int mode,
+                          u32 *d_part /*[2*(tiles+1)]*/, u64 *d_status /*[tiles] zero*/, u32 *d_tile_counter /*zero*/,
+                          uint2 *d_matches, u64 *d_count);
+int smj_launch_join_materialize(SmjCtx *c, const uint2 *d_matches, int64_t j, const int32_t *d_t1, int c1,
+                                const int32_t *d_t2, int c2, int key2, int32_t *d_out);
+
+// ------------------------------------------------------------------ synth (smj_synth.cu)
+int smj_launch_synth(SmjCtx *c, int32_t *d_out, int64_t row0, int64_t rows, int64_t total_rows, int cols,
+                     int key_col, u64 seed, int kind, int64_t key_domain);

@@ -1,0 +1,256 @@
+"""GPU parity tests proper: every C-ABI entry point of libsmj.so against the CPU oracle (oracle/, pinned to the
+reference's cpu_app.c by tests/test_oracle.py) on the same seeded inputs.  Bit-exact: integer data."""
+import hashlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+I32MIN, I32MAX = -2147483648, 2147483647
+
+
+@pytest.fixture(scope="module")
+def smj():
+    import smj_b200
+    if smj_b200.lib().smj_device_count() < 1:
+        pytest.fail("no CUDA device: the gpu-marked tests must run on a B200 (no CPU fallback exists)")
+    return smj_b200
+
+
+def rand_table(rng, n, c, lo=-50, hi=1000):
+    return rng.integers(lo, hi, size=(n, c)).astype(np.int32)
+
+
+def assert_same(got, want, what):
+    assert got.shape == want.shape, f"{what}: shape {got.shape} != {want.shape}"
+    if not np.array_equal(got, want):
+        bad = np.nonzero((got != want).any(axis=1))[0]
+        raise AssertionError(f"{what}: {len(bad)} of {len(want)} rows differ; first at {bad[0]}: got {got[bad[0]]} want {want[bad[0]]}")
+
+
+# ------------------------------------------------------------------ synthetic generator
+@pytest.mark.parametrize("rows,cols,kind,dom,row0,total", [
+    (1000, 4, 0, 0, 0, None), (5000, 5, 0, 0, 12345, 100000), (4096, 8, 1, 97, 0, None), (1, 1, 0, 0, 0, None),
+    (3000, 4, 0, 2147483646, 7, 2_000_000_000),
+])
+def test_synth_matches_numpy_twin(smj, rows, cols, kind, dom, row0, total):
+    t = smj.synth_device_table(rows, cols, seed=3, kind=kind, key_domain=dom, row0=row0, total_rows=total)
+    got = smj.smj.to_numpy(t)
+    smj.free(t)
+    want = smj.datagen.table(rows, cols, 3, kind=kind, key_domain=dom, row0=row0, total_rows=total)
+    assert_same(got, want, "synth")
+    if kind == 0 and row0 == 0 and total is None:
+        assert len(np.unique(got[:, 0])) == rows
+
+
+# ------------------------------------------------------------------ select
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 2047, 2048, 2049, 100_003])
+@pytest.mark.parametrize("cols", [1, 4, 5])
+def test_select_sizes(smj, port, n, cols):
+    rng = np.random.default_rng(n * 7 + cols)
+    t = rand_table(rng, n, cols)
+    col = int(rng.integers(0, cols))
+    assert_same(smj.select(t, col, 300), port.select(t, col, 300), f"select n={n} c={cols}")
+
+
+@pytest.mark.parametrize("val", [I32MIN - 5, I32MIN, -1, 0, 999, I32MAX - 1, I32MAX, I32MAX + 5])
+def test_select_threshold_edges(smj, port, val):
+    rng = np.random.default_rng(1)
+    t = rand_table(rng, 5000, 3)
+    t[::97, 1] = I32MAX
+    t[::89, 1] = I32MIN
+    assert_same(smj.select(t, 1, val), port.select(t, 1, val), f"select val={val}")
+
+
+def test_select_selectivity_extremes_and_device_io(smj, port):
+    rng = np.random.default_rng(2)
+    t = rand_table(rng, 300_000, 8, 0, 1_000_000)
+    for val in (-1, 500_000, 900_000, 2_000_000):
+        assert_same(smj.select(t, 2, val), port.select(t, 2, val), f"select val={val}")
+    d = smj.device_table(t)
+    assert_same(smj.select(d, 2, 500_000, on_device=True), port.select(t, 2, 500_000), "select device->device")
+    smj.free(d)
+
+
+# ------------------------------------------------------------------ sort
+@pytest.mark.parametrize("n", [0, 1, 2, 33, 4095, 4096, 4097, 50_000, 1_000_003])
+def test_sort_sizes(smj, port, n):
+    rng = np.random.default_rng(n)
+    t = np.column_stack([rng.integers(-10**9, 10**9, n), np.arange(n)]).astype(np.int32)
+    assert_same(smj.sort(t, 0), port.sort(t, 0), f"sort n={n}")
+
+
+@pytest.mark.parametrize("cols,key", [(1, 0), (3, 2), (4, 1), (5, 4), (8, 3)])
+def test_sort_is_stable_with_heavy_duplicates(smj, port, cols, key):
+    rng = np.random.default_rng(cols * 10 + key)
+    t = rand_table(rng, 200_000, cols, -20, 20)
+    assert_same(smj.sort(t, key), port.sort(t, key), f"sort dup c={cols} k={key}")
+
+
+def test_sort_extreme_and_constant_keys(smj, port):
+    rng = np.random.default_rng(4)
+    t = rand_table(rng, 70_000, 2, I32MIN, I32MAX)
+    t[::13, 0] = I32MIN
+    t[::17, 0] = I32MAX
+    t[::19, 0] = 0
+    t[::23, 0] = -1
+    assert_same(smj.sort(t, 0), port.sort(t, 0), "sort extremes")
+    c = np.column_stack([np.full(30_000, 7), np.arange(30_000)]).astype(np.int32)   # every radix pass is trivial
+    assert_same(smj.sort(c, 0), c, "sort constant keys")
+    small = np.column_stack([rng.integers(0, 256, 30_000), np.arange(30_000)]).astype(np.int32)   # one live digit
+    assert_same(smj.sort(small, 0), port.sort(small, 0), "sort one-digit keys")
+
+
+def test_sort_device_table_in_place(smj, port):
+    rng = np.random.default_rng(5)
+    t = rand_table(rng, 123_457, 4, 0, 10**6)
+    d = smj.device_table(t)
+    smj.sort(d, 0)
+    assert_same(smj.smj.to_numpy(d), port.sort(t, 0), "sort device in place")
+    smj.free(d)
+
+
+# ------------------------------------------------------------------ merge
+@pytest.mark.parametrize("n1,n2", [(0, 0), (0, 9), (9, 0), (1, 1), (2048, 2048), (2049, 100), (100_000, 37), (150_000, 250_001)])
+def test_merge(smj, port, n1, n2):
+    rng = np.random.default_rng(n1 + 3 * n2)
+    a = port.sort(rand_table(rng, n1, 3, -30, 30 if n1 < 1000 else 5000), 1)
+    b = port.sort(rand_table(rng, n2, 3, -30, 30 if n2 < 1000 else 5000), 1)
+    assert_same(smj.merge(a, b, 1), port.merge(a, b, 1), f"merge {n1}+{n2}")
+
+
+def test_merge_disjoint_and_equal_runs(smj, port):
+    a = np.column_stack([np.arange(0, 50_000), np.zeros(50_000)]).astype(np.int32)
+    b = np.column_stack([np.arange(50_000, 90_000), np.ones(40_000)]).astype(np.int32)
+    assert_same(smj.merge(a, b, 0), port.merge(a, b, 0), "merge disjoint a<b")
+    assert_same(smj.merge(b, a, 0), port.merge(b, a, 0), "merge disjoint b<a")
+    e1 = np.column_stack([np.full(10_000, 5), np.arange(10_000)]).astype(np.int32)
+    e2 = np.column_stack([np.full(7_000, 5), -np.arange(7_000)]).astype(np.int32)
+    assert_same(smj.merge(e1, e2, 0), port.merge(e1, e2, 0), "merge all-equal (a before b)")
+
+
+# ------------------------------------------------------------------ join
+def sorted_pair(port, rng, n1, n2, c1, c2, k1, k2, lo, hi):
+    return port.sort(rand_table(rng, n1, c1, lo, hi), k1), port.sort(rand_table(rng, n2, c2, lo, hi), k2)
+
+
+@pytest.mark.parametrize("n1,n2,hi", [
+    (0, 0, 10), (0, 50, 10), (50, 0, 10), (1, 1, 2), (1000, 1000, 3000), (5000, 3000, 40),
+    (100_000, 100_000, 300_000), (100_000, 100_000, 500), (30_000, 200_000, 7), (200_000, 30_000, 7),
+])
+def test_join_zip(smj, port, n1, n2, hi):
+    rng = np.random.default_rng(n1 * 3 + n2 + hi)
+    l, r = sorted_pair(port, rng, n1, n2, 3, 4, 1, 2, -5, hi)
+    assert_same(smj.join(l, r, 1, 2), port.join(l, r, 1, 2), f"join {n1}x{n2} hi={hi}")
+    assert smj.join_count(l, r, 1, 2) == port.join(l, r, 1, 2).shape[0]
+
+
+def test_join_giant_runs_across_tiles(smj, port):
+    """One key repeated far beyond a tile on both sides (zip pairs i-th with i-th), plus neighbours."""
+    rng = np.random.default_rng(9)
+    def mk(n_big, n_other, c):
+        k = np.concatenate([np.full(n_big, 1000), rng.integers(0, 2000, n_other)])
+        return port.sort(np.column_stack([k] + [rng.integers(0, 10**6, len(k)) for _ in range(c - 1)]).astype(np.int32), 0)
+    for nb1, nb2 in [(20_000, 9_000), (9_000, 20_000), (5_000, 5_000)]:
+        l, r = mk(nb1, 7_000, 2), mk(nb2, 11_000, 3)
+        assert_same(smj.join(l, r, 0, 0), port.join(l, r, 0, 0), f"join giant {nb1}/{nb2}")
+
+
+@pytest.mark.parametrize("c1,c2,k1,k2", [(1, 1, 0, 0), (2, 5, 1, 0), (4, 4, 0, 3), (8, 8, 5, 2), (5, 5, 0, 0)])
+def test_join_column_layouts(smj, port, c1, c2, k1, k2):
+    rng = np.random.default_rng(c1 * 100 + c2 * 10 + k1 + k2)
+    l, r = sorted_pair(port, rng, 20_000, 20_000, c1, c2, k1, k2, 0, 30_000)
+    assert_same(smj.join(l, r, k1, k2), port.join(l, r, k1, k2), f"join layout {c1},{c2},{k1},{k2}")
+
+
+def test_join_many_count(smj, port):
+    rng = np.random.default_rng(12)
+    for n1, n2, hi in [(5000, 4000, 50), (100_000, 80_000, 100_000), (60_000, 60_000, 5)]:
+        l, r = sorted_pair(port, rng, n1, n2, 2, 2, 0, 0, 0, hi)
+        want = port.lib.oracle_join_many(l, n1, 2, r, n2, 2, 0, 0, None, 0)
+        assert smj.join_count(l, r, 0, 0, mode=smj.JOIN_MANY) == want
+
+
+# ------------------------------------------------------------------ whole pipeline
+@pytest.mark.parametrize("case", ["g1", "g2", "kat2", "kat3", "kat4"])
+def test_run_golden(smj, port, golden, golden_csv, case, tmp_path):
+    g = golden["cases"][case]
+    t1 = port.load_csv(golden_csv(f"{case}_data1.csv"))
+    t2 = port.load_csv(golden_csv(f"{case}_data2.csv"))
+    out, st = smj.run(t1, t2, **{{"sel_col1": "select_col1", "sel_val1": "select_val1", "sel_col2": "select_col2",
+                                  "sel_val2": "select_val2", "key1": "join_key1", "key2": "join_key2"}[k]: v
+                                 for k, v in g["knobs"].items()})
+    assert st["rows_selected"] == g["selected"] and st["rows_joined"] == g["joined"]
+    p = str(tmp_path / "out.csv")
+    port.save_csv(p, out)
+    assert hashlib.sha256(open(p, "rb").read()).hexdigest() == g["sha256"]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_run_random_knobs(smj, port, seed):
+    rng = np.random.default_rng(100 + seed)
+    c1, c2 = int(rng.integers(1, 9)), int(rng.integers(1, 9))
+    n1, n2 = int(rng.integers(0, 60_000)), int(rng.integers(0, 60_000))
+    hi = [40, 5000, 10**6][seed % 3]
+    t1, t2 = rand_table(rng, n1, c1, -hi, hi), rand_table(rng, n2, c2, -hi, hi)
+    kn = dict(select_col1=int(rng.integers(0, c1)), select_val1=int(rng.integers(-hi, hi // 2)),
+              select_col2=int(rng.integers(0, c2)), select_val2=int(rng.integers(-hi, hi // 2)),
+              join_key1=int(rng.integers(0, c1)), join_key2=int(rng.integers(0, c2)))
+    want, sel, _ = port.run(t1, t2, kn["select_col1"], kn["select_val1"], kn["select_col2"], kn["select_val2"],
+                            kn["join_key1"], kn["join_key2"])
+    got, st = smj.run(t1, t2, **kn)
+    assert st["rows_selected"] == list(sel)
+    assert_same(got, want, f"run seed={seed} knobs={kn}")
+
+
+def test_run_zipf_heavy_duplicates(smj, port):
+    """BASELINE config 3 at test size: Zipf(1.1) keys on both sides, zip semantics."""
+    t1 = smj.datagen.zipf_table(300_000, 4, 7)
+    t2 = smj.datagen.zipf_table(200_000, 4, 8)
+    want, sel, _ = port.run(t1, t2)
+    got, st = smj.run(t1, t2)
+    assert st["rows_selected"] == list(sel)
+    assert_same(got, want, "run zipf")
+
+
+def test_run_device_resident_and_repeatable(smj, port):
+    t1, t2 = smj.datagen.table(400_000, 4, 1), smj.datagen.table(400_000, 4, 2)
+    want, sel, _ = port.run(t1, t2, 0, 600_000, 0, 600_000, 0, 0)
+    d1, d2 = smj.device_table(t1), smj.device_table(t2)
+    for _ in range(3):   # workspace reuse must not leak state between runs
+        got, st = smj.run(d1, d2, on_device=True, select_val1=600_000, select_val2=600_000)
+        assert_same(got, want, "run device resident")
+        assert st["kernel_launches"] > 0 and st["total_device_ms"] > 0
+    smj.free(d1)
+    smj.free(d2)
+
+
+def test_run_config2_full_size(smj, port):
+    """BASELINE config 2 at full size: 10M x 10M rows, 4 int32 cols, unique keys, 50% selectivity."""
+    n = 10_000_000
+    d1, d2 = smj.synth_device_table(n, 4, 1), smj.synth_device_table(n, 4, 2)
+    out, st = smj.run(d1, d2, on_device=True, select_val1=3 * n // 2, select_val2=3 * n // 2)
+    smj.free(d1)
+    smj.free(d2)
+    # size-independent properties
+    assert out.shape[1] == 7 and out.shape[0] == st["rows_joined"]
+    k = out[:, 0].astype(np.int64)
+    assert (np.diff(k) > 0).all(), "unique keys: result strictly ascending by key"
+    assert k.min() > 3 * n // 2
+    # and the full oracle (the C port finishes this in seconds)
+    t1, t2 = smj.datagen.table(n, 4, 1), smj.datagen.table(n, 4, 2)
+    want, sel, _ = port.run(t1, t2, 0, 3 * n // 2, 0, 3 * n // 2, 0, 0)
+    assert st["rows_selected"] == list(sel)
+    assert_same(out, want, "config 2 full size")
+
+
+def test_errors_are_codes_not_exits(smj):
+    t = np.zeros((10, 3), np.int32)
+    with pytest.raises(smj.SmjError) as e:
+        smj.select(t, 3, 0)
+    assert e.value.code == -1
+    with pytest.raises(smj.SmjError):
+        smj.join(t, t, 0, 5)
+    with pytest.raises(smj.SmjError):
+        smj.run(t, t, select_col1=9)
