@@ -82,6 +82,10 @@ static int ctx_create(int device, SmjCtx **out)
     CUDA_TRY(cudaMallocHost(&c->h_pinned, c->h_pinned_bytes));
     for (auto &e : c->ev) CUDA_TRY(cudaEventCreate(&e));
     for (auto &e : c->pass_ev) CUDA_TRY(cudaEventCreate(&e));
+    // The payload gathers read one 16..32-byte row per random address: ask L2 to fetch single 32-byte sectors
+    // instead of 64/128-byte lines (a hint; ncu showed 3.4x DRAM read amplification on join_materialize without it).
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+    cudaGetLastError();
     // keep freed output buffers cached in the stream-ordered pool
     cudaMemPool_t pool;
     CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -350,7 +354,7 @@ struct ScratchHeader {
 static int pairs_of_table(SmjCtx *c, const int32_t *d_t, int64_t rows, int cols, int key_col, u32 rowid_base, u64 *d_pairs,
                           char *scratch_status, u32 *d_counter, u32 *d_hist, u64 *d_count)
 {
-    return smj_launch_select_pairs(c, d_t, rows, cols, key_col, 0, /*select_all=*/1, key_col, rowid_base, d_pairs,
+    return smj_launch_select_pairs(c, d_t, rows, cols, key_col, 0, /*select_all=*/1, key_col, rowid_base, d_pairs, nullptr,
                                    (u64 *)scratch_status, d_counter, d_hist, d_count);
 }
 
@@ -372,7 +376,8 @@ extern "C" int smj_select(const smj_table_t *in, int col, int64_t val, smj_table
     CUDA_TRY(cudaMemsetAsync(scr, 0, sbytes, c->stream));
     ScratchHeader *h = (ScratchHeader *)scr;
     WS_TRY(pairs, u64 *, c, WS_PAIRS_A1, (size_t)n * 8);
-    SMJ_TRY(smj_launch_select_pairs(c, d_in, n, in->cols, col, val, 0, col, 0, pairs, (u64 *)(scr + sizeof(ScratchHeader)),
+    WS_TRY(tmp_pairs, u64 *, c, WS_PAIRS_B1, (size_t)n * 8);
+    SMJ_TRY(smj_launch_select_pairs(c, d_in, n, in->cols, col, val, 0, col, 0, pairs, tmp_pairs, (u64 *)(scr + sizeof(ScratchHeader)),
                                     &h->counter[0], nullptr, &h->count[0]));
     u64 *hm = (u64 *)c->h_pinned;
     CUDA_TRY(cudaMemcpyAsync(hm, &h->count[0], 8, cudaMemcpyDeviceToHost, c->stream));
@@ -391,16 +396,13 @@ extern "C" int smj_select(const smj_table_t *in, int col, int64_t val, smj_table
 }
 
 // ------------------------------------------------------------------ smj_sort
-// Sorts the n pairs in `pairs` (ping buffer) using `pong`; d_hist must hold their digit histogram.
-static int sort_pairs_with_hist(SmjCtx *c, u64 *pairs, u64 *pong, u32 n, const u32 *d_hist, int scratch_slot, u64 **sorted)
+// Sorts the n pairs in `pairs` (ping buffer) using `pong`; d_hist must hold their digit histogram.  Result in `pairs`.
+static int sort_pairs_with_hist(SmjCtx *c, u64 *pairs, u64 *pong, u32 n, const u32 *d_hist, int scratch_slot)
 {
-    u32 *hh = (u32 *)c->h_pinned;
-    CUDA_TRY(cudaMemcpyAsync(hh, d_hist, SMJ_KEY_PASSES * SMJ_RADIX * 4, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
     const size_t rbytes = smj_radix_scratch_bytes(n);
     WS_TRY(rs, u32 *, c, scratch_slot, rbytes);
     CUDA_TRY(cudaMemsetAsync(rs, 0, rbytes, c->stream));
-    return smj_radix_sort_pairs(c, pairs, pong, n, d_hist, hh, rs, sorted);
+    return smj_radix_sort_pairs(c, pairs, pong, nullptr, n, d_hist, rs);
 }
 
 extern "C" int smj_sort(smj_table_t *inout, int key_col)
@@ -424,12 +426,11 @@ extern "C" int smj_sort(smj_table_t *inout, int key_col)
     WS_TRY(pong, u64 *, c, WS_PAIRS_B1, (size_t)n * 8);
     SMJ_TRY(pairs_of_table(c, d_in, n, inout->cols, key_col, 0, ping, scr + sizeof(ScratchHeader), &h->counter[0],
                            h->hist[0], &h->count[0]));
-    u64 *sorted;
     c->pass_count = 0;
-    SMJ_TRY(sort_pairs_with_hist(c, ping, pong, (u32)n, h->hist[0], WS_RADIX, &sorted));
+    SMJ_TRY(sort_pairs_with_hist(c, ping, pong, (u32)n, h->hist[0], WS_RADIX));
     const size_t bytes = (size_t)n * inout->cols * 4;
     WS_TRY(tmp, int32_t *, c, WS_TMP_ROWS, bytes);
-    SMJ_TRY(smj_launch_gather_rows(c, sorted, n, d_in, inout->cols, tmp));
+    SMJ_TRY(smj_launch_gather_rows(c, ping, n, d_in, inout->cols, tmp));
     CUDA_TRY(cudaMemcpyAsync(inout->data, tmp, bytes, inout->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                              c->stream));
     SMJ_TRY(smj_check_device_flag(c));
@@ -496,7 +497,7 @@ static int join_sorted_pairs(SmjCtx *c, const u64 *pl, u32 m1, const u64 *pr, u3
     uint2 *d_matches = nullptr;
     if (mode == SMJ_JOIN_ZIP) { WS_TRY(mm, uint2 *, c, WS_MATCH, (size_t)mmin * 8); d_matches = mm; }
     else if (!count_only) return smj_set_error(SMJ_EINVAL, "SMJ_JOIN_MANY materialisation is not available in this build; use smj_join_count");
-    SMJ_TRY(smj_launch_join_match(c, pl, m1, pr, m2, mode, d_part, d_status, d_ticket, d_matches, d_jcount));
+    SMJ_TRY(smj_launch_join_match(c, pl, pr, nullptr, m1, m2, mode, d_part, d_status, d_ticket, d_matches, d_jcount));
     u64 *hm = (u64 *)c->h_pinned;
     CUDA_TRY(cudaMemcpyAsync(hm, d_jcount, 8, cudaMemcpyDeviceToHost, c->stream));
     SMJ_TRY(smj_check_device_flag(c));
@@ -506,10 +507,10 @@ static int join_sorted_pairs(SmjCtx *c, const u64 *pl, u32 m1, const u64 *pr, u3
     const int c_out = c1 + c2 - 1;
     if (out->on_device) {
         SMJ_TRY(smj_alloc_out(c, out, j, c_out));
-        SMJ_TRY(smj_launch_join_materialize(c, d_matches, j, d_t1, c1, d_t2, c2, key2, out->data));
+        SMJ_TRY(smj_launch_join_materialize(c, d_matches, nullptr, j, d_t1, c1, d_t2, c2, key2, out->data));
     } else {
         WS_TRY(tmp, int32_t *, c, WS_TMP_ROWS, (size_t)j * c_out * 4);
-        SMJ_TRY(smj_launch_join_materialize(c, d_matches, j, d_t1, c1, d_t2, c2, key2, tmp));
+        SMJ_TRY(smj_launch_join_materialize(c, d_matches, nullptr, j, d_t1, c1, d_t2, c2, key2, tmp));
         SMJ_TRY(emit_out_from_device(c, out, tmp, j, c_out));
     }
     return SMJ_OK;
@@ -575,6 +576,9 @@ static float ev_ms(cudaEvent_t a, cudaEvent_t b)
     return ms;
 }
 
+// Device pipeline of one GPU, no host round trip between the stages: the survivor counts, the radix
+// histograms and the match count stay in device memory, every kernel sizes its work from them, and buffers are
+// sized by their host-known upper bounds (input rows).  The host waits once, at the end.
 int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, smj_table_t *out,
                    smj_stats_t *stats)
 {
@@ -586,6 +590,9 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
     for (int t = 0; t < 2; t++) {
         if (sel_col[t] < 0 || sel_col[t] >= tb[t]->cols) return smj_set_error(SMJ_EINVAL, "SELECT_COL%d=%d out of range", t + 1, sel_col[t]);
         if (key[t] < 0 || key[t] >= tb[t]->cols) return smj_set_error(SMJ_EINVAL, "JOIN_KEY%d=%d out of range", t + 1, key[t]);
+        if (tb[t]->rows > SMJ_MAX_SORT_ROWS)
+            return smj_set_error(SMJ_ETOOBIG, "table %d has %lld rows; this build handles at most 2^30 - 1 per table per GPU", t + 1,
+                                 (long long)tb[t]->rows);
     }
     if (cfg->join_mode != SMJ_JOIN_ZIP) return smj_set_error(SMJ_EINVAL, "smj_run materialises SMJ_JOIN_ZIP only (the reference semantics)");
     const int64_t launches0 = c->launches;
@@ -599,75 +606,61 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
     SMJ_TRY(smj_stage_in(c, t2, WS_T2, &d_t[1]));
     const int64_t n[2] = {t1->rows, t2->rows};
     const int cc[2] = {t1->cols, t2->cols};
-    const size_t tiles[2] = {smj_select_num_tiles(n[0]), smj_select_num_tiles(n[1])};
-    const size_t sbytes = sizeof(ScratchHeader) + (tiles[0] + tiles[1]) * 8;
+    const int c_out = cc[0] + cc[1] - 1;
+    // one zeroed arena: [header][select status x2][radix scratch x2][join header 64 B + join status]; then join partitions
+    const size_t stiles[2] = {smj_select_num_tiles(n[0]), smj_select_num_tiles(n[1])};
+    const size_t rb[2] = {align_up(smj_radix_scratch_bytes((u32)n[0]), 256), align_up(smj_radix_scratch_bytes((u32)n[1]), 256)};
+    const size_t jt = smj_join_num_tiles((u64)n[0] + n[1]);
+    const size_t off_sel = align_up(sizeof(ScratchHeader), 256);
+    const size_t off_radix = align_up(off_sel + (stiles[0] + stiles[1]) * 8, 256);
+    const size_t off_join = off_radix + rb[0] + rb[1];
+    const size_t zero_bytes = align_up(off_join + 64 + jt * 8, 256);
+    const size_t sbytes = zero_bytes + (jt + 1) * 2 * 4;
     WS_TRY(scr, char *, c, WS_SCRATCH, sbytes);
     WS_TRY(ping0, u64 *, c, WS_PAIRS_A1, (size_t)n[0] * 8);
     WS_TRY(ping1, u64 *, c, WS_PAIRS_A2, (size_t)n[1] * 8);
-    u64 *ping[2] = {ping0, ping1};
+    WS_TRY(pong0, u64 *, c, WS_PAIRS_B1, (size_t)n[0] * 8);
+    WS_TRY(pong1, u64 *, c, WS_PAIRS_B2, (size_t)n[1] * 8);
+    u64 *ping[2] = {ping0, ping1}, *pong[2] = {pong0, pong1};
+    const int64_t j_max = n[0] < n[1] ? n[0] : n[1];
+    WS_TRY(mm, uint2 *, c, WS_MATCH, (size_t)j_max * 8);
+    smj_table_t dev_out = {nullptr, 0, c_out, 1};
+    SMJ_TRY(smj_alloc_out(c, &dev_out, j_max, c_out));   // upper bound; rows is set once the count is known
     CUDA_TRY(cudaEventRecord(c->ev[E_H2D], c->stream));
 
-    // ---- select (+ digit histograms), both tables, then one host round trip for the survivor counts
-    CUDA_TRY(cudaMemsetAsync(scr, 0, sbytes, c->stream));
+    // ---- select (+ digit histograms), both tables
+    CUDA_TRY(cudaMemsetAsync(scr, 0, zero_bytes, c->stream));
     ScratchHeader *h = (ScratchHeader *)scr;
-    char *st = scr + sizeof(ScratchHeader);
     for (int t = 0; t < 2; t++)
-        SMJ_TRY(smj_launch_select_pairs(c, d_t[t], n[t], cc[t], sel_col[t], sel_val[t], 0, key[t], 0, ping[t],
-                                        (u64 *)(st + (t ? tiles[0] * 8 : 0)), &h->counter[t], h->hist[t], &h->count[t]));
+        SMJ_TRY(smj_launch_select_pairs(c, d_t[t], n[t], cc[t], sel_col[t], sel_val[t], 0, key[t], 0, ping[t], pong[t],
+                                        (u64 *)(scr + off_sel + (t ? stiles[0] * 8 : 0)), &h->counter[t], h->hist[t], &h->count[t]));
     CUDA_TRY(cudaEventRecord(c->ev[E_SELECT], c->stream));
-    ScratchHeader *hh = (ScratchHeader *)c->h_pinned;
-    CUDA_TRY(cudaMemcpyAsync(hh, h, sizeof(ScratchHeader), cudaMemcpyDeviceToHost, c->stream));
-    SMJ_TRY(smj_check_device_flag(c));
-    const int64_t m[2] = {(int64_t)hh->count[0], (int64_t)hh->count[1]};
-    if (m[0] > SMJ_MAX_SORT_ROWS || m[1] > SMJ_MAX_SORT_ROWS)
-        return smj_set_error(SMJ_ETOOBIG, "selected %lld / %lld rows; this build sorts at most 2^30 - 1 per table per GPU",
-                             (long long)m[0], (long long)m[1]);
-    if (cfg->debug) {   // app.c:294-305 prints one "select" line per DPU; one GPU here
-        printf("==================\n#    select.cu   #\n==================\n");
-        for (int t = 0; t < 2; t++) printf("Table %d : select %lld rows\n", t, (long long)m[t]);
-        printf("####################\n\n");
-    }
 
-    // ---- sort
-    u32 host_hist[2][SMJ_KEY_PASSES * SMJ_RADIX];
-    memcpy(host_hist, hh->hist, sizeof host_hist);
-    u64 *sorted[2];
-    WS_TRY(pong0, u64 *, c, WS_PAIRS_B1, (size_t)m[0] * 8);
-    WS_TRY(pong1, u64 *, c, WS_PAIRS_B2, (size_t)m[1] * 8);
-    u64 *pong[2] = {pong0, pong1};
-    const size_t rb[2] = {align_up(smj_radix_scratch_bytes((u32)m[0]), 256), align_up(smj_radix_scratch_bytes((u32)m[1]), 256)};
-    WS_TRY(rs, char *, c, WS_RADIX, rb[0] + rb[1]);
-    CUDA_TRY(cudaMemsetAsync(rs, 0, rb[0] + rb[1], c->stream));
+    // ---- sort: 4 onesweep passes per table over the device-resident survivor counts
     for (int t = 0; t < 2; t++)
-        SMJ_TRY(smj_radix_sort_pairs(c, ping[t], pong[t], (u32)m[t], h->hist[t], host_hist[t], (u32 *)(rs + (t ? rb[0] : 0)), &sorted[t]));
+        SMJ_TRY(smj_radix_sort_pairs(c, ping[t], pong[t], &h->count[t], (u32)n[t], h->hist[t], (u32 *)(scr + off_radix + (t ? rb[0] : 0))));
     CUDA_TRY(cudaEventRecord(c->ev[E_SORT], c->stream));
-    if (cfg->debug) {
-        printf("==================\n#     sort.cu    #\n==================\n");
-        for (int t = 0; t < 2; t++) printf("Table %d - GPU %d sort %lld rows\n", t, c->device, (long long)m[t]);
-        printf("####################\n\n");
-    }
 
     // ---- join: co-rank, count, scan, write matches; then materialise rows straight from the input tables
-    int64_t j = 0;
-    smj_table_t dev_out = {nullptr, 0, cc[0] + cc[1] - 1, 1};
-    const int c_out = cc[0] + cc[1] - 1;
     {
-        const size_t jt = smj_join_num_tiles((u64)m[0] + m[1]);
-        const size_t jbytes = 64 + jt * 8 + (jt + 1) * 2 * 4;
-        WS_TRY(js, char *, c, WS_PART, jbytes);
-        CUDA_TRY(cudaMemsetAsync(js, 0, 64 + jt * 8, c->stream));
-        const u32 mmin = (u32)(m[0] < m[1] ? m[0] : m[1]);
-        WS_TRY(mm, uint2 *, c, WS_MATCH, (size_t)mmin * 8);
-        SMJ_TRY(smj_launch_join_match(c, sorted[0], (u32)m[0], sorted[1], (u32)m[1], SMJ_JOIN_ZIP, (u32 *)(js + 64 + jt * 8),
-                                      (u64 *)(js + 64), (u32 *)(js + 16), mm, (u64 *)js));
-        u64 *hm = (u64 *)c->h_pinned;
-        CUDA_TRY(cudaMemcpyAsync(hm, js, 8, cudaMemcpyDeviceToHost, c->stream));
-        SMJ_TRY(smj_check_device_flag(c));
-        j = (int64_t)hm[0];
-        SMJ_TRY(smj_alloc_out(c, &dev_out, j, c_out));
-        SMJ_TRY(smj_launch_join_materialize(c, mm, j, d_t[0], cc[0], d_t[1], cc[1], key[1], dev_out.data));
+        char *js = scr + off_join;
+        SMJ_TRY(smj_launch_join_match(c, ping[0], ping[1], &h->count[0], (u32)n[0], (u32)n[1], SMJ_JOIN_ZIP, (u32 *)(scr + zero_bytes),
+                                      (u64 *)(js + 64), (u32 *)(js + 16), mm, &h->jcount));
+        SMJ_TRY(smj_launch_join_materialize(c, mm, &h->jcount, j_max, d_t[0], cc[0], d_t[1], cc[1], key[1], dev_out.data));
     }
     CUDA_TRY(cudaEventRecord(c->ev[E_JOIN], c->stream));
+
+    // ---- the one host wait: counts and the device-side consistency flag
+    ScratchHeader *hh = (ScratchHeader *)c->h_pinned;
+    CUDA_TRY(cudaMemcpyAsync(hh, h, sizeof(ScratchHeader), cudaMemcpyDeviceToHost, c->stream));
+    {
+        int r = smj_check_device_flag(c);
+        if (r != SMJ_OK) { smj_table_free(&dev_out); return r; }
+    }
+    const int64_t m[2] = {(int64_t)hh->count[0], (int64_t)hh->count[1]};
+    const int64_t j = (int64_t)hh->jcount;
+    dev_out.rows = j;
+    if (j == 0) smj_table_free(&dev_out), dev_out.data = nullptr;
 
     // ---- GPU -> CPU (app.c timer 2)
     if (out->on_device) {
@@ -675,12 +668,16 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
     } else {
         SMJ_TRY(smj_alloc_out(c, out, j, c_out));
         if (j) CUDA_TRY(cudaMemcpyAsync(out->data, dev_out.data, (size_t)j * c_out * 4, cudaMemcpyDeviceToHost, c->stream));
-        smj_table_free(&dev_out);
+        if (dev_out.data) smj_table_free(&dev_out);
     }
     CUDA_TRY(cudaEventRecord(c->ev[E_D2H], c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    if (cfg->debug) {
-        printf("==================\n#     join.cu    #\n==================\n");
+    if (cfg->debug) {   // app.c:294-305, 379-400, 694-717 print one line per DPU and stage; one GPU here
+        printf("==================\n#    select.cu   #\n==================\n");
+        for (int t = 0; t < 2; t++) printf("Table %d : select %lld rows\n", t, (long long)m[t]);
+        printf("####################\n\n==================\n#     sort.cu    #\n==================\n");
+        for (int t = 0; t < 2; t++) printf("Table %d - GPU %d sort %lld rows\n", t, c->device, (long long)m[t]);
+        printf("####################\n\n==================\n#     join.cu    #\n==================\n");
         printf("Rows: %lld\nCOL NUM 1: %d / COL NUM 2: %d\n", (long long)j, cc[0], cc[1]);
         printf("GPU %d results: %lld rows\n####################\n\n", c->device, (long long)j);
     }

@@ -34,6 +34,7 @@ struct SmjCtx {
     u32 pass_items[kMaxTimedPasses] = {};
     int pass_count = 0;
     bool radix_attr_set = false;
+    bool select_attr_set = false;
 };
 
 enum SmjSlot {
@@ -66,7 +67,8 @@ size_t smj_select_num_tiles(int64_t n);
 // the 4 x 256 digit histogram of the flipped keys.
 int smj_launch_select_pairs(SmjCtx *c, const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val,
                             int select_all, int key_col, u32 rowid_base, u64 *d_pairs,
-                            u64 *d_status /*[tiles], zero*/, u32 *d_tile_counter /*zero*/,
+                            u64 *d_tmp /*n pairs of scratch, or null: look-back kernel*/,
+                            u64 *d_status /*[smj_select_num_tiles(n)], zero*/, u32 *d_tile_counter /*zero*/,
                             u32 *d_hist /*[4*256] zero, may be null*/, u64 *d_count /*out*/);
 
 // ------------------------------------------------------------------ radix sort (smj_radix.cu)
@@ -74,12 +76,13 @@ size_t smj_radix_num_tiles(u32 n);
 size_t smj_radix_status_words(u32 n);          // per pass
 int smj_launch_radix_hist(SmjCtx *c, const u64 *d_pairs, u32 n, u32 *d_hist /*[4*256], zero*/);
 int smj_launch_radix_scan(SmjCtx *c, const u32 *d_hist, u32 *d_bases /*[4*256]*/);
-int smj_launch_radix_pass(SmjCtx *c, const u64 *d_in, u64 *d_out, u32 n, int pass, const u32 *d_bases_pass,
-                          u32 *d_status /*zero*/, u32 *d_tile_counter /*zero*/);
-// Full LSD sort of n pairs by their high 32 bits (stable). Result pointer in *d_sorted (either buf_a or buf_b).
-// h_hist: host copy of the 4x256 histogram (to skip trivial passes); d_hist on device.
-int smj_radix_sort_pairs(SmjCtx *c, u64 *buf_a, u64 *buf_b, u32 n, const u32 *d_hist, const u32 *h_hist,
-                         u32 *d_scratch /*smj_radix_scratch_bytes(n), zero*/, u64 **d_sorted);
+int smj_launch_radix_pass(SmjCtx *c, const u64 *d_in, u64 *d_out, const u64 *d_n /*device count or null*/, u32 n_max, int pass,
+                          const u32 *d_bases_pass, u32 *d_status /*zero*/, u32 *d_status_next /*zeroed for the next pass*/,
+                          u32 *d_tile_counter /*zero*/);
+// Stable LSD sort by the key half of the first *d_n (<= n_max; d_n null: exactly n_max) pairs of buf_a, result in
+// buf_a (four passes).  d_hist: the 4x256 digit histogram of those pairs (device).  No host synchronisation.
+int smj_radix_sort_pairs(SmjCtx *c, u64 *buf_a, u64 *buf_b, const u64 *d_n, u32 n_max, const u32 *d_hist,
+                         u32 *d_scratch /*smj_radix_scratch_bytes(n_max), zero*/);
 size_t smj_radix_scratch_bytes(u32 n);         // bases + status(4 passes) + counters, all zero-initialised by caller
 
 // ------------------------------------------------------------------ gather (smj_gather.cu)
@@ -98,11 +101,13 @@ int smj_launch_merge_pairs(SmjCtx *c, const u64 *d_a, u32 na, const u64 *d_b, u3
 size_t smj_join_num_tiles(u64 total);
 // zip mode: matches[i] = (left rowid, right rowid) in (key, left position) order; *d_count = number of matches.
 // many mode with d_matches == nullptr: *d_count = sum over left rows of the right run length (count only).
-int smj_launch_join_match(SmjCtx *c, const u64 *d_l, u32 m1, const u64 *d_r, u32 m2, int mode,
+// d_counts: device {m1, m2} (u64 each) or null, in which case m1_max / m2_max are the exact sizes.
+int smj_launch_join_match(SmjCtx *c, const u64 *d_l, const u64 *d_r, const u64 *d_counts, u32 m1_max, u32 m2_max, int mode,
                           u32 *d_part /*[2*(tiles+1)]*/, u64 *d_status /*[tiles] zero*/, u32 *d_tile_counter /*zero*/,
                           uint2 *d_matches, u64 *d_count);
-int smj_launch_join_materialize(SmjCtx *c, const uint2 *d_matches, int64_t j, const int32_t *d_t1, int c1,
-                                const int32_t *d_t2, int c2, int key2, int32_t *d_out);
+// d_nj: device match count or null (then nj_max is exact)
+int smj_launch_join_materialize(SmjCtx *c, const uint2 *d_matches, const u64 *d_nj, int64_t nj_max, const int32_t *d_t1,
+                                int c1, const int32_t *d_t2, int c2, int key2, int32_t *d_out);
 
 // ------------------------------------------------------------------ synth (smj_synth.cu)
 int smj_launch_synth(SmjCtx *c, int32_t *d_out, int64_t row0, int64_t rows, int64_t total_rows, int cols,

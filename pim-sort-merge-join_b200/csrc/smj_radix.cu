@@ -19,117 +19,169 @@ constexpr int RS_IPT = 16;
 constexpr int RS_TILE = RS_THREADS * RS_IPT;   // 4096 pairs = 32 KB
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr u32 RS_FLAG_LOCAL = 1u << 30, RS_FLAG_INCL = 2u << 30, RS_VAL_MASK = (1u << 30) - 1;
-static_assert(RS_THREADS >= SMJ_RADIX, "one thread per digit bin");
+static_assert(RS_THREADS == SMJ_RADIX, "one thread per digit bin");
+constexpr int RS_LB = 8;   // predecessors examined per look-back round
 
-constexpr size_t RS_SMEM = (size_t)RS_TILE * 8 + (size_t)RS_WARPS * SMJ_RADIX * 4 + 2 * SMJ_RADIX * 4 + 32 * 4;
+// shared memory: reordered tile | per-warp digit counters | two alternating per-warp peer-mask arrays | offsets
+constexpr size_t RS_SMEM = (size_t)RS_TILE * 8 + (size_t)RS_WARPS * SMJ_RADIX * 4 + 2 * (size_t)RS_WARPS * SMJ_RADIX * 4 +
+                           SMJ_RADIX * 4 + 32 * 4;
 
-__global__ void __launch_bounds__(RS_THREADS)
-radix_pass_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, u32 n, int shift,
-                  const u32 *__restrict__ bin_base, u32 *status, u32 *tile_counter, u32 *err)
+// Why not __match_any_sync: MATCH.ANY runs on the SM-wide ADU pipe at ~61 cycles per warp instruction on sm_100
+// (profiles/r01_ubench_primitives.txt) and made the first version of this kernel ADU-bound (54 % pipe utilisation,
+// 7 % DRAM).  A shared-memory atomicOr of the lane bit into a per-warp, per-digit mask word gives the same peer mask
+// at ~2.7 cycles per warp instruction.
+__global__ void __launch_bounds__(RS_THREADS, 3)
+radix_pass_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const u64 *__restrict__ n_dev, u32 n_max, int shift,
+                  const u32 *__restrict__ bin_base, u32 *status, u32 *status_next, u32 *tile_counter, u32 *err)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 *s_items = reinterpret_cast<u64 *>(smem_raw);              // RS_TILE, tile in locally sorted order
-    u32 *s_wcnt = reinterpret_cast<u32 *>(s_items + RS_TILE);      // [warp][256] counts -> exclusive over warps
-    u32 *s_lbase = s_wcnt + RS_WARPS * SMJ_RADIX;                  // [256] first local slot of each digit
-    u32 *s_goff = s_lbase + SMJ_RADIX;                             // [256] global slot of local slot 0 of the digit
+    u64 *s_items = reinterpret_cast<u64 *>(smem_raw);              // RS_TILE, tile in digit order
+    u32 *s_wcnt = reinterpret_cast<u32 *>(s_items + RS_TILE);      // [warp][256] counts -> running local slot
+    u32 *s_mask = s_wcnt + RS_WARPS * SMJ_RADIX;                   // [2][warp][256] peer masks (self-resetting)
+    u32 *s_goff = s_mask + 2 * RS_WARPS * SMJ_RADIX;               // [256] global slot minus local slot per digit
     u32 *s_wsum = s_goff + SMJ_RADIX;                              // warp totals of the bin scan
-    __shared__ u32 s_tile;
+    __shared__ u32 s_tile[2];
 
     const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
     const u32 lt = lanemask_lt();
-    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-    for (u32 i = tid; i < RS_WARPS * SMJ_RADIX; i += RS_THREADS) s_wcnt[i] = 0;
-    __syncthreads();
-    const u32 tile = s_tile;
-    const u32 base = tile * RS_TILE;
-    const u32 valid = (n - base < (u32)RS_TILE) ? (n - base) : (u32)RS_TILE;
+    u64 n64 = n_dev ? *n_dev : (u64)n_max;
+    const u32 n = n64 < (u64)n_max ? (u32)n64 : n_max;
+    const u32 num_tiles = (n + RS_TILE - 1) / RS_TILE;
 
-    // warp-striped load: element order inside the tile is (warp, j, lane) == ascending index
+    if (tid == 0) s_tile[0] = atomicAdd(tile_counter, 1u);
+    for (u32 i = tid; i < 2 * RS_WARPS * SMJ_RADIX; i += RS_THREADS) s_mask[i] = 0;
+    __syncthreads();
+    u32 tile = s_tile[0];
+    int par = 0;
+
+    // warp-striped layout: element order inside the tile is (warp, j, lane) == ascending index
     u64 item[RS_IPT];
-    const u32 wbase = base + w * 32 * RS_IPT + lane;
+    if (tile < num_tiles) {
+        const u32 wbase = tile * RS_TILE + w * 32 * RS_IPT + lane;
 #pragma unroll
-    for (int j = 0; j < RS_IPT; j++) {
-        const u32 idx = wbase + j * 32;
-        item[j] = (idx < n) ? in[idx] : ~0ull;   // padding sorts last (digit 255, after every real 255)
+        for (int j = 0; j < RS_IPT; j++) {
+            const u32 idx = wbase + j * 32;
+            item[j] = (idx < n) ? in[idx] : 0ull;
+        }
     }
 
-    u32 rank[RS_IPT];
     u32 *my_cnt = s_wcnt + w * SMJ_RADIX;
-#pragma unroll
-    for (int j = 0; j < RS_IPT; j++) {
-        const u32 d = (u32)(item[j] >> shift) & (SMJ_RADIX - 1);
-        const u32 peers = __match_any_sync(FULL_MASK, d);
-        const u32 leader = __ffs(peers) - 1;
-        u32 pre = 0;
-        if (lane == leader) {
-            pre = my_cnt[d];
-            my_cnt[d] = pre + __popc(peers);
-        }
-        pre = __shfl_sync(FULL_MASK, pre, leader);
-        rank[j] = pre + __popc(peers & lt);
-        __syncwarp();
-    }
-    __syncthreads();
+    while (tile < num_tiles) {
+        const u32 base = tile * RS_TILE;
+        const u32 valid = (n - base < (u32)RS_TILE) ? (n - base) : (u32)RS_TILE;
+        const u32 wvalid_base = w * 32 * RS_IPT + lane;   // tile-relative index of item[0]
 
-    // one thread per digit: totals over warps, publish, local scan, look-back
-    u32 cnt_pad = 0, cnt = 0;
-    if (tid < SMJ_RADIX) {
-        u32 sum = 0;
 #pragma unroll
-        for (int ww = 0; ww < RS_WARPS; ww++) {
-            const u32 t = s_wcnt[ww * SMJ_RADIX + tid];
-            s_wcnt[ww * SMJ_RADIX + tid] = sum;
-            sum += t;
-        }
-        cnt_pad = sum;
-        cnt = sum;
-        if (tid == SMJ_RADIX - 1) cnt -= (u32)RS_TILE - valid;   // do not count the padding
-        st_relaxed(&status[(size_t)tile * SMJ_RADIX + tid], (tile == 0 ? RS_FLAG_INCL : RS_FLAG_LOCAL) | cnt);
-    }
-    const u32 inc = warp_incl_scan(cnt_pad);
-    if (lane == 31) s_wsum[w] = inc;
-    __syncthreads();
-    if (tid < SMJ_RADIX) {
-        u32 wp = 0;
-        for (u32 ww = 0; ww < w; ww++) wp += s_wsum[ww];
-        const u32 excl_local = wp + inc - cnt_pad;
-        s_lbase[tid] = excl_local;
+        for (int i = 0; i < RS_WARPS; i++) s_wcnt[i * SMJ_RADIX + tid] = 0;
+        __syncthreads();
 
-        u32 excl = 0;
-        if (tile > 0) {
-            int t = (int)tile - 1;
-            u32 spins = 0;
-            while (true) {
-                const u32 v = ld_relaxed(&status[(size_t)t * SMJ_RADIX + tid]);
-                const u32 flag = v >> 30;
-                if (flag == 0) {
-                    if (++spins > SMJ_SPIN_LIMIT) { atomicExch(err, SMJ_ERR_SPIN_RADIX); break; }
-                    continue;
+        // ---- early counts: per-warp digit histogram
+#pragma unroll
+        for (int j = 0; j < RS_IPT; j++) {
+            const u32 d = (u32)(item[j] >> shift) & (SMJ_RADIX - 1);
+            if (wvalid_base + j * 32 < valid) atomicAdd(&my_cnt[d], 1u);
+        }
+        __syncthreads();
+
+        // ---- one thread per digit: totals over warps, publish the tile aggregate, scan digits
+        u32 cnt;
+        {
+            u32 c[RS_WARPS], sum = 0;
+#pragma unroll
+            for (int ww = 0; ww < RS_WARPS; ww++) { c[ww] = s_wcnt[ww * SMJ_RADIX + tid]; sum += c[ww]; }
+            cnt = sum;
+            st_relaxed(&status[(size_t)tile * SMJ_RADIX + tid], (tile == 0 ? RS_FLAG_INCL : RS_FLAG_LOCAL) | cnt);
+            status_next[(size_t)tile * SMJ_RADIX + tid] = 0;   // the next pass (next kernel) reuses the other array
+            const u32 inc = warp_incl_scan(cnt);
+            if (lane == 31) s_wsum[w] = inc;
+            __syncthreads();
+            u32 run = inc - cnt;     // exclusive over digits: first local slot of this digit
+            for (u32 ww = 0; ww < w; ww++) run += s_wsum[ww];
+            s_goff[tid] = run;       // local base, turned into (global - local) after the look-back
+#pragma unroll
+            for (int ww = 0; ww < RS_WARPS; ww++) { s_wcnt[ww * SMJ_RADIX + tid] = run; run += c[ww]; }
+        }
+        __syncthreads();
+
+        // ---- rank (stable: lanes in order, rows in order, warps in order) and reorder into shared memory
+#pragma unroll
+        for (int j = 0; j < RS_IPT; j++) {
+            const u32 d = (u32)(item[j] >> shift) & (SMJ_RADIX - 1);
+            const bool ok = wvalid_base + j * 32 < valid;
+            u32 *mk = s_mask + ((j & 1) * RS_WARPS + w) * SMJ_RADIX + d;
+            if (ok) atomicOr(mk, 1u << lane);
+            __syncwarp();
+            const u32 peers = *mk;
+            const u32 pre = my_cnt[d];
+            __syncwarp();
+            if (ok) {
+                if ((peers >> lane) == 1u) {   // highest peer lane: reset the mask, advance the running slot
+                    *mk = 0;
+                    my_cnt[d] = pre + __popc(peers);
                 }
-                excl += v & RS_VAL_MASK;
-                if (flag == 2 || t == 0) break;
-                t--;
+                s_items[pre + __popc(peers & lt)] = item[j];
             }
-            st_relaxed(&status[(size_t)tile * SMJ_RADIX + tid], RS_FLAG_INCL | ((excl + cnt) & RS_VAL_MASK));
         }
-        s_goff[tid] = bin_base[tid] + excl - excl_local;   // mod 2^32: added to a local slot >= excl_local
-    }
-    __syncthreads();
 
+        // ---- next ticket, then this tile's look-back (predecessors published before they started ranking)
+        if (tid == 0) s_tile[par ^ 1] = atomicAdd(tile_counter, 1u);
+        {
+            u32 excl = 0;
+            if (tile > 0) {
+                // Batched look-back: RS_LB predecessors per round trip.  When a whole wave of tiles starts together
+                // none of them has an inclusive prefix yet and tile k needs ~sqrt(2k / RS_LB) rounds, each an L2
+                // round trip; one predecessor per round (the first version) cost ~30 rounds for the last tiles.
+                int t = (int)tile - 1;
+                u32 spins = 0;
+                bool done = false;
+                while (!done) {
+                    u32 v[RS_LB];
 #pragma unroll
-    for (int j = 0; j < RS_IPT; j++) {
-        const u32 d = (u32)(item[j] >> shift) & (SMJ_RADIX - 1);
-        s_items[s_lbase[d] + my_cnt[d] + rank[j]] = item[j];
-    }
-    __syncthreads();
+                    for (int r = 0; r < RS_LB; r++)
+                        v[r] = (t - r >= 0) ? ld_relaxed(&status[(size_t)(t - r) * SMJ_RADIX + tid]) : RS_FLAG_INCL;
+                    int used = 0;
 #pragma unroll
-    for (int k = 0; k < RS_IPT; k++) {
-        const u32 idx = tid + k * RS_THREADS;
-        if (idx < valid) {
-            const u64 it = s_items[idx];
-            const u32 d = (u32)(it >> shift) & (SMJ_RADIX - 1);
-            out[s_goff[d] + idx] = it;
+                    for (int r = 0; r < RS_LB; r++) {
+                        if (!done && used == r) {
+                            const u32 flag = v[r] >> 30;
+                            if (flag != 0) {
+                                excl += v[r] & RS_VAL_MASK;
+                                used = r + 1;
+                                if (flag == 2) done = true;
+                            }
+                        }
+                    }
+                    t -= used;
+                    if (!done && used < RS_LB && ++spins > SMJ_SPIN_LIMIT) { atomicExch(err, SMJ_ERR_SPIN_RADIX); break; }
+                }
+                st_relaxed(&status[(size_t)tile * SMJ_RADIX + tid], RS_FLAG_INCL | ((excl + cnt) & RS_VAL_MASK));
+            }
+            s_goff[tid] = bin_base[tid] + excl - s_goff[tid];   // mod 2^32: added to a local slot >= the local base
         }
+        __syncthreads();
+
+        // ---- issue the next tile's loads, then copy this tile out while they are in flight
+        const u32 next = s_tile[par ^ 1];
+        par ^= 1;
+        if (next < num_tiles) {
+            const u32 wbase = next * RS_TILE + w * 32 * RS_IPT + lane;
+#pragma unroll
+            for (int j = 0; j < RS_IPT; j++) {
+                const u32 idx = wbase + j * 32;
+                item[j] = (idx < n) ? in[idx] : 0ull;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < RS_IPT; k++) {
+            const u32 idx = tid + k * RS_THREADS;
+            if (idx < valid) {
+                const u64 it = s_items[idx];
+                const u32 d = (u32)(it >> shift) & (SMJ_RADIX - 1);
+                out[s_goff[d] + idx] = it;
+            }
+        }
+        tile = next;
+        // the __syncthreads after the counter reset at the loop top orders these reads before the next reorder
     }
 }
 
@@ -174,8 +226,9 @@ size_t smj_radix_status_words(u32 n) { return smj_radix_num_tiles(n) * SMJ_RADIX
 
 size_t smj_radix_scratch_bytes(u32 n)
 {
-    // [bases 4*256][counters 4 (+pad to 16)][status 4 passes]
-    return (size_t)(SMJ_KEY_PASSES * SMJ_RADIX + 16) * 4 + SMJ_KEY_PASSES * smj_radix_status_words(n) * 4;
+    // [bases 4*256][counters 4 (+pad to 16)][status ping][status pong]; the caller zeroes everything once per sort,
+    // each pass re-zeroes the other status array for its successor
+    return (size_t)(SMJ_KEY_PASSES * SMJ_RADIX + 16) * 4 + 2 * smj_radix_status_words(n) * 4;
 }
 
 int smj_launch_radix_hist(SmjCtx *c, const u64 *d_pairs, u32 n, u32 *d_hist)
@@ -195,48 +248,46 @@ int smj_launch_radix_scan(SmjCtx *c, const u32 *d_hist, u32 *d_bases)
     return SMJ_OK;
 }
 
-int smj_launch_radix_pass(SmjCtx *c, const u64 *d_in, u64 *d_out, u32 n, int pass, const u32 *d_bases_pass,
-                          u32 *d_status, u32 *d_tile_counter)
+int smj_launch_radix_pass(SmjCtx *c, const u64 *d_in, u64 *d_out, const u64 *d_n, u32 n_max, int pass,
+                          const u32 *d_bases_pass, u32 *d_status, u32 *d_status_next, u32 *d_tile_counter)
 {
     if (!c->radix_attr_set) {   // function attributes are per device
         CUDA_TRY(cudaFuncSetAttribute(radix_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
         c->radix_attr_set = true;
     }
-    const u32 tiles = (u32)smj_radix_num_tiles(n);
-    radix_pass_kernel<<<tiles, RS_THREADS, RS_SMEM, c->stream>>>(d_in, d_out, n, 32 + pass * SMJ_RADIX_BITS,
-                                                                 d_bases_pass, d_status, d_tile_counter, c->d_err);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const u32 tiles = (u32)smj_radix_num_tiles(n_max);
+    const u32 grid = tiles < (u32)(sms * 3) ? tiles : (u32)(sms * 3);
+    radix_pass_kernel<<<grid, RS_THREADS, RS_SMEM, c->stream>>>(d_in, d_out, d_n, n_max, 32 + pass * SMJ_RADIX_BITS,
+                                                                d_bases_pass, d_status, d_status_next, d_tile_counter, c->d_err);
     KERNEL_CHECK(c);
     return SMJ_OK;
 }
 
-int smj_radix_sort_pairs(SmjCtx *c, u64 *buf_a, u64 *buf_b, u32 n, const u32 *d_hist, const u32 *h_hist,
-                         u32 *d_scratch, u64 **d_sorted)
+// Stable LSD sort of the first *d_n (<= n_max) pairs of buf_a by their key half; buf_b is the ping-pong partner.
+// Four passes, so the result is back in buf_a.  Nothing here waits for the host: the pair count is read on the
+// device, and a digit every key shares costs one identity-permutation pass instead of a host round trip.
+int smj_radix_sort_pairs(SmjCtx *c, u64 *buf_a, u64 *buf_b, const u64 *d_n, u32 n_max, const u32 *d_hist, u32 *d_scratch)
 {
-    // d_scratch: smj_radix_scratch_bytes(n), zeroed by the caller.
-    *d_sorted = buf_a;
-    if (n < 2) return SMJ_OK;
-    if (n > SMJ_MAX_SORT_ROWS) return smj_set_error(SMJ_ETOOBIG, "radix sort of %u pairs exceeds 2^30 - 1", n);
+    if (n_max < 2) return SMJ_OK;
+    if (n_max > SMJ_MAX_SORT_ROWS) return smj_set_error(SMJ_ETOOBIG, "radix sort of %u pairs exceeds 2^30 - 1", n_max);
     u32 *d_bases = d_scratch;
     u32 *d_counters = d_scratch + SMJ_KEY_PASSES * SMJ_RADIX;
-    u32 *d_status = d_counters + 16;
-    const size_t words = smj_radix_status_words(n);
+    u32 *d_status[2] = {d_counters + 16, d_counters + 16 + smj_radix_status_words(n_max)};
     SMJ_TRY(smj_launch_radix_scan(c, d_hist, d_bases));
     u64 *src = buf_a, *dst = buf_b;
     for (int p = 0; p < SMJ_KEY_PASSES; p++) {
-        bool trivial = false;   // every key has the same digit: the pass would be the identity permutation
-        for (int b = 0; b < SMJ_RADIX; b++)
-            if (h_hist[p * SMJ_RADIX + b] == n) { trivial = true; break; }
-        if (trivial) continue;
         const bool timed = c->pass_count < SmjCtx::kMaxTimedPasses;
         if (timed) CUDA_TRY(cudaEventRecord(c->pass_ev[2 * c->pass_count], c->stream));
-        SMJ_TRY(smj_launch_radix_pass(c, src, dst, n, p, d_bases + p * SMJ_RADIX, d_status + p * words, d_counters + p));
+        SMJ_TRY(smj_launch_radix_pass(c, src, dst, d_n, n_max, p, d_bases + p * SMJ_RADIX, d_status[p & 1], d_status[(p + 1) & 1],
+                                      d_counters + p));
         if (timed) {
             CUDA_TRY(cudaEventRecord(c->pass_ev[2 * c->pass_count + 1], c->stream));
-            c->pass_items[c->pass_count] = n;
+            c->pass_items[c->pass_count] = n_max;
             c->pass_count++;
         }
         u64 *t = src; src = dst; dst = t;
     }
-    *d_sorted = src;
     return SMJ_OK;
 }

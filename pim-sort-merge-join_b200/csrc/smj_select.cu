@@ -105,12 +105,201 @@ select_pairs_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int sel
     }
 }
 
+
+// ------------------------------------------------------------------ TMA-fed, warp-specialised variant (the one smj_run uses)
+// A tile is a CONTIGUOUS byte range of the row-major table, so one 1-D bulk copy (cp.async.bulk, SASS UBLKCP) per
+// tile moves it into shared memory without touching registers.  Nine warps per CTA:
+//   warp 8    producer: waits for a free ring stage and issues the bulk copy of the CTA's next tile (full/empty mbarriers);
+//   warps 0-7 compute: predicate, ballot/popc ranks, digit histogram, and the tile's survivors written compacted
+//             WITHIN the tile's own slot of a temporary array (slot t starts at t * tile_rows), plus the tile count.
+// No CTA ever waits for another one: the first two versions of this kernel resolved each tile's global offset with
+// a decoupled look-back inside the streaming loop, and ncu showed 70 % (single role) / 35 % (dedicated scan warp) of
+// all stall samples waiting for that look-back's L2 round trips, with DRAM at 19 % of peak.  Here the offsets come
+// from a separate scan over the tile counts (tile_scan_kernel, microseconds) and a compaction copy of the survivors
+// (8 B per survivor, L2-resident at the 10M-row config), and the table scan itself is a pure stream.
+constexpr int SEL_STAGES = 3;
+constexpr int SEL_STAGE_BYTES = 32768;
+constexpr int SEL_MAX_COLS_TMA = SEL_STAGE_BYTES / 4 / SEL_THREADS;   // 32 columns: at least one row per thread
+constexpr int SELW_THREADS = SEL_THREADS + 32;                         // + producer warp
+constexpr size_t SELW_SMEM = (size_t)SEL_STAGES * SEL_STAGE_BYTES;
+
+template <bool HIST>
+__global__ void __launch_bounds__(SELW_THREADS)
+select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, int sel_col, int32_t sel_val, int select_all,
+                  int key_col, u32 rowid_base, u64 *__restrict__ slots, u32 *__restrict__ tile_count, u32 *hist, u32 num_tiles)
+{
+    extern __shared__ __align__(128) unsigned char sel_smem[];      // stage ring
+    __shared__ __align__(8) u64 s_full[SEL_STAGES], s_empty[SEL_STAGES];
+    __shared__ u32 s_cnt[2][SEL_IPT * SEL_WARPS];
+    __shared__ u32 s_hist[HIST ? SMJ_KEY_PASSES * SMJ_RADIX : 1];
+
+    const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+    const u32 tile_rows = (u32)ipt * SEL_THREADS;
+
+    if (HIST)
+        for (u32 i = tid; i < SMJ_KEY_PASSES * SMJ_RADIX; i += SELW_THREADS) s_hist[i] = 0;
+    if (tid == 0) {
+        for (int st = 0; st < SEL_STAGES; st++) { mbar_init(&s_full[st], 1); mbar_init(&s_empty[st], SEL_WARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (w == SEL_WARPS) {
+        // ------------------------------------------------ producer (one lane); tiles are dealt round-robin
+        if (lane != 0) return;
+        const size_t row_bytes = (size_t)cols * 4;
+        u32 stage = 0, parity = 0;
+        for (u32 t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            mbar_wait(&s_empty[stage], parity ^ 1u);      // passes at once the first time round the ring
+            const int64_t row0 = (int64_t)t * tile_rows;
+            const int64_t rows = (n - row0 < (int64_t)tile_rows) ? (n - row0) : (int64_t)tile_rows;
+            const u32 bytes = (u32)(rows * row_bytes);
+            const u32 b16 = bytes & ~15u;
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(in) + (size_t)row0 * row_bytes;
+            unsigned char *dst = sel_smem + (size_t)stage * SEL_STAGE_BYTES;
+            for (u32 b = b16; b < bytes; b += 4)          // ragged tail of the last tile (< 16 bytes)
+                *reinterpret_cast<int32_t *>(dst + b) = *reinterpret_cast<const int32_t *>(src + b);
+            if (b16) {
+                mbar_expect_tx(&s_full[stage], b16);
+                bulk_g2s(dst, src, b16, &s_full[stage]);
+            } else {
+                mbar_arrive(&s_full[stage]);
+            }
+            if (++stage == SEL_STAGES) { stage = 0; parity ^= 1u; }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------- compute warps
+    const u32 lt = lanemask_lt();
+    u32 stage = 0, parity = 0, it = 0;
+    for (u32 tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+        mbar_wait(&s_full[stage], parity);
+        const int64_t tile_base = (int64_t)tile * tile_rows;
+        const u32 rows_valid = (u32)((n - tile_base < (int64_t)tile_rows) ? (n - tile_base) : (int64_t)tile_rows);
+        const int32_t *s_rows = reinterpret_cast<const int32_t *>(sel_smem + (size_t)stage * SEL_STAGE_BYTES);
+        u32 *cntbuf = s_cnt[it & 1u];
+
+        int32_t key[SEL_IPT];
+        u32 rank[SEL_IPT];
+        u32 passmask = 0;
+#pragma unroll
+        for (int j = 0; j < SEL_IPT; j++) {
+            if (j < ipt) {
+                const u32 row = j * SEL_THREADS + tid;
+                int32_t sv = 0, kv = 0;
+                const bool valid = row < rows_valid;
+                if (valid) {
+                    sv = s_rows[row * cols + sel_col];
+                    kv = (key_col == sel_col) ? sv : s_rows[row * cols + key_col];
+                }
+                const bool pass = valid && (select_all || sv > sel_val);
+                key[j] = kv;
+                const u32 b = __ballot_sync(FULL_MASK, pass);
+                if (lane == 0) cntbuf[j * SEL_WARPS + w] = __popc(b);
+                rank[j] = __popc(b & lt);
+                passmask |= (pass ? 1u : 0u) << j;
+            } else if (lane == 0) {
+                cntbuf[j * SEL_WARPS + w] = 0;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[stage]);   // this warp holds its cells in registers: stage can be refilled
+        named_bar_sync(1, SEL_THREADS);                // counts complete (double-buffered: one barrier per tile)
+
+        // every warp scans the 64 (row group, warp) counts itself: no second barrier, no broadcast
+        const u32 v0 = cntbuf[2 * lane], v1 = cntbuf[2 * lane + 1];
+        const u32 inc = warp_incl_scan(v0 + v1);
+        const u32 ex0 = inc - (v0 + v1);               // exclusive prefix of entry 2*lane; entry 2*lane+1 adds v0
+        if (tid == SEL_THREADS - 1) tile_count[tile] = inc;   // lane 31: the tile total
+        u64 *dst = slots + (size_t)tile_base;
+#pragma unroll
+        for (int j = 0; j < SEL_IPT; j++) {
+            const u32 e = (u32)j * SEL_WARPS + w;      // warp-uniform entry index
+            u32 off = __shfl_sync(FULL_MASK, ex0, e >> 1);
+            const u32 add = __shfl_sync(FULL_MASK, v0, e >> 1);
+            if (e & 1u) off += add;
+            if ((passmask >> j) & 1u) {
+                const u64 p = make_pair(key[j], rowid_base + (u32)(tile_base + j * SEL_THREADS + tid));
+                dst[off + rank[j]] = p;
+                if (HIST) {
+                    const u32 k = pair_key(p);
+#pragma unroll
+                    for (int d = 0; d < SMJ_KEY_PASSES; d++)
+                        atomicAdd(&s_hist[d * SMJ_RADIX + ((k >> (d * SMJ_RADIX_BITS)) & (SMJ_RADIX - 1))], 1u);
+                }
+            }
+        }
+        if (++stage == SEL_STAGES) { stage = 0; parity ^= 1u; }
+    }
+    if (HIST) {
+        named_bar_sync(1, SEL_THREADS);
+        for (u32 i = tid; i < SMJ_KEY_PASSES * SMJ_RADIX; i += SEL_THREADS) {
+            const u32 v = s_hist[i];
+            if (v) atomicAdd(&hist[i], v);
+        }
+    }
+}
+
+// Exclusive scan of per-tile counts (one CTA): offsets[t] = sum of counts[0..t), *total = sum of all.
+// Each thread owns a contiguous chunk, so the block-level part is one scan of 1024 partial sums.
+constexpr int TS_THREADS = 1024;
+__global__ void __launch_bounds__(TS_THREADS) tile_scan_kernel(const u32 *__restrict__ counts, u32 num_tiles, u64 *offsets, u64 *total)
+{
+    __shared__ u64 s_w[TS_THREADS / 32];
+    const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+    const u32 chunk = (num_tiles + TS_THREADS - 1) / TS_THREADS;
+    const u32 lo = tid * chunk < num_tiles ? tid * chunk : num_tiles;
+    const u32 hi = lo + chunk < num_tiles ? lo + chunk : num_tiles;
+    u64 sum = 0;
+    for (u32 i = lo; i < hi; i++) sum += counts[i];
+    u64 inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u64 t = __shfl_up_sync(FULL_MASK, inc, o);
+        if (lane >= (u32)o) inc += t;
+    }
+    if (lane == 31) s_w[w] = inc;
+    __syncthreads();
+    u64 run = inc - sum;
+    for (u32 ww = 0; ww < w; ww++) run += s_w[ww];
+    if (tid == TS_THREADS - 1) *total = run + sum;
+    for (u32 i = lo; i < hi; i++) { offsets[i] = run; run += counts[i]; }
+}
+
+// pairs[offsets[t] + i] = slots[t * tile_rows + i], i < counts[t]: the survivors in table order, contiguous.
+__global__ void __launch_bounds__(256)
+select_compact_kernel(const u64 *__restrict__ slots, const u32 *__restrict__ counts, const u64 *__restrict__ offsets, u32 num_tiles,
+                      u32 tile_rows, u64 *__restrict__ pairs)
+{
+    for (u32 t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const u32 cnt = counts[t];
+        const u64 *src = slots + (size_t)t * tile_rows;
+        u64 *dst = pairs + offsets[t];
+        for (u32 i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
 }  // namespace
 
-size_t smj_select_num_tiles(int64_t n) { return (size_t)((n + SEL_TILE - 1) / SEL_TILE); }
+// rows per thread per tile for the TMA path: the largest power-of-two count (<= 8) whose tile fits one stage
+static int select_ipt(int cols)
+{
+    int ipt = SEL_IPT;
+    while (ipt > 1 && (size_t)ipt * SEL_THREADS * cols * 4 > SEL_STAGE_BYTES) ipt >>= 1;
+    return ipt;
+}
+static bool select_use_tma(const int32_t *d_in, int cols)
+{
+    return cols <= SEL_MAX_COLS_TMA && (((uintptr_t)d_in) & 15) == 0;
+}
+
+// scratch words (u64) per table: look-back status (fallback kernel) or tile offsets + tile counts (TMA path);
+// the smallest tile either path uses is SEL_THREADS rows
+size_t smj_select_num_tiles(int64_t n) { return 2 * (size_t)((n + SEL_THREADS - 1) / SEL_THREADS) + 2; }
 
 int smj_launch_select_pairs(SmjCtx *c, const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val,
-                            int select_all, int key_col, u32 rowid_base, u64 *d_pairs, u64 *d_status,
+                            int select_all, int key_col, u32 rowid_base, u64 *d_pairs, u64 *d_tmp, u64 *d_status,
                             u32 *d_tile_counter, u32 *d_hist, u64 *d_count)
 {
     if (n <= 0) return SMJ_OK;   // caller zeroed *d_count
@@ -118,9 +307,36 @@ int smj_launch_select_pairs(SmjCtx *c, const int32_t *d_in, int64_t n, int cols,
     // compares int64 T against the int64 knob, with int32-valued cells).
     if (sel_val < (int64_t)INT32_MIN) select_all = 1;
     if (!select_all && sel_val >= (int64_t)INT32_MAX) return SMJ_OK;   // nothing passes; *d_count stays 0
-    const u32 tiles = (u32)smj_select_num_tiles(n);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    if (d_tmp && select_use_tma(d_in, cols)) {
+        const int ipt = select_ipt(cols);
+        const int64_t tile_rows = (int64_t)ipt * SEL_THREADS;
+        const u32 tiles = (u32)((n + tile_rows - 1) / tile_rows);
+        const size_t smem = SELW_SMEM;
+        if (!c->select_attr_set) {
+            CUDA_TRY(cudaFuncSetAttribute(select_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(cudaFuncSetAttribute(select_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            c->select_attr_set = true;
+        }
+        u64 *d_offsets = d_status;                                   // [tiles]
+        u32 *d_counts = reinterpret_cast<u32 *>(d_status + tiles);   // [tiles]
+        const u32 grid = tiles < (u32)(sms * 2) ? tiles : (u32)(sms * 2);
+        if (d_hist)
+            select_tma_kernel<true><<<grid, SELW_THREADS, smem, c->stream>>>(d_in, n, cols, ipt, sel_col, (int32_t)sel_val, select_all,
+                                                                            key_col, rowid_base, d_tmp, d_counts, d_hist, tiles);
+        else
+            select_tma_kernel<false><<<grid, SELW_THREADS, smem, c->stream>>>(d_in, n, cols, ipt, sel_col, (int32_t)sel_val, select_all,
+                                                                             key_col, rowid_base, d_tmp, d_counts, nullptr, tiles);
+        KERNEL_CHECK(c);
+        tile_scan_kernel<<<1, TS_THREADS, 0, c->stream>>>(d_counts, tiles, d_offsets, d_count);
+        KERNEL_CHECK(c);
+        const u32 cgrid = tiles < (u32)(sms * 8) ? tiles : (u32)(sms * 8);
+        select_compact_kernel<<<cgrid, 256, 0, c->stream>>>(d_tmp, d_counts, d_offsets, tiles, (u32)tile_rows, d_pairs);
+        KERNEL_CHECK(c);
+        return SMJ_OK;
+    }
+    const u32 tiles = (u32)((n + SEL_TILE - 1) / SEL_TILE);
     const u32 grid = tiles < (u32)(sms * 8) ? tiles : (u32)(sms * 8);
     if (d_hist)
         select_pairs_kernel<true><<<grid, SEL_THREADS, 0, c->stream>>>(d_in, n, cols, sel_col, (int32_t)sel_val,
