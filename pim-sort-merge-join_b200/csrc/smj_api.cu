@@ -480,24 +480,37 @@ extern "C" int smj_merge(const smj_table_t *a, const smj_table_t *b, int key_col
 }
 
 // ------------------------------------------------------------------ smj_join
+// Join scratch of `tiles` tiles inside a byte arena: [tile_count u32 x tiles (zeroed)] [tile_off u64 x tiles] [part u32 x 2(tiles+1)]
+struct JoinScratch { u32 *tile_count; u64 *tile_off; u32 *part; size_t zero_bytes, bytes; };
+static JoinScratch join_scratch(char *base, size_t tiles)
+{
+    JoinScratch j;
+    j.zero_bytes = align_up(tiles * 4, 256);
+    j.tile_count = (u32 *)base;
+    j.tile_off = (u64 *)(base + j.zero_bytes);
+    j.part = (u32 *)(base + j.zero_bytes + align_up(tiles * 8, 256));
+    j.bytes = j.zero_bytes + align_up(tiles * 8, 256) + align_up((tiles + 1) * 2 * 4, 256);
+    return j;
+}
+
 static int join_sorted_pairs(SmjCtx *c, const u64 *pl, u32 m1, const u64 *pr, u32 m2, int mode, bool count_only,
                              const int32_t *d_t1, int c1, const int32_t *d_t2, int c2, int key2, smj_table_t *out,
                              int64_t *rows_out)
 {
-    // scratch for the join lives in WS_PART: [jcount u64][ticket u32 + pad][status tiles*8][part 2*(tiles+1) u32]
-    const size_t tiles = smj_join_num_tiles((u64)m1 + m2);
-    const size_t sbytes = 64 + tiles * 8 + (tiles + 1) * 2 * 4;
-    WS_TRY(js, char *, c, WS_PART, sbytes);
-    CUDA_TRY(cudaMemsetAsync(js, 0, 64 + tiles * 8, c->stream));
+    const size_t tiles = (m1 == 0 || m2 == 0) ? 0 : smj_join_num_tiles((u64)m1 + m2);
+    const JoinScratch sz = join_scratch(nullptr, tiles);
+    WS_TRY(js, char *, c, WS_PART, 256 + sz.bytes);
+    const JoinScratch jsr = join_scratch(js + 256, tiles);
+    CUDA_TRY(cudaMemsetAsync(js, 0, 256 + jsr.zero_bytes, c->stream));
     u64 *d_jcount = (u64 *)js;
-    u32 *d_ticket = (u32 *)(js + 16);
-    u64 *d_status = (u64 *)(js + 64);
-    u32 *d_part = (u32 *)(js + 64 + tiles * 8);
-    const u32 mmin = m1 < m2 ? m1 : m2;
     uint2 *d_matches = nullptr;
-    if (mode == SMJ_JOIN_ZIP) { WS_TRY(mm, uint2 *, c, WS_MATCH, (size_t)mmin * 8); d_matches = mm; }
+    uint2 *d_dense = nullptr;
+    if (mode == SMJ_JOIN_ZIP) {
+        WS_TRY(mm, uint2 *, c, WS_MATCH, tiles * smj_join_tile_size() * 8); d_matches = mm;
+        if (!count_only) { WS_TRY(dd, uint2 *, c, WS_MATCH_DENSE, (size_t)(m1 < m2 ? m1 : m2) * 8); d_dense = dd; }
+    }
     else if (!count_only) return smj_set_error(SMJ_EINVAL, "SMJ_JOIN_MANY materialisation is not available in this build; use smj_join_count");
-    SMJ_TRY(smj_launch_join_match(c, pl, pr, nullptr, m1, m2, mode, d_part, d_status, d_ticket, d_matches, d_jcount));
+    SMJ_TRY(smj_launch_join_match(c, pl, pr, nullptr, m1, m2, mode, jsr.part, jsr.tile_count, jsr.tile_off, d_matches, d_dense, d_jcount));
     u64 *hm = (u64 *)c->h_pinned;
     CUDA_TRY(cudaMemcpyAsync(hm, d_jcount, 8, cudaMemcpyDeviceToHost, c->stream));
     SMJ_TRY(smj_check_device_flag(c));
@@ -507,10 +520,10 @@ static int join_sorted_pairs(SmjCtx *c, const u64 *pl, u32 m1, const u64 *pr, u3
     const int c_out = c1 + c2 - 1;
     if (out->on_device) {
         SMJ_TRY(smj_alloc_out(c, out, j, c_out));
-        SMJ_TRY(smj_launch_join_materialize(c, d_matches, nullptr, j, d_t1, c1, d_t2, c2, key2, out->data));
+        SMJ_TRY(smj_launch_join_materialize(c, d_dense, nullptr, j, d_t1, c1, d_t2, c2, key2, out->data));
     } else {
         WS_TRY(tmp, int32_t *, c, WS_TMP_ROWS, (size_t)j * c_out * 4);
-        SMJ_TRY(smj_launch_join_materialize(c, d_matches, nullptr, j, d_t1, c1, d_t2, c2, key2, tmp));
+        SMJ_TRY(smj_launch_join_materialize(c, d_dense, nullptr, j, d_t1, c1, d_t2, c2, key2, tmp));
         SMJ_TRY(emit_out_from_device(c, out, tmp, j, c_out));
     }
     return SMJ_OK;
@@ -610,12 +623,13 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
     // one zeroed arena: [header][select status x2][radix scratch x2][join header 64 B + join status]; then join partitions
     const size_t stiles[2] = {smj_select_num_tiles(n[0]), smj_select_num_tiles(n[1])};
     const size_t rb[2] = {align_up(smj_radix_scratch_bytes((u32)n[0]), 256), align_up(smj_radix_scratch_bytes((u32)n[1]), 256)};
-    const size_t jt = smj_join_num_tiles((u64)n[0] + n[1]);
+    const size_t jt = (n[0] == 0 || n[1] == 0) ? 0 : smj_join_num_tiles((u64)n[0] + n[1]);
     const size_t off_sel = align_up(sizeof(ScratchHeader), 256);
     const size_t off_radix = align_up(off_sel + (stiles[0] + stiles[1]) * 8, 256);
     const size_t off_join = off_radix + rb[0] + rb[1];
-    const size_t zero_bytes = align_up(off_join + 64 + jt * 8, 256);
-    const size_t sbytes = zero_bytes + (jt + 1) * 2 * 4;
+    const JoinScratch jsz = join_scratch(nullptr, jt);
+    const size_t zero_bytes = off_join + jsz.zero_bytes;
+    const size_t sbytes = off_join + jsz.bytes;
     WS_TRY(scr, char *, c, WS_SCRATCH, sbytes);
     WS_TRY(ping0, u64 *, c, WS_PAIRS_A1, (size_t)n[0] * 8);
     WS_TRY(ping1, u64 *, c, WS_PAIRS_A2, (size_t)n[1] * 8);
@@ -623,7 +637,8 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
     WS_TRY(pong1, u64 *, c, WS_PAIRS_B2, (size_t)n[1] * 8);
     u64 *ping[2] = {ping0, ping1}, *pong[2] = {pong0, pong1};
     const int64_t j_max = n[0] < n[1] ? n[0] : n[1];
-    WS_TRY(mm, uint2 *, c, WS_MATCH, (size_t)j_max * 8);
+    WS_TRY(mm, uint2 *, c, WS_MATCH, jt * smj_join_tile_size() * 8);
+    WS_TRY(md, uint2 *, c, WS_MATCH_DENSE, (size_t)j_max * 8);
     smj_table_t dev_out = {nullptr, 0, c_out, 1};
     SMJ_TRY(smj_alloc_out(c, &dev_out, j_max, c_out));   // upper bound; rows is set once the count is known
     CUDA_TRY(cudaEventRecord(c->ev[E_H2D], c->stream));
@@ -643,10 +658,10 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
 
     // ---- join: co-rank, count, scan, write matches; then materialise rows straight from the input tables
     {
-        char *js = scr + off_join;
-        SMJ_TRY(smj_launch_join_match(c, ping[0], ping[1], &h->count[0], (u32)n[0], (u32)n[1], SMJ_JOIN_ZIP, (u32 *)(scr + zero_bytes),
-                                      (u64 *)(js + 64), (u32 *)(js + 16), mm, &h->jcount));
-        SMJ_TRY(smj_launch_join_materialize(c, mm, &h->jcount, j_max, d_t[0], cc[0], d_t[1], cc[1], key[1], dev_out.data));
+        const JoinScratch jsr = join_scratch(scr + off_join, jt);
+        SMJ_TRY(smj_launch_join_match(c, ping[0], ping[1], &h->count[0], (u32)n[0], (u32)n[1], SMJ_JOIN_ZIP, jsr.part, jsr.tile_count,
+                                      jsr.tile_off, mm, md, &h->jcount));
+        SMJ_TRY(smj_launch_join_materialize(c, md, &h->jcount, j_max, d_t[0], cc[0], d_t[1], cc[1], key[1], dev_out.data));
     }
     CUDA_TRY(cudaEventRecord(c->ev[E_JOIN], c->stream));
 

@@ -46,7 +46,7 @@ enum SmjSlot {
     WS_MATCH,                        // matched (left rowid, right rowid)
     WS_TMP_ROWS, WS_TMP_ROWS2,       // staging for in-place sort / host outputs
     WS_XCHG_SEND1, WS_XCHG_SEND2, WS_XCHG_RECV1, WS_XCHG_RECV2, WS_SAMPLES,
-    WS_MERGE_A, WS_MERGE_B, WS_RADIX,
+    WS_MERGE_A, WS_MERGE_B, WS_RADIX, WS_MATCH_DENSE,
 };
 
 int   smj_set_error(int code, const char *fmt, ...);
@@ -102,12 +102,16 @@ size_t smj_join_num_tiles(u64 total);
 // zip mode: matches[i] = (left rowid, right rowid) in (key, left position) order; *d_count = number of matches.
 // many mode with d_matches == nullptr: *d_count = sum over left rows of the right run length (count only).
 // d_counts: device {m1, m2} (u64 each) or null, in which case m1_max / m2_max are the exact sizes.
+// With tiles = smj_join_num_tiles(m1_max + m2_max): d_part holds 2*(tiles+1) u32, d_tile_count tiles u32 (zeroed by the
+// caller), d_tile_off tiles u64, d_matches tiles * smj_join_tile_size() entries (tile t's matches start at t * tile size).
+// zip mode: *d_count = number of matches (written by the scan); many mode: *d_count += total pair count (count only).
+size_t smj_join_tile_size(void);
+// d_dense (zip mode, may be null): the matches compacted in result order, min(m1_max, m2_max) entries of capacity.
 int smj_launch_join_match(SmjCtx *c, const u64 *d_l, const u64 *d_r, const u64 *d_counts, u32 m1_max, u32 m2_max, int mode,
-                          u32 *d_part /*[2*(tiles+1)]*/, u64 *d_status /*[tiles] zero*/, u32 *d_tile_counter /*zero*/,
-                          uint2 *d_matches, u64 *d_count);
+                          u32 *d_part, u32 *d_tile_count, u64 *d_tile_off, uint2 *d_matches, uint2 *d_dense, u64 *d_count);
 // d_nj: device match count or null (then nj_max is exact)
-int smj_launch_join_materialize(SmjCtx *c, const uint2 *d_matches, const u64 *d_nj, int64_t nj_max, const int32_t *d_t1,
-                                int c1, const int32_t *d_t2, int c2, int key2, int32_t *d_out);
+int smj_launch_join_materialize(SmjCtx *c, const uint2 *d_dense, const u64 *d_nj, int64_t nj_max, const int32_t *d_t1, int c1,
+                                const int32_t *d_t2, int c2, int key2, int32_t *d_out);
 
 // ------------------------------------------------------------------ synth (smj_synth.cu)
 int smj_launch_synth(SmjCtx *c, int32_t *d_out, int64_t row0, int64_t rows, int64_t total_rows, int cols,

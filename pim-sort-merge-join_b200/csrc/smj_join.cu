@@ -81,61 +81,105 @@ join_partition_kernel(const u64 *__restrict__ L, const u64 *__restrict__ R, cons
     }
 }
 
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src_gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Tiles of JN_TILE merged elements, dealt round-robin to persistent CTAs.  No CTA waits for another: a tile's matches
+// go to its own slot of `matches` (slot t starts at t * JN_TILE) with the count in tile_count[t]; the output offsets
+// come from tile_scan_kernel afterwards.  (The first version resolved them in-kernel with a decoupled look-back and
+// spent 37 % of its stall samples behind that barrier.)  The next tile's elements are fetched with cp.async into the
+// other half of a double buffer while the current tile is merged.
 template <int MODE>
 __global__ void __launch_bounds__(JN_THREADS)
 join_match_kernel(const u64 *__restrict__ L, const u64 *__restrict__ R, const u64 *__restrict__ counts, u32 m1_max,
-                  u32 m2_max, const u32 *__restrict__ part, const u32 *__restrict__ runstart, u64 *status,
-                  u32 *tile_counter, uint2 *__restrict__ matches, u64 *count, u32 *err)
+                  u32 m2_max, const u32 *__restrict__ part, const u32 *__restrict__ runstart, uint2 *__restrict__ matches,
+                  u32 *__restrict__ tile_count, u64 *count)
 {
     u32 m1, m2;
     load_counts(counts, m1_max, m2_max, m1, m2);
     const u32 num_tiles = (m1 == 0 || m2 == 0) ? 0u : (u32)(((u64)m1 + m2 + JN_TILE - 1) / JN_TILE);
-    __shared__ __align__(16) u64 s[JN_TILE + 2];
+    constexpr int BUF = JN_TILE + 4;                      // [prev left element][left segment][right segment + halo]
+    __shared__ __align__(16) u64 s_buf[2][BUF];
     __shared__ u32 s_wsum[JN_WARPS];
-    __shared__ u32 s_tile;
-    __shared__ u64 s_base;
     const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
     const u64 total = (u64)m1 + m2;
     u64 many_total = 0;
 
-    while (true) {
-        __syncthreads();
-        if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-        __syncthreads();
-        const u32 tile = s_tile;
-        if (tile >= num_tiles) break;
+    // geometry of a tile from its partition entries
+    struct Geo { u32 a0, na, b0, nb, nbh, rs; };
+    auto geo = [&](u32 tile, u32 a0, u32 a1, u32 rs) {
+        Geo g;
         const u64 d0 = (u64)tile * JN_TILE;
         const u64 d1 = (d0 + JN_TILE < total) ? d0 + JN_TILE : total;
-        const u32 a0 = part[tile], a1 = part[tile + 1];
-        const u32 b0 = (u32)(d0 - a0), b1 = (u32)(d1 - a1);
-        const u32 na = a1 - a0, nb = b1 - b0;
-        const u32 nbh = nb + (b1 < m2 ? 1u : 0u);   // right segment plus one halo element
-        u64 *sA = s, *sB = s + na;
-        for (u32 i = tid; i < na; i += JN_THREADS) sA[i] = L[a0 + i];
-        for (u32 i = tid; i < nbh; i += JN_THREADS) sB[i] = R[b0 + i];
+        g.a0 = a0; g.na = a1 - a0;
+        g.b0 = (u32)(d0 - a0);
+        const u32 b1 = (u32)(d1 - a1);
+        g.nb = b1 - g.b0;
+        g.nbh = g.nb + (b1 < m2 ? 1u : 0u);               // right segment plus one halo element
+        g.rs = rs;
+        return g;
+    };
+    auto fetch = [&](const Geo &g, u64 *buf) {            // buf[0] = L[a0-1] (if any), buf[1..] = left, then right
+        const u32 lead = g.a0 > 0 ? 1u : 0u;
+        const u64 *srcL = L + g.a0 - lead;
+        for (u32 i = tid; i < g.na + lead; i += JN_THREADS) cp_async8(buf + 1 - lead + i, srcL + i);
+        const u64 *srcR = R + g.b0;
+        u64 *dstR = buf + 1 + g.na;
+        for (u32 i = tid; i < g.nbh; i += JN_THREADS) cp_async8(dstR + i, srcR + i);
+        cp_async_commit();
+    };
+
+    u32 tile = blockIdx.x;
+    u32 cur = 0;
+    Geo g = {}, gn = {};
+    if (tile < num_tiles) {
+        g = geo(tile, part[tile], part[tile + 1], runstart[tile]);
+        fetch(g, s_buf[0]);
+        const u32 nt = tile + gridDim.x;
+        if (nt < num_tiles) gn = geo(nt, part[nt], part[nt + 1], runstart[nt]);
+    }
+    while (tile < num_tiles) {
+        cp_async_wait_all();
+        __syncthreads();                                  // tile data visible; the other buffer is free again
+        const u32 next = tile + gridDim.x;
+        if (next < num_tiles) fetch(gn, s_buf[cur ^ 1]);
+        const Geo gc = g;
+        g = gn;
+        {
+            const u32 n2 = next + gridDim.x;              // partition entries two tiles ahead (plain loads, consumed next round)
+            if (n2 < num_tiles) gn = geo(n2, part[n2], part[n2 + 1], runstart[n2]);
+        }
+        const u32 a0 = gc.a0, na = gc.na, b0 = gc.b0, nb = gc.nb, nbh = gc.nbh, tile_rs = gc.rs;
+        u64 *buf = s_buf[cur];
+        const u64 *sA = buf + 1, *sB = buf + 1 + na;
         const bool has_prev = a0 > 0;
-        const u32 prevk = has_prev ? pair_key(L[a0 - 1]) : 0u;
-        const u32 tile_rs = runstart[tile];
-        __syncthreads();
+        const u32 prevk = has_prev ? pair_key(buf[0]) : 0u;
 
         const u32 ntile = na + nb;
         const u32 diag = (tid * JN_VT < ntile) ? tid * JN_VT : ntile;
         u32 a = merge_path(sA, na, sB, nb, diag);
         u32 b = diag - a;
         const u32 steps = (ntile - diag < (u32)JN_VT) ? ntile - diag : (u32)JN_VT;
-        u32 ka = a < na ? pair_key(sA[a]) : 0u, kb = b < nb ? pair_key(sB[b]) : 0u;
+        u64 va = a < na ? sA[a] : 0ull, vb = b < nb ? sB[b] : 0ull;
         uint2 mt[JN_VT];
         u32 mmask = 0;
         bool have = false;
-        u32 runk = 0, run_val = 0;   // zip: first left position of the current key; many: its right run length
+        u32 runk = 0, run_val = 0;   // zip: rank of the current left element inside its key run; many: the right run length
 #pragma unroll
         for (int st = 0; st < JN_VT; st++) {
             if (st < (int)steps) {
+                const u32 ka = pair_key(va), kb = pair_key(vb);
                 const bool takeA = (b >= nb) || (a < na && ka <= kb);
                 if (takeA) {
                     const u32 k = ka;
                     if (MODE == SMJ_JOIN_ZIP) {
-                        if (!(have && runk == k)) {
+                        if (have) {
+                            run_val = (runk == k) ? run_val + 1 : 0u;   // the previous left element was this thread's
+                        } else {                                        // first left element of this thread
                             u32 rs;
                             if (a == 0) rs = (has_prev && prevk == k) ? tile_rs : a0;
                             else if (pair_key(sA[a - 1]) != k) rs = a0 + a;
@@ -143,15 +187,23 @@ join_match_kernel(const u64 *__restrict__ L, const u64 *__restrict__ R, const u6
                                 const u32 lo = lower_bound_key(sA, 0, a, k);
                                 rs = (lo == 0 && has_prev && prevk == k) ? tile_rs : a0 + lo;
                             }
-                            run_val = rs; runk = k; have = true;
+                            run_val = (a0 + a) - rs;
+                            have = true;
                         }
-                        const u64 j = (u64)(b0 + b) + ((a0 + a) - run_val);
-                        if (j < m2) {
-                            const u64 rp = (j - b0 < nbh) ? sB[j - b0] : R[j];
-                            if (pair_key(rp) == k) {
-                                mt[st] = make_uint2(pair_row(sA[a]), pair_row(rp));
-                                mmask |= 1u << st;
-                            }
+                        runk = k;
+                        // partner: the run_val-th right element at or after the right cursor, if its key is k
+                        const u32 jj = b + run_val;                     // tile-relative, halo included
+                        u64 rp = vb;
+                        bool ok = b < nb;
+                        if (run_val != 0u || !ok) {
+                            ok = true;
+                            if (jj < nbh) rp = sB[jj];
+                            else if ((u64)b0 + jj < (u64)m2) rp = R[(u64)b0 + jj];
+                            else ok = false;
+                        }
+                        if (ok && pair_key(rp) == k) {
+                            mt[st] = make_uint2(pair_row(va), pair_row(rp));
+                            mmask |= 1u << st;
                         }
                     } else {
                         if (!(have && runk == k)) {
@@ -163,10 +215,10 @@ join_match_kernel(const u64 *__restrict__ L, const u64 *__restrict__ R, const u6
                         many_total += run_val;
                     }
                     a++;
-                    ka = a < na ? pair_key(sA[a]) : 0u;
+                    va = a < na ? sA[a] : 0ull;
                 } else {
                     b++;
-                    kb = b < nb ? pair_key(sB[b]) : 0u;
+                    vb = b < nb ? sB[b] : 0ull;
                 }
             }
         }
@@ -174,7 +226,7 @@ join_match_kernel(const u64 *__restrict__ L, const u64 *__restrict__ R, const u6
             const u32 cnt = __popc(mmask);
             const u32 inc = warp_incl_scan(cnt);
             if (lane == 31) s_wsum[w] = inc;
-            __syncthreads();   // also: every thread is done reading sA/sB, s[] may be reused below
+            __syncthreads();   // also: every thread is done reading sA/sB, the buffer may be reused for staging
             u32 wp = 0, tile_total = 0;
 #pragma unroll
             for (int ww = 0; ww < JN_WARPS; ww++) {
@@ -182,26 +234,61 @@ join_match_kernel(const u64 *__restrict__ L, const u64 *__restrict__ R, const u6
                 if (ww < (int)w) wp += v;
                 tile_total += v;
             }
-            if (w == 0) {
-                const u64 e = lookback_warp(status, tile, (u64)tile_total, err, SMJ_ERR_SPIN_JOIN);
-                if (lane == 0) {
-                    s_base = e;
-                    if (tile == num_tiles - 1) *count = e + tile_total;
-                }
-            }
-            uint2 *s_out = reinterpret_cast<uint2 *>(s);
+            if (tid == 0) tile_count[tile] = tile_total;
+            uint2 *s_out = reinterpret_cast<uint2 *>(buf);
             u32 o = wp + inc - cnt;
 #pragma unroll
             for (int st = 0; st < JN_VT; st++)
                 if ((mmask >> st) & 1u) s_out[o++] = mt[st];
             __syncthreads();
-            const u64 base = s_base;
-            for (u32 i = tid; i < tile_total; i += JN_THREADS) matches[base + i] = s_out[i];
+            uint2 *dst = matches + (size_t)tile * JN_TILE;
+            for (u32 i = tid; i < tile_total; i += JN_THREADS) dst[i] = s_out[i];
         }
+        tile = next;
+        cur ^= 1;
     }
     if (MODE != SMJ_JOIN_ZIP) {
         many_total = warp_sum(many_total);
         if (lane == 0 && many_total) atomicAdd(count, many_total);
+    }
+}
+
+// Exclusive scan of per-tile counts (one CTA): offsets[t] = sum of counts[0..t), *total = sum of all.
+constexpr int JS_THREADS = 1024;
+__global__ void __launch_bounds__(JS_THREADS)
+join_scan_kernel(const u32 *__restrict__ tile_count, u32 num_tiles, u64 *offsets, u64 *total)
+{
+    __shared__ u64 s_w[JS_THREADS / 32];
+    const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+    const u32 chunk = (num_tiles + JS_THREADS - 1) / JS_THREADS;
+    const u32 lo = tid * chunk < num_tiles ? tid * chunk : num_tiles;
+    const u32 hi = lo + chunk < num_tiles ? lo + chunk : num_tiles;
+    u64 sum = 0;
+    for (u32 i = lo; i < hi; i++) sum += tile_count[i];
+    u64 inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u64 t = __shfl_up_sync(FULL_MASK, inc, o);
+        if (lane >= (u32)o) inc += t;
+    }
+    if (lane == 31) s_w[w] = inc;
+    __syncthreads();
+    u64 run = inc - sum;
+    for (u32 ww = 0; ww < w; ww++) run += s_w[ww];
+    if (tid == JS_THREADS - 1) *total = run + sum;
+    for (u32 i = lo; i < hi; i++) { offsets[i] = run; run += tile_count[i]; }
+}
+
+// dense[offsets[t] + i] = slots[t * JN_TILE + i], i < tile_count[t]: the matches in result order, contiguous.
+__global__ void __launch_bounds__(256)
+join_compact_kernel(const uint2 *__restrict__ slots, const u32 *__restrict__ tile_count, const u64 *__restrict__ tile_off, u32 num_tiles,
+                    uint2 *__restrict__ dense)
+{
+    for (u32 t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const u32 cnt = tile_count[t];
+        const uint2 *src = slots + (size_t)t * JN_TILE;
+        uint2 *dst = dense + tile_off[t];
+        for (u32 i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = src[i];
     }
 }
 
@@ -223,7 +310,9 @@ join_materialize_kernel(const uint2 *__restrict__ matches, const u64 *__restrict
     if (nj_dev) { const u64 v = *nj_dev; nj = v < (u64)nj_max ? (int64_t)v : nj_max; }
     const int c_out = c1 + c2 - 1;
     const int64_t nblocks = (nj + rows_per_block - 1) / rows_per_block;
-    for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+    {
+      int32_t *out_slot = out;
+      for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         const int64_t row0 = blk * rows_per_block;
         const int nrows = (int)((nj - row0 < rows_per_block) ? (nj - row0) : rows_per_block);
         __syncthreads();   // previous block's copy-out is done with s_out
@@ -282,14 +371,16 @@ join_materialize_kernel(const uint2 *__restrict__ matches, const u64 *__restrict
         }
         __syncthreads();
         const int ncell = nrows * c_out;
-        int32_t *o = out + row0 * c_out;
+        int32_t *o = out_slot + row0 * c_out;
         for (int cell = threadIdx.x; cell < ncell; cell += MT_THREADS) o[cell] = s_out[cell];
+      }
     }
 }
 
 }  // namespace
 
 size_t smj_join_num_tiles(u64 total) { return (size_t)((total + JN_TILE - 1) / JN_TILE); }
+size_t smj_join_tile_size(void) { return JN_TILE; }
 
 static int sm_count(SmjCtx *c)
 {
@@ -301,8 +392,11 @@ static int sm_count(SmjCtx *c)
     return n;
 }
 
+// Scratch layout of one join (u32 words): [part tiles+1][runstart tiles+1][tile_count tiles (zeroed by caller)] then
+// u64-aligned [tile_off tiles].  smj_join_scratch_* give the sizes; tiles = smj_join_num_tiles(m1_max + m2_max).
 int smj_launch_join_match(SmjCtx *c, const u64 *d_l, const u64 *d_r, const u64 *d_counts, u32 m1_max, u32 m2_max,
-                          int mode, u32 *d_part, u64 *d_status, u32 *d_tile_counter, uint2 *d_matches, u64 *d_count)
+                          int mode, u32 *d_part, u32 *d_tile_count, u64 *d_tile_off, uint2 *d_matches, uint2 *d_dense,
+                          u64 *d_count)
 {
     if (m1_max == 0 || m2_max == 0) return SMJ_OK;   // caller zeroed *d_count
     const u32 tiles = (u32)smj_join_num_tiles((u64)m1_max + m2_max);   // upper bound; the kernels use the device counts
@@ -310,19 +404,28 @@ int smj_launch_join_match(SmjCtx *c, const u64 *d_l, const u64 *d_r, const u64 *
     join_partition_kernel<<<(tiles + 1 + 7) / 8, 256, 0, c->stream>>>(d_l, d_r, d_counts, m1_max, m2_max, d_part, d_runstart);
     KERNEL_CHECK(c);
     const int sms = sm_count(c);
-    const u32 grid = tiles < (u32)(sms * 8) ? tiles : (u32)(sms * 8);
-    if (mode == SMJ_JOIN_ZIP)
+    const u32 grid = tiles < (u32)(sms * 4) ? tiles : (u32)(sms * 4);   // 58 registers x 256 threads: 4 CTAs per SM
+    if (mode == SMJ_JOIN_ZIP) {
         join_match_kernel<SMJ_JOIN_ZIP><<<grid, JN_THREADS, 0, c->stream>>>(d_l, d_r, d_counts, m1_max, m2_max, d_part, d_runstart,
-                                                                           d_status, d_tile_counter, d_matches, d_count, c->d_err);
-    else
+                                                                           d_matches, d_tile_count, d_count);
+        KERNEL_CHECK(c);
+        join_scan_kernel<<<1, JS_THREADS, 0, c->stream>>>(d_tile_count, tiles, d_tile_off, d_count);
+        if (d_dense) {
+            KERNEL_CHECK(c);
+            const u32 cgrid = tiles < (u32)(sms * 32) ? tiles : (u32)(sms * 32);
+            join_compact_kernel<<<cgrid, 256, 0, c->stream>>>(d_matches, d_tile_count, d_tile_off, tiles, d_dense);
+        }
+    } else {
         join_match_kernel<SMJ_JOIN_MANY><<<grid, JN_THREADS, 0, c->stream>>>(d_l, d_r, d_counts, m1_max, m2_max, d_part, d_runstart,
-                                                                            d_status, d_tile_counter, d_matches, d_count, c->d_err);
+                                                                            d_matches, d_tile_count, d_count);
+    }
     KERNEL_CHECK(c);
     return SMJ_OK;
 }
 
-int smj_launch_join_materialize(SmjCtx *c, const uint2 *d_matches, const u64 *d_nj, int64_t nj_max, const int32_t *d_t1,
-                                int c1, const int32_t *d_t2, int c2, int key2, int32_t *d_out)
+// Joined rows from the dense match list (*d_nj of them, at most nj_max).
+int smj_launch_join_materialize(SmjCtx *c, const uint2 *d_dense, const u64 *d_nj, int64_t nj_max, const int32_t *d_t1, int c1,
+                                const int32_t *d_t2, int c2, int key2, int32_t *d_out)
 {
     if (nj_max <= 0) return SMJ_OK;
     const int c_out = c1 + c2 - 1;
@@ -331,12 +434,12 @@ int smj_launch_join_materialize(SmjCtx *c, const uint2 *d_matches, const u64 *d_
     if (rpb > 1024) rpb = 1024;
     const int64_t nblocks = (nj_max + rpb - 1) / rpb;
     const int sms = sm_count(c);
-    const u32 grid = (u32)(nblocks < (int64_t)sms * 8 ? nblocks : (int64_t)sms * 8);
+    const u32 grid = (u32)(nblocks < (int64_t)sms * 6 ? nblocks : (int64_t)sms * 6);
     const bool vec = (c1 % 4 == 0) && (c2 % 4 == 0) && ((((uintptr_t)d_t1) | ((uintptr_t)d_t2)) & 15) == 0;
     if (vec)
-        join_materialize_kernel<true><<<grid, MT_THREADS, 0, c->stream>>>(d_matches, d_nj, nj_max, d_t1, c1, d_t2, c2, key2, d_out, rpb);
+        join_materialize_kernel<true><<<grid, MT_THREADS, 0, c->stream>>>(d_dense, d_nj, nj_max, d_t1, c1, d_t2, c2, key2, d_out, rpb);
     else
-        join_materialize_kernel<false><<<grid, MT_THREADS, 0, c->stream>>>(d_matches, d_nj, nj_max, d_t1, c1, d_t2, c2, key2, d_out, rpb);
+        join_materialize_kernel<false><<<grid, MT_THREADS, 0, c->stream>>>(d_dense, d_nj, nj_max, d_t1, c1, d_t2, c2, key2, d_out, rpb);
     KERNEL_CHECK(c);
     return SMJ_OK;
 }

@@ -14,118 +14,147 @@
 
 namespace {
 
-constexpr int RS_THREADS = 256;
+constexpr int RS_THREADS = 512;
 constexpr int RS_IPT = 16;
-constexpr int RS_TILE = RS_THREADS * RS_IPT;   // 4096 pairs = 32 KB
+constexpr int RS_TILE = RS_THREADS * RS_IPT;   // 8192 pairs = 64 KB
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr u32 RS_FLAG_LOCAL = 1u << 30, RS_FLAG_INCL = 2u << 30, RS_VAL_MASK = (1u << 30) - 1;
-static_assert(RS_THREADS == SMJ_RADIX, "one thread per digit bin");
+static_assert(RS_THREADS >= SMJ_RADIX, "one thread per digit bin");
 constexpr int RS_LB = 8;   // predecessors examined per look-back round
 
-// shared memory: reordered tile | per-warp digit counters | two alternating per-warp peer-mask arrays | offsets
-constexpr size_t RS_SMEM = (size_t)RS_TILE * 8 + (size_t)RS_WARPS * SMJ_RADIX * 4 + 2 * (size_t)RS_WARPS * SMJ_RADIX * 4 +
+// shared memory: reordered tile | per-warp digit counters | per-warp peer masks | per-digit offsets | scan partials
+constexpr size_t RS_SMEM = (size_t)RS_TILE * 8 + (size_t)RS_WARPS * SMJ_RADIX * 4 + (size_t)RS_WARPS * SMJ_RADIX * 4 +
                            SMJ_RADIX * 4 + 32 * 4;
+
+// digit `pass` (0..3) of the key half of a pair: one PRMT
+__device__ __forceinline__ u32 pair_digit(u64 p, u32 sel) { return __byte_perm((u32)(p >> 32), 0u, sel); }
 
 // Why not __match_any_sync: MATCH.ANY runs on the SM-wide ADU pipe at ~61 cycles per warp instruction on sm_100
 // (profiles/r01_ubench_primitives.txt) and made the first version of this kernel ADU-bound (54 % pipe utilisation,
 // 7 % DRAM).  A shared-memory atomicOr of the lane bit into a per-warp, per-digit mask word gives the same peer mask
 // at ~2.7 cycles per warp instruction.
-__global__ void __launch_bounds__(RS_THREADS, 3)
-radix_pass_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const u64 *__restrict__ n_dev, u32 n_max, int shift,
+//
+// Persistent CTAs of 16 warps take 8192-pair tiles through an atomic ticket (a tile's predecessors have all been
+// started, which is what the look-back needs).  Per tile: per-warp digit counts (shared-memory atomics) -> publish
+// the tile's 256 counts EARLY -> rank and reorder into shared memory -> batched look-back -> coalesced copy-out while
+// the next tile's loads are already in flight.
+template <bool FULL>
+__device__ __forceinline__ void radix_count_tile(const u64 (&item)[RS_IPT], u32 sel, u32 *my_cnt, u32 rel0, u32 valid)
+{
+#pragma unroll
+    for (int j = 0; j < RS_IPT; j++) {
+        const u32 d = pair_digit(item[j], sel);
+        if (FULL || rel0 + j * 32 < valid) atomicAdd(&my_cnt[d], 1u);
+    }
+}
+
+template <bool FULL>
+__device__ __forceinline__ void radix_rank_tile(const u64 (&item)[RS_IPT], u32 sel, u32 *my_cnt, u32 *my_mask, u64 *s_items,
+                                                u32 rel0, u32 valid, u32 lane, u32 lt)
+{
+#pragma unroll
+    for (int j = 0; j < RS_IPT; j++) {
+        const u32 d = pair_digit(item[j], sel);
+        const bool ok = FULL || rel0 + j * 32 < valid;
+        u32 *mk = my_mask + d;
+        if (ok) atomicOr(mk, 1u << lane);
+        __syncwarp();
+        const u32 peers = *mk;
+        const u32 pre = my_cnt[d];
+        __syncwarp();
+        if (ok) {
+            if ((peers >> lane) == 1u) {   // highest peer lane: reset the mask, advance the running slot
+                *mk = 0;
+                my_cnt[d] = pre + __popc(peers);
+            }
+            s_items[pre + __popc(peers & lt)] = item[j];
+        }
+        __syncwarp();                      // the reset lands before the next row's atomicOr
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS, 2)
+radix_pass_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const u64 *__restrict__ n_dev, u32 n_max, int pass,
                   const u32 *__restrict__ bin_base, u32 *status, u32 *status_next, u32 *tile_counter, u32 *err)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *s_items = reinterpret_cast<u64 *>(smem_raw);              // RS_TILE, tile in digit order
     u32 *s_wcnt = reinterpret_cast<u32 *>(s_items + RS_TILE);      // [warp][256] counts -> running local slot
-    u32 *s_mask = s_wcnt + RS_WARPS * SMJ_RADIX;                   // [2][warp][256] peer masks (self-resetting)
-    u32 *s_goff = s_mask + 2 * RS_WARPS * SMJ_RADIX;               // [256] global slot minus local slot per digit
+    u32 *s_mask = s_wcnt + RS_WARPS * SMJ_RADIX;                   // [warp][256] peer masks (self-resetting)
+    u32 *s_goff = s_mask + RS_WARPS * SMJ_RADIX;                   // [256] global slot minus local slot per digit
     u32 *s_wsum = s_goff + SMJ_RADIX;                              // warp totals of the bin scan
     __shared__ u32 s_tile[2];
 
     const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
     const u32 lt = lanemask_lt();
+    const u32 sel = 0x4440u | (u32)pass;
     u64 n64 = n_dev ? *n_dev : (u64)n_max;
     const u32 n = n64 < (u64)n_max ? (u32)n64 : n_max;
     const u32 num_tiles = (n + RS_TILE - 1) / RS_TILE;
 
     if (tid == 0) s_tile[0] = atomicAdd(tile_counter, 1u);
-    for (u32 i = tid; i < 2 * RS_WARPS * SMJ_RADIX; i += RS_THREADS) s_mask[i] = 0;
+    for (u32 i = tid; i < RS_WARPS * SMJ_RADIX; i += RS_THREADS) s_mask[i] = 0;
     __syncthreads();
     u32 tile = s_tile[0];
     int par = 0;
 
     // warp-striped layout: element order inside the tile is (warp, j, lane) == ascending index
+    const u32 rel0 = w * 32 * RS_IPT + lane;   // tile-relative index of item[0]
     u64 item[RS_IPT];
     if (tile < num_tiles) {
-        const u32 wbase = tile * RS_TILE + w * 32 * RS_IPT + lane;
+        const u32 g0 = tile * RS_TILE + rel0;
 #pragma unroll
-        for (int j = 0; j < RS_IPT; j++) {
-            const u32 idx = wbase + j * 32;
-            item[j] = (idx < n) ? in[idx] : 0ull;
-        }
+        for (int j = 0; j < RS_IPT; j++) item[j] = (g0 + j * 32 < n) ? in[g0 + j * 32] : 0ull;
     }
 
     u32 *my_cnt = s_wcnt + w * SMJ_RADIX;
+    u32 *my_mask = s_mask + w * SMJ_RADIX;
     while (tile < num_tiles) {
         const u32 base = tile * RS_TILE;
         const u32 valid = (n - base < (u32)RS_TILE) ? (n - base) : (u32)RS_TILE;
-        const u32 wvalid_base = w * 32 * RS_IPT + lane;   // tile-relative index of item[0]
+        const bool full = valid == (u32)RS_TILE;
 
 #pragma unroll
-        for (int i = 0; i < RS_WARPS; i++) s_wcnt[i * SMJ_RADIX + tid] = 0;
+        for (int i = 0; i < RS_WARPS * SMJ_RADIX / RS_THREADS; i++) s_wcnt[i * RS_THREADS + tid] = 0;
         __syncthreads();
 
         // ---- early counts: per-warp digit histogram
-#pragma unroll
-        for (int j = 0; j < RS_IPT; j++) {
-            const u32 d = (u32)(item[j] >> shift) & (SMJ_RADIX - 1);
-            if (wvalid_base + j * 32 < valid) atomicAdd(&my_cnt[d], 1u);
-        }
+        if (full) radix_count_tile<true>(item, sel, my_cnt, rel0, valid);
+        else radix_count_tile<false>(item, sel, my_cnt, rel0, valid);
         __syncthreads();
 
         // ---- one thread per digit: totals over warps, publish the tile aggregate, scan digits
-        u32 cnt;
-        {
-            u32 c[RS_WARPS], sum = 0;
+        u32 cnt = 0;
+        if (tid < SMJ_RADIX) {
 #pragma unroll
-            for (int ww = 0; ww < RS_WARPS; ww++) { c[ww] = s_wcnt[ww * SMJ_RADIX + tid]; sum += c[ww]; }
-            cnt = sum;
+            for (int ww = 0; ww < RS_WARPS; ww++) cnt += s_wcnt[ww * SMJ_RADIX + tid];
             st_relaxed(&status[(size_t)tile * SMJ_RADIX + tid], (tile == 0 ? RS_FLAG_INCL : RS_FLAG_LOCAL) | cnt);
             status_next[(size_t)tile * SMJ_RADIX + tid] = 0;   // the next pass (next kernel) reuses the other array
             const u32 inc = warp_incl_scan(cnt);
             if (lane == 31) s_wsum[w] = inc;
-            __syncthreads();
-            u32 run = inc - cnt;     // exclusive over digits: first local slot of this digit
+            s_goff[tid] = inc - cnt;                           // exclusive within this warp's 32 digits
+        }
+        __syncthreads();
+        if (tid < SMJ_RADIX) {
+            u32 run = s_goff[tid];                             // -> exclusive over all digits: first local slot
             for (u32 ww = 0; ww < w; ww++) run += s_wsum[ww];
-            s_goff[tid] = run;       // local base, turned into (global - local) after the look-back
+            s_goff[tid] = run;                                 // local base, turned into (global - local) after the look-back
 #pragma unroll
-            for (int ww = 0; ww < RS_WARPS; ww++) { s_wcnt[ww * SMJ_RADIX + tid] = run; run += c[ww]; }
+            for (int ww = 0; ww < RS_WARPS; ww++) {
+                const u32 c = s_wcnt[ww * SMJ_RADIX + tid];
+                s_wcnt[ww * SMJ_RADIX + tid] = run;
+                run += c;
+            }
         }
         __syncthreads();
 
         // ---- rank (stable: lanes in order, rows in order, warps in order) and reorder into shared memory
-#pragma unroll
-        for (int j = 0; j < RS_IPT; j++) {
-            const u32 d = (u32)(item[j] >> shift) & (SMJ_RADIX - 1);
-            const bool ok = wvalid_base + j * 32 < valid;
-            u32 *mk = s_mask + ((j & 1) * RS_WARPS + w) * SMJ_RADIX + d;
-            if (ok) atomicOr(mk, 1u << lane);
-            __syncwarp();
-            const u32 peers = *mk;
-            const u32 pre = my_cnt[d];
-            __syncwarp();
-            if (ok) {
-                if ((peers >> lane) == 1u) {   // highest peer lane: reset the mask, advance the running slot
-                    *mk = 0;
-                    my_cnt[d] = pre + __popc(peers);
-                }
-                s_items[pre + __popc(peers & lt)] = item[j];
-            }
-        }
+        if (full) radix_rank_tile<true>(item, sel, my_cnt, my_mask, s_items, rel0, valid, lane, lt);
+        else radix_rank_tile<false>(item, sel, my_cnt, my_mask, s_items, rel0, valid, lane, lt);
 
         // ---- next ticket, then this tile's look-back (predecessors published before they started ranking)
-        if (tid == 0) s_tile[par ^ 1] = atomicAdd(tile_counter, 1u);
-        {
+        if (tid == RS_THREADS - 1) s_tile[par ^ 1] = atomicAdd(tile_counter, 1u);
+        if (tid < SMJ_RADIX) {
             u32 excl = 0;
             if (tile > 0) {
                 // Batched look-back: RS_LB predecessors per round trip.  When a whole wave of tiles starts together
@@ -164,20 +193,16 @@ radix_pass_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const u64 *
         const u32 next = s_tile[par ^ 1];
         par ^= 1;
         if (next < num_tiles) {
-            const u32 wbase = next * RS_TILE + w * 32 * RS_IPT + lane;
+            const u32 g0 = next * RS_TILE + rel0;
 #pragma unroll
-            for (int j = 0; j < RS_IPT; j++) {
-                const u32 idx = wbase + j * 32;
-                item[j] = (idx < n) ? in[idx] : 0ull;
-            }
+            for (int j = 0; j < RS_IPT; j++) item[j] = (g0 + j * 32 < n) ? in[g0 + j * 32] : 0ull;
         }
 #pragma unroll
         for (int k = 0; k < RS_IPT; k++) {
             const u32 idx = tid + k * RS_THREADS;
-            if (idx < valid) {
+            if (full || idx < valid) {
                 const u64 it = s_items[idx];
-                const u32 d = (u32)(it >> shift) & (SMJ_RADIX - 1);
-                out[s_goff[d] + idx] = it;
+                out[s_goff[pair_digit(it, sel)] + idx] = it;
             }
         }
         tile = next;
@@ -258,8 +283,8 @@ int smj_launch_radix_pass(SmjCtx *c, const u64 *d_in, u64 *d_out, const u64 *d_n
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     const u32 tiles = (u32)smj_radix_num_tiles(n_max);
-    const u32 grid = tiles < (u32)(sms * 3) ? tiles : (u32)(sms * 3);
-    radix_pass_kernel<<<grid, RS_THREADS, RS_SMEM, c->stream>>>(d_in, d_out, d_n, n_max, 32 + pass * SMJ_RADIX_BITS,
+    const u32 grid = tiles < (u32)(sms * 2) ? tiles : (u32)(sms * 2);
+    radix_pass_kernel<<<grid, RS_THREADS, RS_SMEM, c->stream>>>(d_in, d_out, d_n, n_max, pass,
                                                                 d_bases_pass, d_status, d_status_next, d_tile_counter, c->d_err);
     KERNEL_CHECK(c);
     return SMJ_OK;

@@ -331,7 +331,7 @@ int smj_launch_select_pairs(SmjCtx *c, const int32_t *d_in, int64_t n, int cols,
         KERNEL_CHECK(c);
         tile_scan_kernel<<<1, TS_THREADS, 0, c->stream>>>(d_counts, tiles, d_offsets, d_count);
         KERNEL_CHECK(c);
-        const u32 cgrid = tiles < (u32)(sms * 8) ? tiles : (u32)(sms * 8);
+        const u32 cgrid = tiles < (u32)(sms * 32) ? tiles : (u32)(sms * 32);
         select_compact_kernel<<<cgrid, 256, 0, c->stream>>>(d_tmp, d_counts, d_offsets, tiles, (u32)tile_rows, d_pairs);
         KERNEL_CHECK(c);
         return SMJ_OK;
