@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N>1 only: per-GPU rows fixed (weak) or total fixed")
     args = ap.parse_args()
     name = args.workload or "c2"
     w = WORKLOADS[name]

@@ -1,0 +1,122 @@
+"""bench_multi.py -- the N>1 arm of bench.py: one process per GPU (torchrun), key-range partitioned join.
+
+Weak scaling: every rank holds a 10M-row block of each table of a virtual N x 10M-row pair (unique keys in
+[1, 3*N*10M], 50 % select), i.e. per-GPU input is BASELINE configs[1] whatever N is; the exchange step (grouped
+ncclSend/ncclRecv inside libsmj.so) moves (N-1)/N of the selected rows.  Timing is on the device (CUDA events inside
+smj_run, library stream), max over ranks; rank 0 prints the JSON line."""
+import ctypes as C
+import json
+import os
+import time
+
+
+def run_multi(args, w, name):
+    import smj_b200
+    from smj_b200 import smj as S
+    from bench import ClockSampler, peaks, knobs_for
+    rank, world, local = smj_b200.dist.init()
+    L = smj_b200.lib()
+    G = world
+    n1, n2, cols = w["n1"], w["n2"], w["cols"]
+    if args.scaling == "strong":
+        n1, n2 = n1 // G, n2 // G
+    tot1, tot2 = n1 * G, n2 * G
+    wv = dict(w, n1=tot1, n2=tot2)
+    v1, v2 = knobs_for(wv)
+    cfg = S.default_config(select_val1=v1, select_val2=v2, nr_gpus=G)
+    d1 = smj_b200.synth_device_table(n1, cols, 1, row0=rank * n1, total_rows=tot1)
+    d2 = smj_b200.synth_device_table(n2, cols, 2, row0=rank * n2, total_rows=tot2)
+    args.warmup = max(args.warmup, 3)
+
+    def step():
+        out, st = smj_b200.run(d1, d2, cfg=cfg, on_device=True, keep_output=True)
+        L.smj_table_free(C.byref(out))
+        return st
+
+    for _ in range(args.warmup):
+        st = step()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    smj_b200.dist.barrier()
+    t0 = time.perf_counter()
+    dev_ms, launches, pass_ms, passes = 0.0, 0, 0.0, 0
+    stages = {k: 0.0 for k in ("sort_ms", "exchange_ms", "merge_ms", "join_ms")}
+    nvlink = 0.0
+    for _ in range(args.steps):
+        st = step()
+        dev_ms += st["total_device_ms"]
+        launches += st["kernel_launches"]
+        pass_ms += st["sort_pass_ms_avg"] * st["sort_passes"]
+        passes += st["sort_passes"]
+        nvlink += st["bytes_nvlink"]
+        for k in stages:
+            stages[k] += st[k]
+    smj_b200.dist.barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    clk = clocks.stop() if rank == 0 else None
+    ms = smj_b200.dist.max_over_ranks(dev_ms / args.steps)
+    wall_ms = smj_b200.dist.max_over_ranks(wall_ms)
+    launches = int(smj_b200.dist.sum_over_ranks(launches))
+    joined = int(smj_b200.dist.sum_over_ranks(st["rows_joined"]))
+    sel = [int(smj_b200.dist.sum_over_ranks(st["rows_selected"][t])) for t in range(2)]
+    nvlink_max = smj_b200.dist.max_over_ranks(nvlink / args.steps)
+    stage_max = {k: smj_b200.dist.max_over_ranks(v / args.steps) for k, v in stages.items()}
+    nrows = tot1 + tot2
+    value = nrows / ms / 1e3
+
+    # end to end through the C-ABI with pinned HOST buffers on every rank
+    e2e = None
+    if not args.no_e2e:
+        hp = []
+        for d in (d1, d2):
+            p = C.c_void_p()
+            S.check(L.smj_host_alloc(C.byref(p), d.rows * d.cols * 4))
+            S.check(L.smj_memcpy_d2h(p, d.data, d.rows * d.cols * 4))
+            hp.append(S.Table(p.value, d.rows, d.cols, 0))
+        h2d = sum(t.rows * t.cols * 4 for t in hp)
+        d2h = 0
+        for i in range(2 + args.steps):
+            if i == 2:
+                smj_b200.dist.barrier()
+                t0 = time.perf_counter()
+            out, st2 = smj_b200.run(hp[0], hp[1], cfg=cfg, on_device=False, keep_output=True)
+            d2h = out.rows * out.cols * 4
+            L.smj_table_free(C.byref(out))
+        smj_b200.dist.barrier()
+        e_ms = smj_b200.dist.max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+        e2e = {"value": nrows / e_ms / 1e3, "unit": "Mrows/s", "ms_per_step": e_ms,
+               "h2d_bytes_per_step": int(smj_b200.dist.sum_over_ranks(h2d)), "d2h_bytes_per_step": int(smj_b200.dist.sum_over_ranks(d2h))}
+        for t in hp:
+            L.smj_host_free(t.data)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        m_avg = (sel[0] + sel[1]) / 2.0 / G
+        pass_avg_ms = pass_ms / max(passes, 1)
+        achieved = 16.0 * m_avg / (pass_avg_ms * 1e-3) / 1e9 if pass_avg_ms > 0 else 0.0
+        line = {
+            "metric": "select+sort+merge-join throughput", "value": value, "unit": "Mrows/s", "n_gpus": G, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": f"{w['desc']} per GPU ({args.scaling} scaling): {tot1} x {tot2} rows over {G} GPUs, key-range "
+                                   "partitioned via grouped ncclSend/ncclRecv", "name": name, "join_mode": "zip (cpu_app.c semantics)",
+                       "rows_selected": sel, "rows_joined": joined, "parallelism": f"key-range x{G}",
+                       "l2": "per-GPU inputs (2 x 160 MB) larger than the 126 MB L2; no explicit flush"},
+            "stage_ms": stage_max, "wall_ms_per_step": wall_ms, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "radix_pass_kernel (onesweep scatter pass)", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": 16.0 * m_avg, "avg_launch_ms": pass_avg_ms,
+                         "nvlink_bytes_sent_per_gpu": nvlink_max,
+                         "nvlink_gbs_per_gpu": nvlink_max / (stage_max["exchange_ms"] * 1e-3) / 1e9 if stage_max["exchange_ms"] > 0 else None,
+                         "nvlink_peak_gbs": 770.0},
+            "cpu_baseline": None, "e2e": e2e, "clocks": clk,
+        }
+        print(json.dumps(line), flush=True)
+    smj_b200.free(d1)
+    smj_b200.free(d2)
+    L.smj_shutdown()
+    import torch.distributed as dist
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0

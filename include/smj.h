@@ -95,6 +95,16 @@ void smj_shutdown(void);
 int  smj_dist_unique_id(void *nccl_id_128);
 int  smj_init_dist(const smj_config_t *cfg, int rank, int world, int local_device, const void *nccl_id_128);
 
+/* Host-only planning steps of the key-range exchange (no GPU needed; the CPU tests drive them under gloo):
+ * replace the host range split of app.c:589-633.  Keys are in the engine's order-preserving unsigned form
+ * (uint32_t)key ^ 0x80000000u; a sample equal to 0xffffffff means "none" (empty table on that rank).
+ * smj_plan_splitters: world-1 splitters = the b/world quantiles of the gathered samples; rank b owns keys in
+ *   [splitter[b-1], splitter[b]) (splitter[-1] = 0, splitter[world-1] = +inf), so equal keys share a rank.
+ * smj_plan_exchange: counts[src*world+dst] = rows src sends to dst; recv_offsets[src] = row offset of src's run in
+ *   rank me's receive buffer (runs in source-rank order), *recv_total = rows me receives. */
+int  smj_plan_splitters(const uint32_t *samples, int64_t n_samples, int world, uint32_t *splitters);
+int  smj_plan_exchange(const int64_t *counts, int world, int me, int64_t *recv_offsets, int64_t *recv_total);
+
 /* == select.c:63-194 (DPU select) / cpu_app.c:81-112: rows with in[row][col] > val, order preserved */
 int  smj_select(const smj_table_t *in, int col, int64_t val, smj_table_t *out);
 /* == sort_dpu.c:189-328 / cpu_app.c:172-202: stable ascending sort of whole rows by column key_col, in place */

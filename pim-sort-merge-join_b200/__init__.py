@@ -6,3 +6,4 @@ from .smj import (  # noqa: F401
     device_table, synth_device_table, free, JOIN_ZIP, JOIN_MANY,
 )
 from . import datagen  # noqa: F401
+from . import dist  # noqa: F401

@@ -160,6 +160,21 @@ extern "C" int smj_init(const smj_config_t *cfg)
 int smj_dist_shutdown(void);
 static void pinned_clear(void);
 
+// One-process-per-GPU mode: this process drives exactly `device` (as g_ctx[0]).
+int smj_init_on_device(const smj_config_t *cfg, int device)
+{
+    if (g_inited) smj_shutdown();
+    if (cfg) g_cfg = *cfg; else smj_config_default(&g_cfg);
+    const int ndev = smj_device_count();
+    if (ndev < 1) return smj_set_error(SMJ_ENODEVICE, "no CUDA device visible (libsmj has no CPU fallback)");
+    if (device < 0 || device >= ndev) return smj_set_error(SMJ_EINVAL, "local device %d out of range (%d visible)", device, ndev);
+    int r = ctx_create(device, &g_ctx[0]);
+    if (r != SMJ_OK) { smj_shutdown(); return r; }
+    g_nctx = 1;
+    g_inited = true;
+    return SMJ_OK;
+}
+
 extern "C" void smj_shutdown(void)
 {
     smj_dist_shutdown();
@@ -526,6 +541,38 @@ static int join_sorted_pairs(SmjCtx *c, const u64 *pl, u32 m1, const u64 *pr, u3
         SMJ_TRY(smj_launch_join_materialize(c, d_dense, nullptr, j, d_t1, c1, d_t2, c2, key2, tmp));
         SMJ_TRY(emit_out_from_device(c, out, tmp, j, c_out));
     }
+    return SMJ_OK;
+}
+
+int smj_join_pairs_to_table(SmjCtx *c, const u64 *pl, u32 m1, const u64 *pr, u32 m2, const int32_t *d_t1, int c1, const int32_t *d_t2,
+                            int c2, int key2, smj_table_t *out, int64_t *rows_out)
+{
+    return join_sorted_pairs(c, pl, m1, pr, m2, SMJ_JOIN_ZIP, false, d_t1, c1, d_t2, c2, key2, out, rows_out);
+}
+
+// select (or all rows) -> (key,rowid) pairs -> stable sort; one host wait for the survivor count.
+// table_idx picks the workspace slots (0: table 1, 1: table 2).  *d_sorted stays valid until those slots are reused.
+int smj_sorted_pairs_of_table(SmjCtx *c, const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val, int select_all,
+                              int key_col, int table_idx, u64 **d_sorted, int64_t *m_out)
+{
+    if (n > SMJ_MAX_SORT_ROWS) return smj_set_error(SMJ_ETOOBIG, "%lld rows exceed 2^30 - 1 per table per GPU", (long long)n);
+    const size_t sw = smj_select_num_tiles(n);
+    const size_t off_sel = align_up(sizeof(ScratchHeader), 256);
+    const size_t off_radix = align_up(off_sel + sw * 8, 256);
+    const size_t rb = align_up(smj_radix_scratch_bytes((u32)n), 256);
+    WS_TRY(scr, char *, c, WS_RADIX, off_radix + rb);
+    WS_TRY(ping, u64 *, c, table_idx ? WS_PAIRS_A2 : WS_PAIRS_A1, (size_t)n * 8);
+    WS_TRY(pong, u64 *, c, table_idx ? WS_PAIRS_B2 : WS_PAIRS_B1, (size_t)n * 8);
+    CUDA_TRY(cudaMemsetAsync(scr, 0, off_radix + rb, c->stream));
+    ScratchHeader *h = (ScratchHeader *)scr;
+    SMJ_TRY(smj_launch_select_pairs(c, d_in, n, cols, sel_col, sel_val, select_all, key_col, 0, ping, pong, (u64 *)(scr + off_sel),
+                                    &h->counter[0], h->hist[0], &h->count[0]));
+    SMJ_TRY(smj_radix_sort_pairs(c, ping, pong, &h->count[0], (u32)n, h->hist[0], (u32 *)(scr + off_radix)));
+    u64 *hm = (u64 *)c->h_pinned;
+    CUDA_TRY(cudaMemcpyAsync(hm, &h->count[0], 8, cudaMemcpyDeviceToHost, c->stream));
+    SMJ_TRY(smj_check_device_flag(c));
+    *m_out = (int64_t)hm[0];
+    *d_sorted = ping;
     return SMJ_OK;
 }
 

@@ -53,6 +53,7 @@ ABI_SYMBOLS = [
     "smj_merge", "smj_join", "smj_run", "smj_join_count", "smj_table_free", "smj_strerror", "smj_last_error",
     "smj_host_alloc", "smj_host_free", "smj_device_alloc", "smj_device_free", "smj_memcpy_h2d", "smj_memcpy_d2h",
     "smj_device_sync", "smj_synth_table", "smj_kernel_launches", "smj_device_count", "smj_version",
+    "smj_plan_splitters", "smj_plan_exchange",
 ]
 
 _lib = None
@@ -105,6 +106,8 @@ def lib():
     L.smj_synth_table.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_uint64, C.c_int,
                                   C.c_int64]
     L.smj_kernel_launches.restype = C.c_int64
+    L.smj_plan_splitters.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+    L.smj_plan_exchange.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int64)]
     _lib = L
     return L
 
