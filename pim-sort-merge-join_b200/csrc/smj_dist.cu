@@ -385,8 +385,8 @@ int smj_run_multi(const smj_config_t *cfg, const smj_table_t *t1, const smj_tabl
         stats->kernel_launches = c->launches - launches0;
         double sum = 0;
         for (int p = 0; p < c->pass_count; p++) sum += dist_ev_ms(c->pass_ev[2 * p], c->pass_ev[2 * p + 1]);
-        stats->sort_passes = c->pass_count;
-        stats->sort_pass_ms_avg = c->pass_count ? sum / c->pass_count : 0;
+        stats->sort_passes = c->pass_count * SMJ_KEY_PASSES;   // each timed group is one table's four passes
+        stats->sort_pass_ms_avg = c->pass_count ? sum / (c->pass_count * SMJ_KEY_PASSES) : 0;
     }
     return SMJ_OK;
 }

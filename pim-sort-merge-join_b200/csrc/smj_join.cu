@@ -284,11 +284,13 @@ __global__ void __launch_bounds__(256)
 join_compact_kernel(const uint2 *__restrict__ slots, const u32 *__restrict__ tile_count, const u64 *__restrict__ tile_off, u32 num_tiles,
                     uint2 *__restrict__ dense)
 {
-    for (u32 t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const u32 lane = threadIdx.x & 31u;
+    const u32 warps = gridDim.x * (blockDim.x >> 5);
+    for (u32 t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < num_tiles; t += warps) {   // one warp per tile
         const u32 cnt = tile_count[t];
         const uint2 *src = slots + (size_t)t * JN_TILE;
         uint2 *dst = dense + tile_off[t];
-        for (u32 i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = src[i];
+        for (u32 i = lane; i < cnt; i += 32) dst[i] = src[i];
     }
 }
 
@@ -412,7 +414,7 @@ int smj_launch_join_match(SmjCtx *c, const u64 *d_l, const u64 *d_r, const u64 *
         join_scan_kernel<<<1, JS_THREADS, 0, c->stream>>>(d_tile_count, tiles, d_tile_off, d_count);
         if (d_dense) {
             KERNEL_CHECK(c);
-            const u32 cgrid = tiles < (u32)(sms * 32) ? tiles : (u32)(sms * 32);
+            const u32 cgrid = (tiles + 7) / 8 < (u32)(sms * 8) ? (tiles + 7) / 8 : (u32)(sms * 8);
             join_compact_kernel<<<cgrid, 256, 0, c->stream>>>(d_matches, d_tile_count, d_tile_off, tiles, d_dense);
         }
     } else {

@@ -12,6 +12,16 @@
 #include "smj_internal.h"
 #include "smj_dev.cuh"
 
+// Optional per-phase cycle accounting for tools/radix_lab.cu (compiled out of libsmj.so).
+#ifdef SMJ_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[16];
+#define PHASE_INIT() long long ph_t = clock64()
+#define PHASE(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_phase_cycles[i], (unsigned long long)(t_ - ph_t)); ph_t = t_; } } while (0)
+#else
+#define PHASE_INIT() do { } while (0)
+#define PHASE(i) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int RS_THREADS = 512;
@@ -109,6 +119,7 @@ radix_pass_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const u64 *
 
     u32 *my_cnt = s_wcnt + w * SMJ_RADIX;
     u32 *my_mask = s_mask + w * SMJ_RADIX;
+    PHASE_INIT();
     while (tile < num_tiles) {
         const u32 base = tile * RS_TILE;
         const u32 valid = (n - base < (u32)RS_TILE) ? (n - base) : (u32)RS_TILE;
@@ -117,11 +128,13 @@ radix_pass_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const u64 *
 #pragma unroll
         for (int i = 0; i < RS_WARPS * SMJ_RADIX / RS_THREADS; i++) s_wcnt[i * RS_THREADS + tid] = 0;
         __syncthreads();
+        PHASE(0);   // zero counters (+ wait for this tile's loads to be issued)
 
         // ---- early counts: per-warp digit histogram
         if (full) radix_count_tile<true>(item, sel, my_cnt, rel0, valid);
         else radix_count_tile<false>(item, sel, my_cnt, rel0, valid);
         __syncthreads();
+        PHASE(1);   // load latency + count
 
         // ---- one thread per digit: totals over warps, publish the tile aggregate, scan digits
         u32 cnt = 0;
@@ -147,11 +160,13 @@ radix_pass_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const u64 *
             }
         }
         __syncthreads();
+        PHASE(2);   // digit totals, publish, scan
 
         // ---- rank (stable: lanes in order, rows in order, warps in order) and reorder into shared memory
         if (full) radix_rank_tile<true>(item, sel, my_cnt, my_mask, s_items, rel0, valid, lane, lt);
         else radix_rank_tile<false>(item, sel, my_cnt, my_mask, s_items, rel0, valid, lane, lt);
 
+        PHASE(3);   // rank + reorder (thread 0's view)
         // ---- next ticket, then this tile's look-back (predecessors published before they started ranking)
         if (tid == RS_THREADS - 1) s_tile[par ^ 1] = atomicAdd(tile_counter, 1u);
         if (tid < SMJ_RADIX) {
@@ -187,7 +202,9 @@ radix_pass_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const u64 *
             }
             s_goff[tid] = bin_base[tid] + excl - s_goff[tid];   // mod 2^32: added to a local slot >= the local base
         }
+        PHASE(4);   // look-back (thread 0's digit)
         __syncthreads();
+        PHASE(5);   // wait for the other warps (rank stragglers, other digits' look-back)
 
         // ---- issue the next tile's loads, then copy this tile out while they are in flight
         const u32 next = s_tile[par ^ 1];
@@ -205,6 +222,7 @@ radix_pass_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const u64 *
                 out[s_goff[pair_digit(it, sel)] + idx] = it;
             }
         }
+        PHASE(6);   // next loads issued + copy-out
         tile = next;
         // the __syncthreads after the counter reset at the loop top orders these reads before the next reorder
     }
@@ -302,17 +320,18 @@ int smj_radix_sort_pairs(SmjCtx *c, u64 *buf_a, u64 *buf_b, const u64 *d_n, u32 
     u32 *d_status[2] = {d_counters + 16, d_counters + 16 + smj_radix_status_words(n_max)};
     SMJ_TRY(smj_launch_radix_scan(c, d_hist, d_bases));
     u64 *src = buf_a, *dst = buf_b;
+    // one event pair around the four back-to-back passes (per-pass event records cost more stream time than they measure)
+    const bool timed = c->pass_count < SmjCtx::kMaxTimedPasses;
+    if (timed) CUDA_TRY(cudaEventRecord(c->pass_ev[2 * c->pass_count], c->stream));
     for (int p = 0; p < SMJ_KEY_PASSES; p++) {
-        const bool timed = c->pass_count < SmjCtx::kMaxTimedPasses;
-        if (timed) CUDA_TRY(cudaEventRecord(c->pass_ev[2 * c->pass_count], c->stream));
         SMJ_TRY(smj_launch_radix_pass(c, src, dst, d_n, n_max, p, d_bases + p * SMJ_RADIX, d_status[p & 1], d_status[(p + 1) & 1],
                                       d_counters + p));
-        if (timed) {
-            CUDA_TRY(cudaEventRecord(c->pass_ev[2 * c->pass_count + 1], c->stream));
-            c->pass_items[c->pass_count] = n_max;
-            c->pass_count++;
-        }
         u64 *t = src; src = dst; dst = t;
+    }
+    if (timed) {
+        CUDA_TRY(cudaEventRecord(c->pass_ev[2 * c->pass_count + 1], c->stream));
+        c->pass_items[c->pass_count] = n_max;
+        c->pass_count++;
     }
     return SMJ_OK;
 }

@@ -268,15 +268,19 @@ __global__ void __launch_bounds__(TS_THREADS) tile_scan_kernel(const u32 *__rest
 }
 
 // pairs[offsets[t] + i] = slots[t * tile_rows + i], i < counts[t]: the survivors in table order, contiguous.
+// One WARP per tile: a tile is ~1-2 K pairs, and with 64 tiles in flight per SM instead of 8 (one per CTA) the
+// dependent count/offset -> data round trips overlap.
 __global__ void __launch_bounds__(256)
 select_compact_kernel(const u64 *__restrict__ slots, const u32 *__restrict__ counts, const u64 *__restrict__ offsets, u32 num_tiles,
                       u32 tile_rows, u64 *__restrict__ pairs)
 {
-    for (u32 t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const u32 lane = threadIdx.x & 31u;
+    const u32 warps = gridDim.x * (blockDim.x >> 5);
+    for (u32 t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < num_tiles; t += warps) {
         const u32 cnt = counts[t];
         const u64 *src = slots + (size_t)t * tile_rows;
         u64 *dst = pairs + offsets[t];
-        for (u32 i = threadIdx.x; i < cnt; i += blockDim.x) dst[i] = src[i];
+        for (u32 i = lane; i < cnt; i += 32) dst[i] = src[i];
     }
 }
 
@@ -331,7 +335,7 @@ int smj_launch_select_pairs(SmjCtx *c, const int32_t *d_in, int64_t n, int cols,
         KERNEL_CHECK(c);
         tile_scan_kernel<<<1, TS_THREADS, 0, c->stream>>>(d_counts, tiles, d_offsets, d_count);
         KERNEL_CHECK(c);
-        const u32 cgrid = tiles < (u32)(sms * 32) ? tiles : (u32)(sms * 32);
+        const u32 cgrid = (tiles + 7) / 8 < (u32)(sms * 8) ? (tiles + 7) / 8 : (u32)(sms * 8);
         select_compact_kernel<<<cgrid, 256, 0, c->stream>>>(d_tmp, d_counts, d_offsets, tiles, (u32)tile_rows, d_pairs);
         KERNEL_CHECK(c);
         return SMJ_OK;
