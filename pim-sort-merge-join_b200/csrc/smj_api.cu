@@ -78,6 +78,7 @@ static int ctx_create(int device, SmjCtx **out)
     CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaMalloc(&c->d_err, 256));
     CUDA_TRY(cudaMemset(c->d_err, 0, 256));
+    CUDA_TRY(cudaMalloc((void **)&c->d_out_ptr, 256));
     c->h_pinned_bytes = 1 << 16;
     CUDA_TRY(cudaMallocHost(&c->h_pinned, c->h_pinned_bytes));
     for (auto &e : c->ev) CUDA_TRY(cudaEventCreate(&e));
@@ -103,6 +104,8 @@ static void ctx_destroy(SmjCtx *c)
     for (int i = 0; i < SmjCtx::kSlots; i++) if (c->slot[i]) cudaFree(c->slot[i]);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->pass_ev) if (e) cudaEventDestroy(e);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    if (c->d_out_ptr) cudaFree(c->d_out_ptr);
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -121,6 +124,7 @@ void *smj_ws(SmjCtx *c, int slot, size_t bytes)
     if (e != cudaSuccess) { smj_cuda_fail(e, "workspace cudaMalloc", __FILE__, __LINE__); return nullptr; }
     c->slot[slot] = p;
     c->slot_bytes[slot] = want;
+    c->ws_gen++;
     return p;
 }
 #define WS_TRY(var, type, c, slot, bytes) type var = (type)smj_ws(c, slot, bytes); if (!var) return SMJ_ENOMEM
@@ -690,25 +694,70 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
     SMJ_TRY(smj_alloc_out(c, &dev_out, j_max, c_out));   // upper bound; rows is set once the count is known
     CUDA_TRY(cudaEventRecord(c->ev[E_H2D], c->stream));
 
-    // ---- select (+ digit histograms), both tables
-    CUDA_TRY(cudaMemsetAsync(scr, 0, zero_bytes, c->stream));
+    // ---- the device pipeline: ~23 launches with no host wait in between.  A call that repeats the previous call's
+    // tables, shapes and knobs replays it as ONE CUDA graph (the launch gaps are ~8 % of a 0.6 ms step); the output
+    // buffer is new every call, so the materialise kernel reads its pointer from a device cell written just before.
     ScratchHeader *h = (ScratchHeader *)scr;
-    for (int t = 0; t < 2; t++)
-        SMJ_TRY(smj_launch_select_pairs(c, d_t[t], n[t], cc[t], sel_col[t], sel_val[t], 0, key[t], 0, ping[t], pong[t],
-                                        (u64 *)(scr + off_sel + (t ? stiles[0] * 8 : 0)), &h->counter[t], h->hist[t], &h->count[t]));
-    CUDA_TRY(cudaEventRecord(c->ev[E_SELECT], c->stream));
-
-    // ---- sort: 4 onesweep passes per table over the device-resident survivor counts
-    for (int t = 0; t < 2; t++)
-        SMJ_TRY(smj_radix_sort_pairs(c, ping[t], pong[t], &h->count[t], (u32)n[t], h->hist[t], (u32 *)(scr + off_radix + (t ? rb[0] : 0))));
-    CUDA_TRY(cudaEventRecord(c->ev[E_SORT], c->stream));
-
-    // ---- join: co-rank, count, scan, write matches; then materialise rows straight from the input tables
-    {
-        const JoinScratch jsr = join_scratch(scr + off_join, jt);
-        SMJ_TRY(smj_launch_join_match(c, ping[0], ping[1], &h->count[0], (u32)n[0], (u32)n[1], SMJ_JOIN_ZIP, jsr.part, jsr.tile_count,
-                                      jsr.tile_off, mm, md, &h->jcount));
-        SMJ_TRY(smj_launch_join_materialize(c, md, &h->jcount, j_max, d_t[0], cc[0], d_t[1], cc[1], key[1], dev_out.data));
+    u64 key_now[16] = {(u64)(uintptr_t)d_t[0], (u64)(uintptr_t)d_t[1], (u64)n[0], (u64)n[1], (u64)cc[0], (u64)cc[1],
+                       (u64)sel_col[0], (u64)sel_col[1], (u64)sel_val[0], (u64)sel_val[1], (u64)key[0], (u64)key[1], c->ws_gen,
+                       (u64)(uintptr_t)scr, 0, 0};
+    static const bool graphs_on = !(getenv("SMJ_NO_GRAPH") && atoi(getenv("SMJ_NO_GRAPH")) != 0);
+    if (memcmp(key_now, c->graph_key, sizeof key_now) != 0) {
+        memcpy(c->graph_key, key_now, sizeof key_now);
+        c->graph_seen = 0;
+        if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    }
+    c->graph_seen++;
+    const bool replay = graphs_on && c->graph_exec != nullptr;
+    const bool capture = graphs_on && !replay && c->graph_seen >= 2;   // the first call warms attributes and slots eagerly
+    int32_t **h_ptr = (int32_t **)((char *)c->h_pinned + c->h_pinned_bytes - 128);
+    *h_ptr = dev_out.data;
+    CUDA_TRY(cudaMemcpyAsync(c->d_out_ptr, h_ptr, sizeof(int32_t *), cudaMemcpyHostToDevice, c->stream));
+    if (!replay) {
+        const int64_t l0 = c->launches;
+        if (capture) CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = SMJ_OK;
+        do {
+#define PIPE_TRY(x) if ((rc = (x)) != SMJ_OK) break
+#define PIPE_CUDA(x) if (cudaError_t e_ = (x)) { rc = smj_cuda_fail(e_, #x, __FILE__, __LINE__); break; }
+            // select (+ digit histograms), both tables
+            PIPE_CUDA(cudaMemsetAsync(scr, 0, zero_bytes, c->stream));
+            for (int t = 0; t < 2 && rc == SMJ_OK; t++)
+                rc = smj_launch_select_pairs(c, d_t[t], n[t], cc[t], sel_col[t], sel_val[t], 0, key[t], 0, ping[t], pong[t],
+                                             (u64 *)(scr + off_sel + (t ? stiles[0] * 8 : 0)), &h->counter[t], h->hist[t], &h->count[t]);
+            if (rc != SMJ_OK) break;
+            PIPE_CUDA(smj_event_record(c->ev[E_SELECT], c->stream));
+            // sort: 4 onesweep passes per table over the device-resident survivor counts
+            for (int t = 0; t < 2 && rc == SMJ_OK; t++)
+                rc = smj_radix_sort_pairs(c, ping[t], pong[t], &h->count[t], (u32)n[t], h->hist[t], (u32 *)(scr + off_radix + (t ? rb[0] : 0)));
+            if (rc != SMJ_OK) break;
+            PIPE_CUDA(smj_event_record(c->ev[E_SORT], c->stream));
+            // join: co-rank, count, scan, compact the matches; then materialise rows straight from the input tables
+            const JoinScratch jsr = join_scratch(scr + off_join, jt);
+            PIPE_TRY(smj_launch_join_match(c, ping[0], ping[1], &h->count[0], (u32)n[0], (u32)n[1], SMJ_JOIN_ZIP, jsr.part, jsr.tile_count,
+                                           jsr.tile_off, mm, md, &h->jcount));
+            PIPE_TRY(smj_launch_join_materialize(c, md, &h->jcount, j_max, d_t[0], cc[0], d_t[1], cc[1], key[1], nullptr, c->d_out_ptr));
+#undef PIPE_TRY
+#undef PIPE_CUDA
+        } while (0);
+        if (capture) {
+            cudaGraph_t g = nullptr;
+            cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+            if (rc == SMJ_OK && e != cudaSuccess) rc = smj_cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+            if (rc == SMJ_OK) {
+                e = cudaGraphInstantiate(&c->graph_exec, g, 0);
+                if (e != cudaSuccess) { c->graph_exec = nullptr; rc = smj_cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__); }
+            }
+            if (g) cudaGraphDestroy(g);
+            c->graph_launches = c->launches - l0;
+            c->launches = l0;   // counted again when the graph is launched below
+        }
+        if (rc != SMJ_OK) { cudaGetLastError(); smj_table_free(&dev_out); return rc; }
+    }
+    if (replay || capture) {
+        CUDA_TRY(cudaGraphLaunch(c->graph_exec, c->stream));
+        c->launches += c->graph_launches;
+        c->pass_count = 2;   // the two timed sort groups are event-record nodes of the graph
     }
     CUDA_TRY(cudaEventRecord(c->ev[E_JOIN], c->stream));
 

@@ -35,6 +35,13 @@ struct SmjCtx {
     int pass_count = 0;
     bool radix_attr_set = false;
     bool select_attr_set = false;
+    // CUDA-graph replay of the smj_run device pipeline (same tables, shapes and knobs as the previous call)
+    u64 ws_gen = 0;                  // bumped whenever a workspace slot is (re)allocated
+    u64 graph_key[16] = {};
+    int graph_seen = 0;              // consecutive calls with this key: 1st runs eagerly, 2nd captures, later ones replay
+    cudaGraphExec_t graph_exec = nullptr;
+    int64_t graph_launches = 0;      // kernels inside the captured pipeline
+    int32_t **d_out_ptr = nullptr;   // device cell holding the output pointer the materialise kernel writes through
 };
 
 enum SmjSlot {
@@ -56,6 +63,15 @@ void *smj_ws(SmjCtx *c, int slot, size_t bytes);     // nullptr on failure (erro
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return smj_cuda_fail(e_, #x, __FILE__, __LINE__); } while (0)
 #define SMJ_TRY(x)  do { int r_ = (x); if (r_ != SMJ_OK) return r_; } while (0)
 #define KERNEL_CHECK(c) do { (c)->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return smj_cuda_fail(e_, "kernel launch", __FILE__, __LINE__); } while (0)
+
+// cudaEventRecord that also works while the stream is being captured into a graph (becomes an event-record node)
+static inline cudaError_t smj_event_record(cudaEvent_t ev, cudaStream_t st)
+{
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive)
+        return cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal);
+    return cudaEventRecord(ev, st);
+}
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -110,8 +126,9 @@ size_t smj_join_tile_size(void);
 int smj_launch_join_match(SmjCtx *c, const u64 *d_l, const u64 *d_r, const u64 *d_counts, u32 m1_max, u32 m2_max, int mode,
                           u32 *d_part, u32 *d_tile_count, u64 *d_tile_off, uint2 *d_matches, uint2 *d_dense, u64 *d_count);
 // d_nj: device match count or null (then nj_max is exact)
+// d_out_indirect (may be null): device cell holding the output pointer, read instead of d_out (graph replay)
 int smj_launch_join_materialize(SmjCtx *c, const uint2 *d_dense, const u64 *d_nj, int64_t nj_max, const int32_t *d_t1, int c1,
-                                const int32_t *d_t2, int c2, int key2, int32_t *d_out);
+                                const int32_t *d_t2, int c2, int key2, int32_t *d_out, int32_t *const *d_out_indirect = nullptr);
 
 // ------------------------------------------------------------------ synth (smj_synth.cu)
 int smj_launch_synth(SmjCtx *c, int32_t *d_out, int64_t row0, int64_t rows, int64_t total_rows, int cols,

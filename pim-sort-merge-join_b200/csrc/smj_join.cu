@@ -305,9 +305,10 @@ template <bool VEC>
 __global__ void __launch_bounds__(MT_THREADS)
 join_materialize_kernel(const uint2 *__restrict__ matches, const u64 *__restrict__ nj_dev, int64_t nj_max,
                         const int32_t *__restrict__ t1, int c1, const int32_t *__restrict__ t2, int c2, int key2,
-                        int32_t *__restrict__ out, int rows_per_block)
+                        int32_t *__restrict__ out_direct, int32_t *const *__restrict__ out_indirect, int rows_per_block)
 {
     __shared__ __align__(16) int32_t s_out[MT_SMEM_CELLS];
+    int32_t *__restrict__ out = out_indirect ? *out_indirect : out_direct;
     int64_t nj = nj_max;
     if (nj_dev) { const u64 v = *nj_dev; nj = v < (u64)nj_max ? (int64_t)v : nj_max; }
     const int c_out = c1 + c2 - 1;
@@ -427,7 +428,7 @@ int smj_launch_join_match(SmjCtx *c, const u64 *d_l, const u64 *d_r, const u64 *
 
 // Joined rows from the dense match list (*d_nj of them, at most nj_max).
 int smj_launch_join_materialize(SmjCtx *c, const uint2 *d_dense, const u64 *d_nj, int64_t nj_max, const int32_t *d_t1, int c1,
-                                const int32_t *d_t2, int c2, int key2, int32_t *d_out)
+                                const int32_t *d_t2, int c2, int key2, int32_t *d_out, int32_t *const *d_out_indirect)
 {
     if (nj_max <= 0) return SMJ_OK;
     const int c_out = c1 + c2 - 1;
@@ -439,9 +440,9 @@ int smj_launch_join_materialize(SmjCtx *c, const uint2 *d_dense, const u64 *d_nj
     const u32 grid = (u32)(nblocks < (int64_t)sms * 6 ? nblocks : (int64_t)sms * 6);
     const bool vec = (c1 % 4 == 0) && (c2 % 4 == 0) && ((((uintptr_t)d_t1) | ((uintptr_t)d_t2)) & 15) == 0;
     if (vec)
-        join_materialize_kernel<true><<<grid, MT_THREADS, 0, c->stream>>>(d_dense, d_nj, nj_max, d_t1, c1, d_t2, c2, key2, d_out, rpb);
+        join_materialize_kernel<true><<<grid, MT_THREADS, 0, c->stream>>>(d_dense, d_nj, nj_max, d_t1, c1, d_t2, c2, key2, d_out, d_out_indirect, rpb);
     else
-        join_materialize_kernel<false><<<grid, MT_THREADS, 0, c->stream>>>(d_dense, d_nj, nj_max, d_t1, c1, d_t2, c2, key2, d_out, rpb);
+        join_materialize_kernel<false><<<grid, MT_THREADS, 0, c->stream>>>(d_dense, d_nj, nj_max, d_t1, c1, d_t2, c2, key2, d_out, d_out_indirect, rpb);
     KERNEL_CHECK(c);
     return SMJ_OK;
 }

@@ -322,14 +322,14 @@ int smj_radix_sort_pairs(SmjCtx *c, u64 *buf_a, u64 *buf_b, const u64 *d_n, u32 
     u64 *src = buf_a, *dst = buf_b;
     // one event pair around the four back-to-back passes (per-pass event records cost more stream time than they measure)
     const bool timed = c->pass_count < SmjCtx::kMaxTimedPasses;
-    if (timed) CUDA_TRY(cudaEventRecord(c->pass_ev[2 * c->pass_count], c->stream));
+    if (timed) CUDA_TRY(smj_event_record(c->pass_ev[2 * c->pass_count], c->stream));
     for (int p = 0; p < SMJ_KEY_PASSES; p++) {
         SMJ_TRY(smj_launch_radix_pass(c, src, dst, d_n, n_max, p, d_bases + p * SMJ_RADIX, d_status[p & 1], d_status[(p + 1) & 1],
                                       d_counters + p));
         u64 *t = src; src = dst; dst = t;
     }
     if (timed) {
-        CUDA_TRY(cudaEventRecord(c->pass_ev[2 * c->pass_count + 1], c->stream));
+        CUDA_TRY(smj_event_record(c->pass_ev[2 * c->pass_count + 1], c->stream));
         c->pass_items[c->pass_count] = n_max;
         c->pass_count++;
     }
