@@ -23,6 +23,7 @@
 #include "smj_dev.cuh"
 
 #include <dlfcn.h>
+#include <time.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -150,8 +151,11 @@ extern "C" int smj_plan_exchange(const int64_t *counts, int world, int me, int64
 // ------------------------------------------------------------------ init / shutdown
 bool smj_dist_active(void) { return g_dist.active; }
 
+static void peer_unmap_all();
+
 int smj_dist_shutdown(void)
 {
+    peer_unmap_all();
     if (g_dist.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g_dist.comm);
     g_dist = DistState();
     return SMJ_OK;
@@ -201,7 +205,275 @@ static float dist_ev_ms(cudaEvent_t a, cudaEvent_t b)
     return ms;
 }
 
+// ------------------------------------------------------------------ partition-first pipeline (default)
+bool smj_partition_supported(const int32_t *d_in, int cols);
+size_t smj_partition_scratch_bytes(int64_t n, int cols);
+int smj_launch_sample_rows(SmjCtx *c, const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val, int key_col, int S,
+                           u32 *d_samples);
+int smj_launch_select_partition(SmjCtx *c, const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val, int key_col,
+                                const u32 *d_splitters, int G, int32_t *d_slots, char *d_scratch, u64 **d_bucket_start);
+int smj_launch_partition_compact(SmjCtx *c, int64_t n, int cols, int sel_val_none, int G, const int32_t *d_slots, char *d_scratch,
+                                 int32_t *d_send, int32_t *const *d_dst_by_bucket);
+int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, smj_table_t *out, smj_stats_t *stats);
+static int smj_run_multi_sorted(const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, smj_table_t *out, smj_stats_t *stats);
+
+// Peer receive buffers mapped through CUDA IPC (one process per GPU on one box): g_peer[t][r] is rank r's receive buffer
+// of table t as seen from this process.  Re-mapped whenever the owner reallocated (its handle changed).
+struct PeerMap { void *base = nullptr; cudaIpcMemHandle_t handle; bool have = false; };
+static PeerMap g_peer[2][8];
+
+static void peer_unmap_all()
+{
+    for (int t = 0; t < 2; t++)
+        for (int r = 0; r < 8; r++) {
+            if (g_peer[t][r].base) cudaIpcCloseMemHandle(g_peer[t][r].base);
+            g_peer[t][r] = PeerMap();
+        }
+    cudaGetLastError();
+}
+
+// select + key-range partition of the ROWS (one streaming pass, smj_partition.cu) -> exchange -> the single-GPU pipeline
+// (sort + join, select disabled) on what arrived.  Compared with sorting first and merging the received runs
+// (smj_run_multi_sorted below, SMJ_DIST_MODE=merge) no row is gathered at random before it travels and there are no merge
+// rounds (0.51 ms per step at 8 GPUs).  The exchange itself is FUSED into the compaction kernel: each (tile, bucket)
+// segment is stored straight into the destination rank's receive buffer through a CUDA-IPC mapping, i.e. over NVLink
+// from the SMs (SMJ_DIST_EXCHANGE=nccl falls back to a send buffer + grouped ncclSend/ncclRecv, which reached 240 GB/s
+// per GPU here against ~770 GB/s for peer copies).
 int smj_run_multi(const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, smj_table_t *out, smj_stats_t *stats)
+{
+    if (!g_dist.active) return smj_set_error(SMJ_EINVAL, "nr_gpus > 1 needs one process per GPU: call smj_init_dist first (see INTEGRATION.md)");
+    if (cfg->join_mode != SMJ_JOIN_ZIP) return smj_set_error(SMJ_EINVAL, "smj_run materialises SMJ_JOIN_ZIP only (the reference semantics)");
+    const char *mode = getenv("SMJ_DIST_MODE");
+    if (mode && strcmp(mode, "merge") == 0) return smj_run_multi_sorted(cfg, t1, t2, out, stats);
+    const char *xmode = getenv("SMJ_DIST_EXCHANGE");
+    const bool use_peer = !(xmode && strcmp(xmode, "nccl") == 0);
+    SmjCtx *c = g_ctx[0];
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int G = g_dist.world, me = g_dist.rank;
+    const smj_table_t *tb[2] = {t1, t2};
+    const int sel_col[2] = {cfg->select_col1, cfg->select_col2};
+    const int64_t sel_val[2] = {cfg->select_val1, cfg->select_val2};
+    const int key[2] = {cfg->join_key1, cfg->join_key2};
+    for (int t = 0; t < 2; t++) {
+        if (sel_col[t] < 0 || sel_col[t] >= tb[t]->cols) return smj_set_error(SMJ_EINVAL, "SELECT_COL%d=%d out of range", t + 1, sel_col[t]);
+        if (key[t] < 0 || key[t] >= tb[t]->cols) return smj_set_error(SMJ_EINVAL, "JOIN_KEY%d=%d out of range", t + 1, key[t]);
+    }
+    const int64_t launches0 = c->launches;
+    enum { E_START, E_H2D, E_PART, E_XCHG, E_SAMP, E_SPLIT, E_CNT };
+    cudaEvent_t *ev = c->ev + 8;   // smj_run_single below uses c->ev[0..5]
+    static const bool trace = getenv("SMJ_DIST_TRACE") != nullptr;
+    CUDA_TRY(cudaEventRecord(ev[E_START], c->stream));
+    const int32_t *d_t[2];
+    SMJ_TRY(smj_stage_in(c, t1, WS_T1, &d_t[0]));
+    SMJ_TRY(smj_stage_in(c, t2, WS_T2, &d_t[1]));
+    const int cc[2] = {t1->cols, t2->cols};
+    if ((tb[0]->rows && !smj_partition_supported(d_t[0], cc[0])) || (tb[1]->rows && !smj_partition_supported(d_t[1], cc[1])))
+        return smj_run_multi_sorted(cfg, t1, t2, out, stats);   // > 32 columns or a table that is not 16-byte aligned
+    CUDA_TRY(cudaEventRecord(ev[E_H2D], c->stream));
+
+    // ---- 1. splitters: regular row samples of both tables on every rank (predicate applied), all-gathered
+    const int S = 1024;
+    const int MSG = 2 * (G + 1) + 2;                   // per-rank count message: bucket starts of both tables + receive capacities
+    u32 *d_samp = (u32 *)smj_ws(c, WS_SAMPLES, (size_t)(2 * S) * 4 * (G + 1) + 4096 + (size_t)MSG * 8 * (G + 1) + 1024);
+    if (!d_samp) return SMJ_ENOMEM;
+    u32 *d_samp_all = d_samp + 2 * S;
+    u32 *d_split = d_samp_all + (size_t)G * 2 * S;
+    u64 *d_msg = (u64 *)(d_split + 16);                // [MSG]
+    u64 *d_msg_all = d_msg + MSG;                      // [G][MSG]
+    int32_t **d_dst = (int32_t **)(d_msg_all + (size_t)G * MSG);   // [2][8] destination pointers per bucket
+    unsigned char *d_hnd = (unsigned char *)(d_dst + 16);          // [G+1][2][64] IPC handles
+    for (int t = 0; t < 2; t++)
+        SMJ_TRY(smj_launch_sample_rows(c, d_t[t], tb[t]->rows, cc[t], sel_col[t], sel_val[t], key[t], S, d_samp + t * S));
+    NCCL_TRY(g_nccl.AllGather(d_samp, d_samp_all, (size_t)2 * S, ncclUint32, g_dist.comm, c->stream));
+    CUDA_TRY(cudaEventRecord(ev[E_SAMP], c->stream));
+    char *hp = (char *)c->h_pinned;                    // pinned mailbox: [samples 64 KB would not fit] -> use vectors for big, pinned for small
+    std::vector<uint32_t> h_samp((size_t)G * 2 * S), h_split((size_t)std::max(G - 1, 1));
+    CUDA_TRY(cudaMemcpyAsync(h_samp.data(), d_samp_all, h_samp.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    SMJ_TRY(smj_plan_splitters(h_samp.data(), (int64_t)h_samp.size(), G, h_split.data()));
+    uint32_t *hp_split = (uint32_t *)(hp + 1024);
+    for (int b = 0; b + 1 < G; b++) hp_split[b] = h_split[b];
+    if (G > 1) CUDA_TRY(cudaMemcpyAsync(d_split, hp_split, (size_t)(G - 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaEventRecord(ev[E_SPLIT], c->stream));
+
+    // ---- 2. select + partition of the rows by destination rank (rows grouped by bucket inside every tile's slot)
+    int32_t *slots[2];
+    char *pscr[2];
+    u64 *d_bs[2];
+    int none[2];
+    for (int t = 0; t < 2; t++) {
+        const size_t cells = (size_t)tb[t]->rows * cc[t];
+        slots[t] = (int32_t *)smj_ws(c, t ? WS_TMP_ROWS2 : WS_TMP_ROWS, cells * 4);
+        pscr[t] = (char *)smj_ws(c, t ? WS_MERGE_B : WS_MERGE_A, smj_partition_scratch_bytes(tb[t]->rows, cc[t]));
+        if (!slots[t] || !pscr[t]) return SMJ_ENOMEM;
+        none[t] = (sel_val[t] >= (int64_t)INT32_MAX) ? 1 : 0;
+        SMJ_TRY(smj_launch_select_partition(c, d_t[t], tb[t]->rows, cc[t], sel_col[t], sel_val[t], key[t], d_split, G, slots[t], pscr[t], &d_bs[t]));
+        CUDA_TRY(cudaMemcpyAsync(d_msg + t * (G + 1), d_bs[t], (size_t)(G + 1) * 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    // receive capacities (rows) ride along so that every rank knows who must grow its buffer this step
+    uint64_t *hp_cap = (uint64_t *)(hp + 2048);
+    for (int t = 0; t < 2; t++) hp_cap[t] = (uint64_t)(c->slot_bytes[t ? WS_XCHG_RECV2 : WS_XCHG_RECV1] / ((size_t)cc[t] * 4));
+    CUDA_TRY(cudaMemcpyAsync(d_msg + 2 * (G + 1), hp_cap, 16, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaEventRecord(ev[E_PART], c->stream));
+
+    // ---- 3. the G x G row-count matrix
+    NCCL_TRY(g_nccl.AllGather(d_msg, d_msg_all, (size_t)MSG, ncclUint64, g_dist.comm, c->stream));
+    CUDA_TRY(cudaEventRecord(ev[E_CNT], c->stream));
+    uint64_t *h_msg = (uint64_t *)(hp + 4096);         // [G][MSG] <= 8 * 20 * 8 bytes
+    CUDA_TRY(cudaMemcpyAsync(h_msg, d_msg_all, (size_t)G * MSG * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    std::vector<int64_t> counts[2], recv_off[2];
+    int64_t recv_total[2], m[2];
+    bool someone_grows = false;
+    for (int t = 0; t < 2; t++) {
+        counts[t].assign((size_t)G * G, 0);
+        recv_off[t].assign((size_t)G, 0);
+        for (int src = 0; src < G; src++)
+            for (int dst = 0; dst < G; dst++) {
+                const uint64_t *b = h_msg + (size_t)src * MSG + (size_t)t * (G + 1);
+                counts[t][(size_t)src * G + dst] = (int64_t)(b[dst + 1] - b[dst]);
+            }
+        SMJ_TRY(smj_plan_exchange(counts[t].data(), G, me, recv_off[t].data(), &recv_total[t]));
+        m[t] = (int64_t)h_msg[(size_t)me * MSG + (size_t)t * (G + 1) + G];
+        if (recv_total[t] > SMJ_MAX_SORT_ROWS)
+            return smj_set_error(SMJ_ETOOBIG, "rank %d would receive %lld rows of table %d (limit 2^30 - 1 per GPU)", me, (long long)recv_total[t], t + 1);
+        for (int r = 0; r < G; r++) {                  // the same verdict on every rank: does rank r have to grow table t?
+            int64_t tot = 0;
+            for (int src = 0; src < G; src++) tot += counts[t][(size_t)src * G + r];
+            const uint64_t cap = h_msg[(size_t)r * MSG + 2 * (G + 1) + t];
+            if ((uint64_t)tot > cap || !g_peer[t][r].have) someone_grows = true;
+        }
+    }
+    int32_t *recv[2];
+    for (int t = 0; t < 2; t++) {
+        // 25 % head room so that a slightly different split next step does not force a re-map on every rank
+        const size_t want = (size_t)recv_total[t] * cc[t] * 4;
+        const int slot = t ? WS_XCHG_RECV2 : WS_XCHG_RECV1;
+        recv[t] = (int32_t *)smj_ws(c, slot, c->slot_bytes[slot] >= want ? want : want + want / 4);
+        if (!recv[t]) return SMJ_ENOMEM;
+    }
+
+    double sent_bytes = 0;
+    bool peer_ok = use_peer;
+    if (use_peer && someone_grows) {
+        // every rank publishes the IPC handles of its two receive buffers; peers map what changed
+        unsigned char *hp_h = (unsigned char *)(hp + 8192);        // [2][64] mine, then [G][2][64]
+        for (int t = 0; t < 2; t++) {
+            cudaIpcMemHandle_t hnd;
+            if (cudaIpcGetMemHandle(&hnd, recv[t]) != cudaSuccess) { cudaGetLastError(); memset(&hnd, 0, sizeof hnd); }
+            memcpy(hp_h + t * 64, &hnd, 64);
+        }
+        CUDA_TRY(cudaMemcpyAsync(d_hnd, hp_h, 128, cudaMemcpyHostToDevice, c->stream));
+        NCCL_TRY(g_nccl.AllGather(d_hnd, d_hnd + 128, 128, /*ncclUint8*/ 1, g_dist.comm, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(hp_h + 128, d_hnd + 128, (size_t)G * 128, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        for (int r = 0; r < G; r++)
+            for (int t = 0; t < 2; t++) {
+                PeerMap &pm = g_peer[t][r];
+                const unsigned char *hb = hp_h + 128 + (size_t)r * 128 + t * 64;
+                if (r == me) { pm.have = true; pm.base = nullptr; continue; }
+                if (pm.have && memcmp(&pm.handle, hb, 64) == 0) continue;
+                if (pm.base) { cudaIpcCloseMemHandle(pm.base); pm.base = nullptr; }
+                memcpy(&pm.handle, hb, 64);
+                cudaError_t e = cudaIpcOpenMemHandle(&pm.base, pm.handle, cudaIpcMemLazyEnablePeerAccess);
+                pm.have = (e == cudaSuccess);
+                if (e != cudaSuccess) { cudaGetLastError(); pm.base = nullptr; peer_ok = false; }
+            }
+        // all ranks must agree on the path: one failed mapping anywhere sends everybody to NCCL for this step
+        uint64_t *hp_ok = (uint64_t *)(hp + 3072);
+        *hp_ok = peer_ok ? 1 : 0;
+        CUDA_TRY(cudaMemcpyAsync(d_msg, hp_ok, 8, cudaMemcpyHostToDevice, c->stream));
+        NCCL_TRY(g_nccl.AllGather(d_msg, d_msg_all, 1, ncclUint64, g_dist.comm, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(h_msg, d_msg_all, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        for (int r = 0; r < G; r++) if (!h_msg[r]) peer_ok = false;
+        if (!peer_ok) for (int t = 0; t < 2; t++) for (int r = 0; r < G; r++) g_peer[t][r].have = false;   // try again next step
+    }
+
+    if (peer_ok) {
+        // ---- 4a. fused compaction + exchange: segments are stored straight into the owners' receive buffers (NVLink)
+        int32_t **hp_dst = (int32_t **)(hp + 3200);
+        for (int t = 0; t < 2; t++)
+            for (int b = 0; b < 8; b++) {
+                int32_t *p = nullptr;
+                if (b < G) {
+                    int64_t before = 0;                              // rows the lower ranks put in front of mine at rank b
+                    for (int src = 0; src < me; src++) before += counts[t][(size_t)src * G + b];
+                    int32_t *base = (b == me) ? recv[t] : (int32_t *)g_peer[t][b].base;
+                    p = base + (size_t)before * cc[t];
+                    if (b != me) sent_bytes += (double)counts[t][(size_t)me * G + b] * cc[t] * 4;
+                }
+                hp_dst[t * 8 + b] = p;
+            }
+        CUDA_TRY(cudaMemcpyAsync(d_dst, hp_dst, 16 * sizeof(int32_t *), cudaMemcpyHostToDevice, c->stream));
+        for (int t = 0; t < 2; t++)
+            SMJ_TRY(smj_launch_partition_compact(c, tb[t]->rows, cc[t], none[t], G, slots[t], pscr[t], nullptr, d_dst + t * 8));
+        // every rank's stores must have landed before anybody sorts: a collective after the kernels is that barrier
+        NCCL_TRY(g_nccl.AllGather(d_msg, d_msg_all, 1, ncclUint64, g_dist.comm, c->stream));
+    } else {
+        // ---- 4b. send buffer + one grouped ncclSend/ncclRecv all-to-all
+        int32_t *send[2];
+        for (int t = 0; t < 2; t++) {
+            send[t] = (int32_t *)smj_ws(c, t ? WS_XCHG_SEND2 : WS_XCHG_SEND1, (size_t)tb[t]->rows * cc[t] * 4);
+            if (!send[t]) return SMJ_ENOMEM;
+            SMJ_TRY(smj_launch_partition_compact(c, tb[t]->rows, cc[t], none[t], G, slots[t], pscr[t], send[t], nullptr));
+        }
+        NCCL_TRY(g_nccl.GroupStart());
+        for (int t = 0; t < 2; t++) {
+            const uint64_t *mine = h_msg + (size_t)me * MSG + (size_t)t * (G + 1);
+            for (int peer = 0; peer < G; peer++) {
+                const int64_t scount = counts[t][(size_t)me * G + peer] * cc[t];
+                const int64_t rcount = counts[t][(size_t)peer * G + me] * cc[t];
+                const int32_t *sbuf = send[t] + (size_t)mine[peer] * cc[t];
+                int32_t *rbuf = recv[t] + (size_t)recv_off[t][peer] * cc[t];
+                if (peer == me) {
+                    if (scount) CUDA_TRY(cudaMemcpyAsync(rbuf, sbuf, (size_t)scount * 4, cudaMemcpyDeviceToDevice, c->stream));
+                    continue;
+                }
+                if (scount) { NCCL_TRY(g_nccl.Send(sbuf, (size_t)scount, ncclInt32, peer, g_dist.comm, c->stream)); sent_bytes += (double)scount * 4; }
+                if (rcount) NCCL_TRY(g_nccl.Recv(rbuf, (size_t)rcount, ncclInt32, peer, g_dist.comm, c->stream));
+            }
+        }
+        NCCL_TRY(g_nccl.GroupEnd());
+    }
+    CUDA_TRY(cudaEventRecord(ev[E_XCHG], c->stream));
+
+    // ---- 5. this rank's key range: the single-GPU pipeline on the received rows, select disabled.  Runs arrived in
+    // source-rank order with original order inside each, so the stable sort reproduces the reference's order.
+    smj_config_t local = *cfg;
+    local.nr_gpus = 1;
+    local.select_col1 = 0; local.select_col2 = 0;
+    local.select_val1 = INT64_MIN; local.select_val2 = INT64_MIN;
+    const smj_table_t r1 = {recv[0], recv_total[0], cc[0], 1}, r2 = {recv[1], recv_total[1], cc[1], 1};
+    smj_stats_t ls;
+    SMJ_TRY(smj_run_single(c, &local, &r1, &r2, out, &ls));
+    if (trace && me == 0)
+        fprintf(stderr, "[dist] %s exchange; dev ms: samples+allgather %.3f | splitters %.3f | select/partition %.3f | counts %.3f | compaction+exchange %.3f | local %.3f\n",
+                peer_ok ? "peer-store" : "nccl", dist_ev_ms(ev[E_H2D], ev[E_SAMP]), dist_ev_ms(ev[E_SAMP], ev[E_SPLIT]),
+                dist_ev_ms(ev[E_SPLIT], ev[E_PART]), dist_ev_ms(ev[E_PART], ev[E_CNT]), dist_ev_ms(ev[E_CNT], ev[E_XCHG]), ls.total_device_ms);
+    if (cfg->debug) {
+        printf("==================\n#   exchange.cu  #\n==================\n");
+        for (int t = 0; t < 2; t++)
+            printf("Table %d - GPU %d selected %lld rows, owns %lld rows after the key-range exchange\n", t, me, (long long)m[t], (long long)recv_total[t]);
+        printf("####################\n\n");
+    }
+    if (stats) {
+        *stats = ls;
+        stats->h2d_ms = dist_ev_ms(ev[E_START], ev[E_H2D]);
+        stats->select_ms = dist_ev_ms(ev[E_H2D], ev[E_PART]);          // samples + splitters + select/partition of both tables
+        stats->exchange_ms = dist_ev_ms(ev[E_PART], ev[E_XCHG]);       // count all-gather + compaction/exchange
+        stats->sort_ms = ls.select_ms + ls.sort_ms;                     // pairs of the received rows + the four passes
+        stats->merge_ms = 0;
+        stats->total_device_ms = dist_ev_ms(ev[E_H2D], c->ev[4]);      // through smj_run_single's end-of-join event
+        for (int t = 0; t < 2; t++) { stats->rows_in[t] = tb[t]->rows; stats->rows_selected[t] = m[t]; }
+        stats->bytes_nvlink = sent_bytes;
+        stats->kernel_launches = c->launches - launches0;
+    }
+    return SMJ_OK;
+}
+
+// ------------------------------------------------------------------ sort-first pipeline (SMJ_DIST_MODE=merge)
+static int smj_run_multi_sorted(const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, smj_table_t *out, smj_stats_t *stats)
 {
     if (!g_dist.active) return smj_set_error(SMJ_EINVAL, "nr_gpus > 1 needs one process per GPU: call smj_init_dist first (see INTEGRATION.md)");
     if (cfg->join_mode != SMJ_JOIN_ZIP) return smj_set_error(SMJ_EINVAL, "smj_run materialises SMJ_JOIN_ZIP only (the reference semantics)");

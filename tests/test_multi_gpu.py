@@ -60,14 +60,22 @@ def _ngpus():
     return smj_b200.lib().smj_device_count()
 
 
-@pytest.mark.parametrize("world", [2, 4])
+# path: default = select+partition, exchange fused into the compaction kernel over CUDA-IPC peer memory;
+#       "nccl" = same partitioning, send buffer + grouped ncclSend/ncclRecv; "merge" = sort first, exchange, merge-path merge tree
+@pytest.mark.parametrize("world,path", [(2, "peer"), (2, "nccl"), (2, "merge"), (4, "peer"), (4, "merge")])
 @pytest.mark.parametrize("case", ["unique", "dups", "tiny"])
-def test_key_range_join_matches_single_process_oracle(case, world, tmp_path):
+def test_key_range_join_matches_single_process_oracle(case, world, path, tmp_path):
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     env = dict(os.environ, SMJ_ROOT=ROOT, SMJ_CASE=case)
+    env.pop("SMJ_DIST_MODE", None)
+    env.pop("SMJ_DIST_EXCHANGE", None)
+    if path == "nccl":
+        env["SMJ_DIST_EXCHANGE"] = "nccl"
+    if path == "merge":
+        env["SMJ_DIST_MODE"] = "merge"
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                         "--master-port", str(29700 + world), str(script)], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
