@@ -214,6 +214,7 @@ int smj_launch_select_partition(SmjCtx *c, const int32_t *d_in, int64_t n, int c
                                 const u32 *d_splitters, int G, int32_t *d_slots, char *d_scratch, u64 **d_bucket_start);
 int smj_launch_partition_compact(SmjCtx *c, int64_t n, int cols, int sel_val_none, int G, const int32_t *d_slots, char *d_scratch,
                                  int32_t *d_send, int32_t *const *d_dst_by_bucket);
+int smj_launch_splitters(SmjCtx *c, const u32 *d_samples, int n_samples, int G, u32 *d_splitters);
 int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, smj_table_t *out, smj_stats_t *stats);
 static int smj_run_multi_sorted(const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, smj_table_t *out, smj_stats_t *stats);
 
@@ -272,7 +273,7 @@ int smj_run_multi(const smj_config_t *cfg, const smj_table_t *t1, const smj_tabl
     CUDA_TRY(cudaEventRecord(ev[E_H2D], c->stream));
 
     // ---- 1. splitters: regular row samples of both tables on every rank (predicate applied), all-gathered
-    const int S = 1024;
+    const int S = G <= 4 ? 1024 : 4096 / G;          // <= 8192 samples in all: one CTA sorts them in shared memory
     const int MSG = 2 * (G + 1) + 2;                   // per-rank count message: bucket starts of both tables + receive capacities
     u32 *d_samp = (u32 *)smj_ws(c, WS_SAMPLES, (size_t)(2 * S) * 4 * (G + 1) + 4096 + (size_t)MSG * 8 * (G + 1) + 1024);
     if (!d_samp) return SMJ_ENOMEM;
@@ -286,14 +287,8 @@ int smj_run_multi(const smj_config_t *cfg, const smj_table_t *t1, const smj_tabl
         SMJ_TRY(smj_launch_sample_rows(c, d_t[t], tb[t]->rows, cc[t], sel_col[t], sel_val[t], key[t], S, d_samp + t * S));
     NCCL_TRY(g_nccl.AllGather(d_samp, d_samp_all, (size_t)2 * S, ncclUint32, g_dist.comm, c->stream));
     CUDA_TRY(cudaEventRecord(ev[E_SAMP], c->stream));
-    char *hp = (char *)c->h_pinned;                    // pinned mailbox: [samples 64 KB would not fit] -> use vectors for big, pinned for small
-    std::vector<uint32_t> h_samp((size_t)G * 2 * S), h_split((size_t)std::max(G - 1, 1));
-    CUDA_TRY(cudaMemcpyAsync(h_samp.data(), d_samp_all, h_samp.size() * 4, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    SMJ_TRY(smj_plan_splitters(h_samp.data(), (int64_t)h_samp.size(), G, h_split.data()));
-    uint32_t *hp_split = (uint32_t *)(hp + 1024);
-    for (int b = 0; b + 1 < G; b++) hp_split[b] = h_split[b];
-    if (G > 1) CUDA_TRY(cudaMemcpyAsync(d_split, hp_split, (size_t)(G - 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    char *hp = (char *)c->h_pinned;                    // small pinned mailbox for the host legs below
+    SMJ_TRY(smj_launch_splitters(c, d_samp_all, G * 2 * S, G, d_split));   // same samples, same kernel, same splitters on every rank
     CUDA_TRY(cudaEventRecord(ev[E_SPLIT], c->stream));
 
     // ---- 2. select + partition of the rows by destination rank (rows grouped by bucket inside every tile's slot)

@@ -239,6 +239,46 @@ __global__ void sample_rows_kernel(const int32_t *__restrict__ in, int64_t n, in
     samples[i] = v;
 }
 
+// Device twin of smj_plan_splitters (smj_dist.cu): sort the gathered samples (one CTA, bitonic in shared memory), drop the
+// "none" marks (0xffffffff sorts last), splitter b = sample at quantile b/G.  Every rank runs it on the same gathered
+// samples, so every rank gets the same splitters without a host round trip.
+constexpr int SPL_THREADS = 1024;
+__global__ void __launch_bounds__(SPL_THREADS) splitters_kernel(const u32 *__restrict__ samples, int n_samples, int n_pow2, int G, u32 *splitters)
+{
+    extern __shared__ u32 s_s[];
+    __shared__ int s_valid;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_valid = 0;
+    for (int i = tid; i < n_pow2; i += SPL_THREADS) s_s[i] = i < n_samples ? samples[i] : 0xffffffffu;
+    __syncthreads();
+    for (int k = 2; k <= n_pow2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n_pow2; i += SPL_THREADS) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const u32 a = s_s[i], b = s_s[p];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { s_s[i] = b; s_s[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    int local = 0;
+    for (int i = tid; i < n_pow2; i += SPL_THREADS) local += s_s[i] != 0xffffffffu;
+    atomicAdd(&s_valid, local);
+    __syncthreads();
+    const int nv = s_valid;
+    if (tid >= 1 && tid < G) {
+        u32 v = 0xffffffffu;
+        if (nv > 0) {
+            long long pos = (long long)tid * nv / G;
+            if (pos >= nv) pos = nv - 1;
+            v = s_s[pos];
+        }
+        splitters[tid - 1] = v;
+    }
+}
+
 int pt_ipt(int cols)
 {
     int ipt = PT_IPT;
@@ -312,6 +352,23 @@ int smj_launch_partition_compact(SmjCtx *c, int64_t n, int cols, int sel_val_non
     const u32 cgrid = (u32)((segs + 7) / 8 < (u64)sms * 8 ? (segs + 7) / 8 : (u64)sms * 8);
     partition_compact_kernel<<<cgrid, 256, 0, c->stream>>>(d_slots, d_counts, d_off, d_bs, (u32)tiles, G, (u32)(pt_ipt(cols) * PT_THREADS), cols,
                                                            d_send, d_dst_by_bucket);
+    KERNEL_CHECK(c);
+    return SMJ_OK;
+}
+
+// splitters[0..G-2] from n_samples gathered samples (<= 16384), on the device
+int smj_launch_splitters(SmjCtx *c, const u32 *d_samples, int n_samples, int G, u32 *d_splitters)
+{
+    if (G <= 1) return SMJ_OK;
+    int p2 = 1;
+    while (p2 < n_samples) p2 <<= 1;
+    if (p2 > 16384) return smj_set_error(SMJ_EINVAL, "smj_launch_splitters: %d samples (max 16384)", n_samples);
+    static bool attr_set[16] = {};
+    if (!attr_set[c->device & 15]) {
+        CUDA_TRY(cudaFuncSetAttribute(splitters_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 4));
+        attr_set[c->device & 15] = true;
+    }
+    splitters_kernel<<<1, SPL_THREADS, (size_t)p2 * 4, c->stream>>>(d_samples, n_samples, p2, G, d_splitters);
     KERNEL_CHECK(c);
     return SMJ_OK;
 }
