@@ -99,6 +99,9 @@ int smj_launch_radix_pass(SmjCtx *c, const u64 *d_in, u64 *d_out, const u64 *d_n
 // buf_a (four passes).  d_hist: the 4x256 digit histogram of those pairs (device).  No host synchronisation.
 int smj_radix_sort_pairs(SmjCtx *c, u64 *buf_a, u64 *buf_b, const u64 *d_n, u32 n_max, const u32 *d_hist,
                          u32 *d_scratch /*smj_radix_scratch_bytes(n_max), zero*/);
+// the same for one or two pair arrays in the same four launches (their tiles share the CTAs of each launch)
+int smj_radix_sort_pairs_n(SmjCtx *c, int nprob, u64 *const *buf_a, u64 *const *buf_b, const u64 *const *d_n, const u32 *n_max,
+                           const u32 *const *d_hist, u32 *const *d_scratch);
 size_t smj_radix_scratch_bytes(u32 n);         // bases + status(4 passes) + counters, all zero-initialised by caller
 
 // ------------------------------------------------------------------ gather (smj_gather.cu)

@@ -83,9 +83,21 @@ __device__ __forceinline__ void radix_rank_tile(const u64 (&item)[RS_IPT], u32 s
     }
 }
 
+// One sort problem of a pass (one table's pair array).  A launch covers up to two of them: their tiles share one
+// ticket space (table 1's tiles first), so the CTAs run 2x as many tiles per launch and the wave-quantisation loss
+// (2.06 tiles per CTA = 3 tile times at the 10M-row config) is halved; every problem keeps its own look-back chain.
+struct RadixProblem {
+    const u64 *in;
+    u64 *out;
+    const u64 *n_dev;      // device count or null
+    u32 n_max;
+    const u32 *bin_base;   // [256] first output slot of each digit
+    u32 *status, *status_next;
+};
+struct RadixLaunch { RadixProblem p[2]; int nprob; };
+
 __global__ void __launch_bounds__(RS_THREADS, 2)
-radix_pass_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const u64 *__restrict__ n_dev, u32 n_max, int pass,
-                  const u32 *__restrict__ bin_base, u32 *status, u32 *status_next, u32 *tile_counter, u32 *err)
+radix_pass_kernel(const RadixLaunch L, int pass, u32 *tile_counter, u32 *err)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *s_items = reinterpret_cast<u64 *>(smem_raw);              // RS_TILE, tile in digit order
@@ -98,29 +110,48 @@ radix_pass_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const u64 *
     const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
     const u32 lt = lanemask_lt();
     const u32 sel = 0x4440u | (u32)pass;
-    u64 n64 = n_dev ? *n_dev : (u64)n_max;
-    const u32 n = n64 < (u64)n_max ? (u32)n64 : n_max;
-    const u32 num_tiles = (n + RS_TILE - 1) / RS_TILE;
+    // sizes of both problems (device-resident counts), and the shared ticket space [0, tiles0) [tiles0, tiles0 + tiles1)
+    u32 n0, n1 = 0;
+    {
+        const u64 v = L.p[0].n_dev ? *L.p[0].n_dev : (u64)L.p[0].n_max;
+        n0 = v < (u64)L.p[0].n_max ? (u32)v : L.p[0].n_max;
+        if (L.nprob > 1) {
+            const u64 v1 = L.p[1].n_dev ? *L.p[1].n_dev : (u64)L.p[1].n_max;
+            n1 = v1 < (u64)L.p[1].n_max ? (u32)v1 : L.p[1].n_max;
+        }
+    }
+    const u32 tiles0 = (n0 + RS_TILE - 1) / RS_TILE;
+    const u32 all_tiles = tiles0 + (n1 + RS_TILE - 1) / RS_TILE;
 
     if (tid == 0) s_tile[0] = atomicAdd(tile_counter, 1u);
     for (u32 i = tid; i < RS_WARPS * SMJ_RADIX; i += RS_THREADS) s_mask[i] = 0;
     __syncthreads();
-    u32 tile = s_tile[0];
+    u32 ticket = s_tile[0];
     int par = 0;
 
     // warp-striped layout: element order inside the tile is (warp, j, lane) == ascending index
     const u32 rel0 = w * 32 * RS_IPT + lane;   // tile-relative index of item[0]
     u64 item[RS_IPT];
-    if (tile < num_tiles) {
-        const u32 g0 = tile * RS_TILE + rel0;
+    if (ticket < all_tiles) {
+        const bool second = ticket >= tiles0;
+        const u64 *src_in = second ? L.p[1].in : L.p[0].in;
+        const u32 nn = second ? n1 : n0;
+        const u32 g0 = (second ? ticket - tiles0 : ticket) * RS_TILE + rel0;
 #pragma unroll
-        for (int j = 0; j < RS_IPT; j++) item[j] = (g0 + j * 32 < n) ? in[g0 + j * 32] : 0ull;
+        for (int j = 0; j < RS_IPT; j++) item[j] = (g0 + j * 32 < nn) ? src_in[g0 + j * 32] : 0ull;
     }
 
     u32 *my_cnt = s_wcnt + w * SMJ_RADIX;
     u32 *my_mask = s_mask + w * SMJ_RADIX;
     PHASE_INIT();
-    while (tile < num_tiles) {
+    while (ticket < all_tiles) {
+        const bool second = ticket >= tiles0;
+        const RadixProblem &P = second ? L.p[1] : L.p[0];
+        const u32 n = second ? n1 : n0;
+        const u32 tile = second ? ticket - tiles0 : ticket;
+        u64 *__restrict__ out = P.out;
+        const u32 *__restrict__ bin_base = P.bin_base;
+        u32 *status = P.status, *status_next = P.status_next;
         const u32 base = tile * RS_TILE;
         const u32 valid = (n - base < (u32)RS_TILE) ? (n - base) : (u32)RS_TILE;
         const bool full = valid == (u32)RS_TILE;
@@ -209,10 +240,13 @@ radix_pass_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const u64 *
         // ---- issue the next tile's loads, then copy this tile out while they are in flight
         const u32 next = s_tile[par ^ 1];
         par ^= 1;
-        if (next < num_tiles) {
-            const u32 g0 = next * RS_TILE + rel0;
+        if (next < all_tiles) {
+            const bool nsecond = next >= tiles0;
+            const u64 *src_in = nsecond ? L.p[1].in : L.p[0].in;
+            const u32 nn = nsecond ? n1 : n0;
+            const u32 g0 = (nsecond ? next - tiles0 : next) * RS_TILE + rel0;
 #pragma unroll
-            for (int j = 0; j < RS_IPT; j++) item[j] = (g0 + j * 32 < n) ? in[g0 + j * 32] : 0ull;
+            for (int j = 0; j < RS_IPT; j++) item[j] = (g0 + j * 32 < nn) ? src_in[g0 + j * 32] : 0ull;
         }
 #pragma unroll
         for (int k = 0; k < RS_IPT; k++) {
@@ -223,7 +257,7 @@ radix_pass_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, const u64 *
             }
         }
         PHASE(6);   // next loads issued + copy-out
-        tile = next;
+        ticket = next;
         // the __syncthreads after the counter reset at the loop top orders these reads before the next reorder
     }
 }
@@ -291,8 +325,7 @@ int smj_launch_radix_scan(SmjCtx *c, const u32 *d_hist, u32 *d_bases)
     return SMJ_OK;
 }
 
-int smj_launch_radix_pass(SmjCtx *c, const u64 *d_in, u64 *d_out, const u64 *d_n, u32 n_max, int pass,
-                          const u32 *d_bases_pass, u32 *d_status, u32 *d_status_next, u32 *d_tile_counter)
+static int launch_radix_pass(SmjCtx *c, const RadixLaunch &L, int pass, u32 *d_tile_counter)
 {
     if (!c->radix_attr_set) {   // function attributes are per device
         CUDA_TRY(cudaFuncSetAttribute(radix_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
@@ -300,38 +333,71 @@ int smj_launch_radix_pass(SmjCtx *c, const u64 *d_in, u64 *d_out, const u64 *d_n
     }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    const u32 tiles = (u32)smj_radix_num_tiles(n_max);
-    const u32 grid = tiles < (u32)(sms * 2) ? tiles : (u32)(sms * 2);
-    radix_pass_kernel<<<grid, RS_THREADS, RS_SMEM, c->stream>>>(d_in, d_out, d_n, n_max, pass,
-                                                                d_bases_pass, d_status, d_status_next, d_tile_counter, c->d_err);
+    size_t tiles = 0;
+    for (int i = 0; i < L.nprob; i++) tiles += smj_radix_num_tiles(L.p[i].n_max);
+    if (tiles == 0) return SMJ_OK;
+    const u32 grid = tiles < (size_t)(sms * 2) ? (u32)tiles : (u32)(sms * 2);
+    radix_pass_kernel<<<grid, RS_THREADS, RS_SMEM, c->stream>>>(L, pass, d_tile_counter, c->d_err);
     KERNEL_CHECK(c);
     return SMJ_OK;
 }
 
-// Stable LSD sort of the first *d_n (<= n_max) pairs of buf_a by their key half; buf_b is the ping-pong partner.
-// Four passes, so the result is back in buf_a.  Nothing here waits for the host: the pair count is read on the
-// device, and a digit every key shares costs one identity-permutation pass instead of a host round trip.
-int smj_radix_sort_pairs(SmjCtx *c, u64 *buf_a, u64 *buf_b, const u64 *d_n, u32 n_max, const u32 *d_hist, u32 *d_scratch)
+int smj_launch_radix_pass(SmjCtx *c, const u64 *d_in, u64 *d_out, const u64 *d_n, u32 n_max, int pass,
+                          const u32 *d_bases_pass, u32 *d_status, u32 *d_status_next, u32 *d_tile_counter)
 {
-    if (n_max < 2) return SMJ_OK;
-    if (n_max > SMJ_MAX_SORT_ROWS) return smj_set_error(SMJ_ETOOBIG, "radix sort of %u pairs exceeds 2^30 - 1", n_max);
-    u32 *d_bases = d_scratch;
-    u32 *d_counters = d_scratch + SMJ_KEY_PASSES * SMJ_RADIX;
-    u32 *d_status[2] = {d_counters + 16, d_counters + 16 + smj_radix_status_words(n_max)};
-    SMJ_TRY(smj_launch_radix_scan(c, d_hist, d_bases));
-    u64 *src = buf_a, *dst = buf_b;
+    RadixLaunch L = {};
+    L.nprob = 1;
+    L.p[0] = {d_in, d_out, d_n, n_max, d_bases_pass, d_status, d_status_next};
+    return launch_radix_pass(c, L, pass, d_tile_counter);
+}
+
+// Stable LSD sort of one or two pair arrays at once (problem i: the first *d_n[i] (<= n_max[i]) pairs of buf_a[i], buf_b[i]
+// its ping-pong partner, d_hist[i] its 4x256 digit histogram, d_scratch[i] smj_radix_scratch_bytes(n_max[i]) zeroed bytes).
+// Four passes, so each result is back in buf_a[i].  Nothing here waits for the host: the pair counts are read on the
+// device, and a digit every key shares costs one identity-permutation pass instead of a host round trip.
+int smj_radix_sort_pairs_n(SmjCtx *c, int nprob, u64 *const *buf_a, u64 *const *buf_b, const u64 *const *d_n, const u32 *n_max,
+                           const u32 *const *d_hist, u32 *const *d_scratch)
+{
+    if (nprob < 1 || nprob > 2) return smj_set_error(SMJ_EINVAL, "radix sort of %d arrays at once (1 or 2)", nprob);
+    u32 *d_bases[2], *d_counters[2], *d_status[2][2];
+    u64 *src[2], *dst[2];
+    int live = 0, idx[2];
+    for (int i = 0; i < nprob; i++) {
+        if (n_max[i] > SMJ_MAX_SORT_ROWS) return smj_set_error(SMJ_ETOOBIG, "radix sort of %u pairs exceeds 2^30 - 1", n_max[i]);
+        if (n_max[i] < 2) continue;
+        d_bases[live] = d_scratch[i];
+        d_counters[live] = d_scratch[i] + SMJ_KEY_PASSES * SMJ_RADIX;
+        d_status[live][0] = d_counters[live] + 16;
+        d_status[live][1] = d_counters[live] + 16 + smj_radix_status_words(n_max[i]);
+        src[live] = buf_a[i]; dst[live] = buf_b[i];
+        SMJ_TRY(smj_launch_radix_scan(c, d_hist[i], d_bases[live]));
+        idx[live++] = i;
+    }
+    if (live == 0) return SMJ_OK;
     // one event pair around the four back-to-back passes (per-pass event records cost more stream time than they measure)
     const bool timed = c->pass_count < SmjCtx::kMaxTimedPasses;
     if (timed) CUDA_TRY(smj_event_record(c->pass_ev[2 * c->pass_count], c->stream));
     for (int p = 0; p < SMJ_KEY_PASSES; p++) {
-        SMJ_TRY(smj_launch_radix_pass(c, src, dst, d_n, n_max, p, d_bases + p * SMJ_RADIX, d_status[p & 1], d_status[(p + 1) & 1],
-                                      d_counters + p));
-        u64 *t = src; src = dst; dst = t;
+        RadixLaunch L = {};
+        L.nprob = live;
+        for (int k = 0; k < live; k++) {
+            const int i = idx[k];
+            L.p[k] = {src[k], dst[k], d_n[i], n_max[i], d_bases[k] + p * SMJ_RADIX, d_status[k][p & 1], d_status[k][(p + 1) & 1]};
+        }
+        SMJ_TRY(launch_radix_pass(c, L, p, d_counters[0] + p));   // the shared ticket counter lives in the first problem's scratch
+        for (int k = 0; k < live; k++) { u64 *t = src[k]; src[k] = dst[k]; dst[k] = t; }
     }
     if (timed) {
         CUDA_TRY(smj_event_record(c->pass_ev[2 * c->pass_count + 1], c->stream));
-        c->pass_items[c->pass_count] = n_max;
+        u64 items = 0;
+        for (int k = 0; k < live; k++) items += n_max[idx[k]];
+        c->pass_items[c->pass_count] = (u32)(items > 0xffffffffull ? 0xffffffffull : items);
         c->pass_count++;
     }
     return SMJ_OK;
+}
+
+int smj_radix_sort_pairs(SmjCtx *c, u64 *buf_a, u64 *buf_b, const u64 *d_n, u32 n_max, const u32 *d_hist, u32 *d_scratch)
+{
+    return smj_radix_sort_pairs_n(c, 1, &buf_a, &buf_b, &d_n, &n_max, &d_hist, &d_scratch);
 }
