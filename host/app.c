@@ -13,7 +13,8 @@
  *   - run-time knob overrides from the environment: SMJ_NR_GPUS, SMJ_SELECT_COL1/2, SMJ_SELECT_VAL1/2,
  *     SMJ_JOIN_KEY1/2, SMJ_DEBUG, SMJ_RESULT (output path), SMJ_JSON=1 (one JSON line with the stage times);
  *   - CSV parse / emit are timed separately from the device pipeline (BASELINE.json: "CSV parse/emit timed
- *     separately"), printed after the banner.
+ *     separately"), printed after the banner; both run on the GPU (smj_csv_parse / smj_csv_format) unless SMJ_CSV=host
+ *     or the text is irregular (host/csv.c then reproduces the reference's sequential parser).
  * Errors behave like the reference: a file that cannot be opened -> perror + exit(EXIT_FAILURE) (app.c:31-35),
  * a library failure -> message + exit(EXIT_FAILURE) (DPU_ASSERT, include/dpu/dpu.h:144).
  */
@@ -61,17 +62,46 @@ static void env_i64(const char *name, int64_t *v)
     if (s && *s) *v = strtoll(s, NULL, 10);
 }
 
+/* CSV -> table.  The file is read whole into pinned memory and parsed ON THE GPU (smj_csv_parse); text only a
+ * sequential pass can interpret the reference's way (a 1023+ character line, ragged rows) goes through host/csv.c.
+ * SMJ_CSV=host forces the host parser and writer. */
+static int g_csv_on_gpu = 1;
+
 static void load_or_die(const char *path, smj_table_t *t)
 {
+    if (g_csv_on_gpu) {
+        FILE *f = fopen(path, "rb");
+        if (!f) { perror("Failed to open file"); exit(EXIT_FAILURE); }   /* the reference's message (app.c:33) */
+        fseek(f, 0, SEEK_END);
+        long sz = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        char *buf = (char *)pinned_alloc((uint64_t)sz + 1);
+        if (!buf) { fprintf(stderr, "out of pinned memory for %s\n", path); exit(EXIT_FAILURE); }
+        size_t got = fread(buf, 1, (size_t)sz, f);
+        fclose(f);
+        int rc = smj_csv_parse(buf, got, t);
+        smj_host_free(buf);
+        if (rc == SMJ_OK) { if (t->rows < 0) t->rows = 0; return; }
+        if (rc != SMJ_EIRREGULAR) {
+            fprintf(stderr, "smj_csv_parse(%s) failed: %s (%s)\n", path, smj_strerror(rc), smj_last_error());
+            exit(EXIT_FAILURE);
+        }
+    }
     int cols = 0;
     int64_t rows = 0;
     int32_t *data = NULL;
     if (csv_load(path, &data, &rows, &cols, pinned_alloc) != 0) {
-        perror("Failed to open file");   /* the reference's message (app.c:33) */
+        perror("Failed to open file");
         exit(EXIT_FAILURE);
     }
     if (rows < 0) rows = 0;
     t->data = data; t->rows = rows; t->cols = cols; t->on_device = 0;
+}
+
+static void release_input(smj_table_t *t)
+{
+    if (t->on_device) smj_table_free(t);
+    else smj_host_free(t->data);
 }
 
 int main(int argc, char *argv[])
@@ -89,12 +119,15 @@ int main(int argc, char *argv[])
     env_int("SMJ_DEBUG", &cfg.debug);
     const char *result_path = getenv("SMJ_RESULT");
     if (!result_path || !*result_path) result_path = "./data/result.csv";
+    const char *csv_mode = getenv("SMJ_CSV");
+    if (csv_mode && strcmp(csv_mode, "host") == 0) g_csv_on_gpu = 0;
 
     /* replaces dpu_alloc + dpu_load; done before the CSV load so the tables land in pinned memory */
     SMJ_ASSERT(smj_init(&cfg));
 
     double t0 = now_ms();
     smj_table_t t1, t2, out = {NULL, 0, 0, 0};
+    out.on_device = g_csv_on_gpu;   /* the result stays in HBM when the GPU also formats it */
     load_or_die(argv[1], &t1);
     load_or_die(argv[2], &t2);
     double parse_ms = now_ms() - t0;
@@ -103,7 +136,18 @@ int main(int argc, char *argv[])
     SMJ_ASSERT(smj_run(&cfg, &t1, &t2, &out, &st));
 
     t0 = now_ms();
-    if (csv_save(result_path, out.data, out.rows, out.cols ? out.cols : t1.cols + t2.cols - 1) != 0) {
+    if (!out.cols) out.cols = t1.cols + t2.cols - 1;
+    if (g_csv_on_gpu) {
+        char *text = NULL;
+        size_t bytes = 0;
+        SMJ_ASSERT(smj_csv_format(&out, &text, &bytes));
+        FILE *f = fopen(result_path, "wb");
+        if (!f || fwrite(text, 1, bytes, f) != bytes || fclose(f) != 0) {
+            perror("Failed to open file");
+            exit(EXIT_FAILURE);
+        }
+        smj_host_free(text);
+    } else if (csv_save(result_path, out.data, out.rows, out.cols) != 0) {
         perror("Failed to open file");
         exit(EXIT_FAILURE);
     }
@@ -136,8 +180,8 @@ int main(int argc, char *argv[])
                (long long)st.kernel_launches);
 
     smj_table_free(&out);
-    smj_host_free(t1.data);
-    smj_host_free(t2.data);
+    release_input(&t1);
+    release_input(&t2);
     smj_shutdown();   /* replaces dpu_free (app.c:756) */
     return 0;
 }

@@ -46,6 +46,7 @@ extern "C" {
 #define SMJ_ETOOBIG    -5   /* row count exceeds what this build supports (2^30 selected rows per table per GPU) */
 #define SMJ_ENCCL      -6   /* NCCL error */
 #define SMJ_EINTERNAL  -7   /* device-side consistency check failed */
+#define SMJ_EIRREGULAR -8   /* smj_csv_parse: the text needs the sequential host parser to reproduce the reference exactly */
 
 /* join modes */
 #define SMJ_JOIN_ZIP   0    /* == cpu_app.c:204-266 / join.c:153-248: i-th left duplicate pairs with i-th right duplicate */
@@ -134,6 +135,18 @@ void smj_device_free(void *p);
 int  smj_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes);
 int  smj_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes);
 int  smj_device_sync(void);
+
+/* ---- CSV text <-> tables on the GPU ----
+ * smj_csv_parse == set_csv_size + load_csv (cpu_app.c:15-79 == app.c:28-92) for regular files: `text` is the whole file
+ * in host memory; *out becomes a library-owned DEVICE table (smj_table_free).  cols = tokens of the first line,
+ * rows = lines - 1 (rows = -1 for an empty file, as the reference computes), cells = atoi(token) with glibc's
+ * semantics.  Returns SMJ_EIRREGULAR when only a sequential pass reproduces the reference: a line of 1023+ characters
+ * (fgets(line, 1024) splits it), a row whose token count differs from the header's, an embedded NUL -- the caller then
+ * uses its sequential parser (host/csv.c does).
+ * smj_csv_format == save_to_csv (cpu_app.c:268-301 == app.c:720-755): header col1..colN, "%ld" cells, ',' separators,
+ * '\n' line ends; t may be a host or a device table; *text is pinned host memory (smj_host_free), *bytes its length. */
+int  smj_csv_parse(const char *text, size_t bytes, smj_table_t *out);
+int  smj_csv_format(const smj_table_t *t, char **text, size_t *bytes);
 
 /* ---- deterministic synthetic tables (replaces the unseeded data/generate_data.py:4-26) ----
  * kind 0: column key_col = a seeded bijection of the row index into [1, 3*total_rows] (unique keys, as

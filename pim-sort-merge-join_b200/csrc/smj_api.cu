@@ -45,6 +45,7 @@ extern "C" const char *smj_strerror(int code)
     case SMJ_ETOOBIG: return "input exceeds the supported row count";
     case SMJ_ENCCL: return "NCCL error";
     case SMJ_EINTERNAL: return "device-side consistency check failed";
+    case SMJ_EIRREGULAR: return "CSV text needs the sequential host parser";
     default: return "unknown error";
     }
 }

@@ -53,7 +53,7 @@ ABI_SYMBOLS = [
     "smj_merge", "smj_join", "smj_run", "smj_join_count", "smj_table_free", "smj_strerror", "smj_last_error",
     "smj_host_alloc", "smj_host_free", "smj_device_alloc", "smj_device_free", "smj_memcpy_h2d", "smj_memcpy_d2h",
     "smj_device_sync", "smj_synth_table", "smj_kernel_launches", "smj_device_count", "smj_version",
-    "smj_plan_splitters", "smj_plan_exchange",
+    "smj_plan_splitters", "smj_plan_exchange", "smj_csv_parse", "smj_csv_format",
 ]
 
 _lib = None
@@ -106,6 +106,8 @@ def lib():
     L.smj_synth_table.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_uint64, C.c_int,
                                   C.c_int64]
     L.smj_kernel_launches.restype = C.c_int64
+    L.smj_csv_parse.argtypes = [C.c_char_p, C.c_size_t, TP]
+    L.smj_csv_format.argtypes = [TP, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.smj_plan_splitters.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
     L.smj_plan_exchange.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int64)]
     _lib = L
@@ -238,3 +240,25 @@ def run(t1, t2, cfg=None, on_device=False, keep_output=False, **knobs):
     if keep_output:
         return out, st.as_dict()
     return _take(out), st.as_dict()
+
+
+# ------------------------------------------------------------------ CSV on the GPU
+def csv_parse(data):
+    """bytes of a whole CSV file -> numpy table via smj_csv_parse; raises SmjError(-8) when the text is irregular."""
+    out = Table(None, 0, 0, 1)
+    check(lib().smj_csv_parse(data, len(data), C.byref(out)))
+    if out.rows <= 0:
+        r, c = out.rows, out.cols
+        lib().smj_table_free(C.byref(out))
+        return np.empty((max(r, 0), c), np.int32)
+    return _take(out)
+
+
+def csv_format(t):
+    """table (numpy or Table) -> CSV bytes via smj_csv_format."""
+    tin, keep = _in(t)
+    p, n = C.c_void_p(), C.c_size_t()
+    check(lib().smj_csv_format(C.byref(tin), C.byref(p), C.byref(n)))
+    data = C.string_at(p.value, n.value)
+    lib().smj_host_free(p)
+    return data

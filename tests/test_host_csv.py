@@ -145,3 +145,83 @@ def test_c_driver_env_knobs_and_errors(golden, golden_csv, tmp_path):
     bad = subprocess.run([os.path.join(HOST, "app"), "/nonexistent.csv", "/nonexistent.csv"], cwd=tmp_path,
                          capture_output=True, text=True, timeout=120)
     assert bad.returncode != 0 and "Failed to open file" in bad.stderr
+
+
+# ------------------------------------------------------------------ CSV on the GPU (smj_csv_parse / smj_csv_format)
+@pytest.fixture(scope="module")
+def smj_gpu():
+    import smj_b200
+    if smj_b200.lib().smj_device_count() < 1:
+        pytest.fail("no CUDA device: the gpu-marked tests must run on a B200")
+    return smj_b200
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["g1", "g2", "kat2", "kat3", "kat4"])
+def test_gpu_csv_parse_golden_inputs(case, smj_gpu, port, golden_csv):
+    for i in (1, 2):
+        p = golden_csv(f"{case}_data{i}.csv")
+        got = smj_gpu.csv_parse(open(p, "rb").read())
+        assert np.array_equal(got, port.load_csv(p))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["crlf", "spaces_signs", "stops_at_junk", "no_trailing_newline", "int32_extremes", "header_only", "single_col"])
+def test_gpu_csv_parse_regular_quirks_match_reference(name, smj_gpu, ref, tmp_path):
+    p = str(tmp_path / f"{name}.csv")
+    open(p, "w", newline="").write(QUIRKS[name])
+    got = smj_gpu.csv_parse(QUIRKS[name].encode())
+    want = ref.load_csv(p)
+    assert got.shape == want.shape and np.array_equal(got, want), (got, want)
+
+
+@pytest.mark.gpu
+def test_gpu_csv_parse_overflow_and_irregular(smj_gpu, ref, tmp_path):
+    text = "a,b\n99999999999999999999,-99999999999999999999\n4294967297,-4294967297\n"
+    p = str(tmp_path / "big.csv")
+    open(p, "w").write(text)
+    assert np.array_equal(smj_gpu.csv_parse(text.encode()), ref.load_csv(p))
+    # ragged rows, collapsed empty fields, over-long lines and NUL bytes are handed back to the sequential parser
+    for bad in (QUIRKS["empty_fields_collapse"], QUIRKS["short_and_long_rows"], "a,b\n" + "1" * 1500 + ",2\n", "a,b\n1,\x002\n", "a,b\n1,2\n\n"):
+        with pytest.raises(smj_gpu.SmjError) as e:
+            smj_gpu.csv_parse(bad.encode())
+        assert e.value.code == -8
+    assert smj_gpu.csv_parse(b"").shape[0] == 0
+
+
+@pytest.mark.gpu
+def test_gpu_csv_format_matches_reference_writer_and_roundtrips(smj_gpu, ref, tmp_path):
+    rng = np.random.default_rng(3)
+    for shape in [(0, 3), (1, 1), (257, 7), (5000, 4), (300_000, 5)]:
+        t = rng.integers(-2**31, 2**31 - 1, size=shape).astype(np.int32)
+        if t.size:
+            t.flat[0], t.flat[-1] = -2**31, 2**31 - 1
+            t.flat[t.size // 2] = 0
+        got = smj_gpu.csv_format(t)
+        b = str(tmp_path / "b.csv")
+        ref.save_csv(b, t)
+        assert got == open(b, "rb").read()
+        if shape[0]:
+            assert np.array_equal(smj_gpu.csv_parse(got), t)
+    d = smj_gpu.device_table(rng.integers(-1000, 1000, size=(1234, 6)).astype(np.int32))
+    text = smj_gpu.csv_format(d)
+    assert np.array_equal(smj_gpu.csv_parse(text), smj_gpu.smj.to_numpy(d))
+    smj_gpu.free(d)
+
+
+@pytest.mark.gpu
+def test_c_driver_host_csv_mode_and_irregular_fallback(golden, golden_csv, tmp_path):
+    subprocess.run(["make", "-s", "-C", HOST], check=True)
+    g = golden["cases"]["g2"]
+    (tmp_path / "data").mkdir()
+    env = dict(os.environ, SMJ_CSV="host")
+    r = subprocess.run([os.path.join(HOST, "app"), golden_csv("g2_data1.csv"), golden_csv("g2_data2.csv")], cwd=tmp_path,
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert hashlib.sha256(open(tmp_path / "data" / "result.csv", "rb").read()).hexdigest() == g["sha256"]
+    # an irregular first table (one ragged row appended) must still run: the driver falls back to host/csv.c for it
+    rag = tmp_path / "ragged.csv"
+    rag.write_bytes(open(golden_csv("kat2_data1.csv"), "rb").read() + b"1\n")
+    r = subprocess.run([os.path.join(HOST, "app"), str(rag), golden_csv("kat2_data2.csv")], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
