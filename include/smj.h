@@ -50,7 +50,8 @@ extern "C" {
 
 /* join modes */
 #define SMJ_JOIN_ZIP   0    /* == cpu_app.c:204-266 / join.c:153-248: i-th left duplicate pairs with i-th right duplicate */
-#define SMJ_JOIN_MANY  1    /* true many-to-many equi-join (extension, order (key, left row, right row)) */
+#define SMJ_JOIN_MANY  1    /* true many-to-many equi-join (extension, order (key, left row, right row)); results that would
+                               not fit in device memory are refused with SMJ_ETOOBIG -- use smj_join_count for those */
 
 /* row-major int32 table; replaces {dpu_block_t bl; T rows[]} (common.h:13-18, select.c:16) */
 typedef struct {

@@ -528,8 +528,10 @@ static int join_sorted_pairs(SmjCtx *c, const u64 *pl, u32 m1, const u64 *pr, u3
     if (mode == SMJ_JOIN_ZIP) {
         WS_TRY(mm, uint2 *, c, WS_MATCH, tiles * smj_join_tile_size() * 8); d_matches = mm;
         if (!count_only) { WS_TRY(dd, uint2 *, c, WS_MATCH_DENSE, (size_t)(m1 < m2 ? m1 : m2) * 8); d_dense = dd; }
+    } else if (!count_only) {
+        WS_TRY(mm, uint2 *, c, WS_MATCH, (size_t)m1 * 8 + 8); d_matches = mm;   // (first right position, run length) per left element
+        CUDA_TRY(cudaMemsetAsync(mm, 0, (size_t)m1 * 8 + 8, c->stream));       // left elements past the right table's end keep an empty run
     }
-    else if (!count_only) return smj_set_error(SMJ_EINVAL, "SMJ_JOIN_MANY materialisation is not available in this build; use smj_join_count");
     SMJ_TRY(smj_launch_join_match(c, pl, pr, nullptr, m1, m2, mode, jsr.part, jsr.tile_count, jsr.tile_off, d_matches, d_dense, d_jcount));
     u64 *hm = (u64 *)c->h_pinned;
     CUDA_TRY(cudaMemcpyAsync(hm, d_jcount, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -537,6 +539,18 @@ static int join_sorted_pairs(SmjCtx *c, const u64 *pl, u32 m1, const u64 *pr, u3
     const int64_t j = (int64_t)hm[0];
     *rows_out = j;
     if (count_only) return SMJ_OK;
+    if (mode == SMJ_JOIN_MANY) {
+        // the many-to-many result can dwarf its inputs (cL * cR rows per key): refuse what cannot be held, expand the rest
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const double need = (double)j * (8.0 + 4.0 * (c1 + c2 - 1)) + (double)smj_join_many_scratch_bytes(m1);
+        if (need > 0.8 * (double)free_b)
+            return smj_set_error(SMJ_ETOOBIG, "SMJ_JOIN_MANY result of %lld rows needs %.1f GB; use smj_join_count or SMJ_JOIN_ZIP", (long long)j, need / 1e9);
+        WS_TRY(dd, uint2 *, c, WS_MATCH_DENSE, (size_t)j * 8);
+        WS_TRY(xs, char *, c, WS_MERGE_A, smj_join_many_scratch_bytes(m1));
+        d_dense = dd;
+        SMJ_TRY(smj_launch_join_many_expand(c, pl, pr, d_matches, m1, (u64)j, xs, d_dense));
+    }
     const int c_out = c1 + c2 - 1;
     if (out->on_device) {
         SMJ_TRY(smj_alloc_out(c, out, j, c_out));
@@ -659,10 +673,39 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
             return smj_set_error(SMJ_ETOOBIG, "table %d has %lld rows; this build handles at most 2^30 - 1 per table per GPU", t + 1,
                                  (long long)tb[t]->rows);
     }
-    if (cfg->join_mode != SMJ_JOIN_ZIP) return smj_set_error(SMJ_EINVAL, "smj_run materialises SMJ_JOIN_ZIP only (the reference semantics)");
+    if (cfg->join_mode != SMJ_JOIN_ZIP && cfg->join_mode != SMJ_JOIN_MANY) return smj_set_error(SMJ_EINVAL, "smj_run: bad join_mode %d", cfg->join_mode);
     const int64_t launches0 = c->launches;
     c->pass_count = 0;
     enum { E_START, E_H2D, E_SELECT, E_SORT, E_JOIN, E_D2H };
+    if (cfg->join_mode == SMJ_JOIN_MANY) {
+        // Extension (not the reference's semantics): every pair of equal keys.  The result size is data dependent and
+        // unbounded by the inputs, so this path waits for the host between the stages (stage entry points underneath).
+        CUDA_TRY(cudaEventRecord(c->ev[E_START], c->stream));
+        const int32_t *dm[2];
+        SMJ_TRY(smj_stage_in(c, t1, WS_T1, &dm[0]));
+        SMJ_TRY(smj_stage_in(c, t2, WS_T2, &dm[1]));
+        CUDA_TRY(cudaEventRecord(c->ev[E_H2D], c->stream));
+        u64 *sp[2];
+        int64_t mm_[2];
+        for (int t = 0; t < 2; t++)
+            SMJ_TRY(smj_sorted_pairs_of_table(c, dm[t], tb[t]->rows, tb[t]->cols, sel_col[t], sel_val[t], 0, key[t], t, &sp[t], &mm_[t]));
+        CUDA_TRY(cudaEventRecord(c->ev[E_SORT], c->stream));
+        int64_t jm = 0;
+        SMJ_TRY(join_sorted_pairs(c, sp[0], (u32)mm_[0], sp[1], (u32)mm_[1], SMJ_JOIN_MANY, false, dm[0], tb[0]->cols, dm[1], tb[1]->cols, key[1], out, &jm));
+        CUDA_TRY(cudaEventRecord(c->ev[E_JOIN], c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (stats) {
+            memset(stats, 0, sizeof *stats);
+            stats->h2d_ms = ev_ms(c->ev[E_START], c->ev[E_H2D]);
+            stats->sort_ms = ev_ms(c->ev[E_H2D], c->ev[E_SORT]);
+            stats->join_ms = ev_ms(c->ev[E_SORT], c->ev[E_JOIN]);
+            stats->total_device_ms = ev_ms(c->ev[E_H2D], c->ev[E_JOIN]);
+            for (int t = 0; t < 2; t++) { stats->rows_in[t] = tb[t]->rows; stats->rows_selected[t] = mm_[t]; }
+            stats->rows_joined = jm;
+            stats->kernel_launches = c->launches - launches0;
+        }
+        return SMJ_OK;
+    }
 
     // ---- CPU -> GPU (app.c timer 0)
     CUDA_TRY(cudaEventRecord(c->ev[E_START], c->stream));

@@ -128,6 +128,11 @@ size_t smj_join_tile_size(void);
 // d_dense (zip mode, may be null): the matches compacted in result order, min(m1_max, m2_max) entries of capacity.
 int smj_launch_join_match(SmjCtx *c, const u64 *d_l, const u64 *d_r, const u64 *d_counts, u32 m1_max, u32 m2_max, int mode,
                           u32 *d_part, u32 *d_tile_count, u64 *d_tile_off, uint2 *d_matches, uint2 *d_dense, u64 *d_count);
+// many-to-many: with mode = SMJ_JOIN_MANY, d_matches (if not null) receives one (first right position, right run length)
+// entry per left element; smj_launch_join_many_expand turns them into the dense match list of `total` pairs.
+size_t smj_join_many_scratch_bytes(u32 m1);
+int smj_launch_join_many_expand(SmjCtx *c, const u64 *d_l, const u64 *d_r, const uint2 *d_runs, u32 m1, u64 total, char *d_scratch,
+                                uint2 *d_dense);
 // d_nj: device match count or null (then nj_max is exact)
 // d_out_indirect (may be null): device cell holding the output pointer, read instead of d_out (graph replay)
 int smj_launch_join_materialize(SmjCtx *c, const uint2 *d_dense, const u64 *d_nj, int64_t nj_max, const int32_t *d_t1, int c1,

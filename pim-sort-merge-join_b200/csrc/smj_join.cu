@@ -97,7 +97,7 @@ template <int MODE>
 __global__ void __launch_bounds__(JN_THREADS)
 join_match_kernel(const u64 *__restrict__ L, const u64 *__restrict__ R, const u64 *__restrict__ counts, u32 m1_max,
                   u32 m2_max, const u32 *__restrict__ part, const u32 *__restrict__ runstart, uint2 *__restrict__ matches,
-                  u32 *__restrict__ tile_count, u64 *count)
+                  u32 *__restrict__ tile_count, u64 *count, uint2 *__restrict__ many_runs)
 {
     u32 m1, m2;
     load_counts(counts, m1_max, m2_max, m1, m2);
@@ -213,6 +213,8 @@ join_match_kernel(const u64 *__restrict__ L, const u64 *__restrict__ R, const u6
                             run_val = ub - (b0 + b); runk = k; have = true;
                         }
                         many_total += run_val;
+                        // per left element: (first right position of its key, right run length) for the expand step
+                        if (many_runs) many_runs[a0 + a] = make_uint2(b0 + b, run_val);
                     }
                     a++;
                     va = a < na ? sA[a] : 0ull;
@@ -382,6 +384,105 @@ join_materialize_kernel(const uint2 *__restrict__ matches, const u64 *__restrict
 
 }  // namespace
 
+// ---- many-to-many expansion (SMJ_JOIN_MANY): runs[i] = (first right position, right run length) of left element i.
+namespace {
+constexpr int EX_BLOCK = 4096;   // left elements per scan block
+
+// block_sum[b] = sum of run lengths of left elements [b*EX_BLOCK, (b+1)*EX_BLOCK)
+__global__ void __launch_bounds__(256) many_blocksum_kernel(const uint2 *__restrict__ runs, u32 m1, u64 *block_sum)
+{
+    __shared__ u64 s_w[8];
+    const u32 base = blockIdx.x * EX_BLOCK;
+    u64 sum = 0;
+    for (u32 i = threadIdx.x; i < (u32)EX_BLOCK; i += 256) if (base + i < m1) sum += runs[base + i].y;
+    sum = warp_sum(sum);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) { u64 t = 0; for (int w = 0; w < 8; w++) t += s_w[w]; block_sum[blockIdx.x] = t; }
+}
+
+// exclusive scan of the block sums (one CTA, chunk per thread) and the grand total
+__global__ void __launch_bounds__(1024) many_blockscan_kernel(u64 *block_sum, u32 nblocks, u64 *total)
+{
+    __shared__ u64 s_w[32];
+    const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+    const u32 chunk = (nblocks + 1023) / 1024;
+    const u32 lo = tid * chunk < nblocks ? tid * chunk : nblocks, hi = lo + chunk < nblocks ? lo + chunk : nblocks;
+    u64 sum = 0;
+    for (u32 i = lo; i < hi; i++) sum += block_sum[i];
+    u64 inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u64 t = __shfl_up_sync(FULL_MASK, inc, o); if (lane >= (u32)o) inc += t; }
+    if (lane == 31) s_w[w] = inc;
+    __syncthreads();
+    u64 run = inc - sum;
+    for (u32 ww = 0; ww < w; ww++) run += s_w[ww];
+    if (tid == 1023) *total = run + sum;
+    for (u32 i = lo; i < hi; i++) { const u64 v = block_sum[i]; block_sum[i] = run; run += v; }
+}
+
+// off[i] = output row of the first pair of left element i (exclusive scan inside the block + the block's offset)
+__global__ void __launch_bounds__(256) many_offsets_kernel(const uint2 *__restrict__ runs, u32 m1, const u64 *__restrict__ block_off, u64 *off)
+{
+    __shared__ u64 s_w[8];
+    const u32 base = blockIdx.x * EX_BLOCK;
+    constexpr int PER = EX_BLOCK / 256;   // 16 consecutive elements per thread
+    const u32 t0 = base + threadIdx.x * PER;
+    u32 v[PER];
+    u64 sum = 0;
+#pragma unroll
+    for (int q = 0; q < PER; q++) { v[q] = (t0 + q < m1) ? runs[t0 + q].y : 0u; sum += v[q]; }
+    const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    u64 inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u64 t = __shfl_up_sync(FULL_MASK, inc, o); if (lane >= (u32)o) inc += t; }
+    if (lane == 31) s_w[w] = inc;
+    __syncthreads();
+    u64 run = block_off[blockIdx.x] + inc - sum;
+    for (u32 ww = 0; ww < w; ww++) run += s_w[ww];
+#pragma unroll
+    for (int q = 0; q < PER; q++) { if (t0 + q < m1) off[t0 + q] = run; run += v[q]; }
+}
+
+// pair o -> (left row id, right row id): left element = the last one whose offset is <= o
+__global__ void __launch_bounds__(256)
+many_expand_kernel(const u64 *__restrict__ L, const u64 *__restrict__ R, const uint2 *__restrict__ runs, const u64 *__restrict__ off, u32 m1,
+                   u64 total, uint2 *__restrict__ dense)
+{
+    const u64 o = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= total) return;
+    u32 lo = 0, hi = m1;                      // upper_bound(off, o) - 1
+    while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (off[mid] <= o) lo = mid + 1; else hi = mid; }
+    u32 i = lo - 1;
+    // elements with an empty run share their offset with the next one: step back to the one that owns row o
+    while (runs[i].y == 0u || off[i] + runs[i].y <= o) i--;
+    const uint2 r = runs[i];
+    dense[o] = make_uint2(pair_row(L[i]), pair_row(R[r.x + (u32)(o - off[i])]));
+}
+}  // namespace
+
+// Expands the per-left-element runs written by smj_launch_join_match(mode = SMJ_JOIN_MANY, d_matches = runs) into the dense
+// (left row id, right row id) list, order (key, left position, right position).  total = the count the match step returned.
+size_t smj_join_many_scratch_bytes(u32 m1) { return ((size_t)(m1 + EX_BLOCK - 1) / EX_BLOCK + 2) * 8 + (size_t)m1 * 8 + 64; }
+int smj_launch_join_many_expand(SmjCtx *c, const u64 *d_l, const u64 *d_r, const uint2 *d_runs, u32 m1, u64 total, char *d_scratch,
+                                uint2 *d_dense)
+{
+    if (m1 == 0 || total == 0) return SMJ_OK;
+    const u32 nblocks = (m1 + EX_BLOCK - 1) / EX_BLOCK;
+    u64 *d_total = (u64 *)d_scratch;
+    u64 *d_bsum = (u64 *)(d_scratch + 64);
+    u64 *d_off = d_bsum + nblocks + 1;
+    many_blocksum_kernel<<<nblocks, 256, 0, c->stream>>>(d_runs, m1, d_bsum);
+    KERNEL_CHECK(c);
+    many_blockscan_kernel<<<1, 1024, 0, c->stream>>>(d_bsum, nblocks, d_total);
+    KERNEL_CHECK(c);
+    many_offsets_kernel<<<nblocks, 256, 0, c->stream>>>(d_runs, m1, d_bsum, d_off);
+    KERNEL_CHECK(c);
+    many_expand_kernel<<<(u32)((total + 255) / 256), 256, 0, c->stream>>>(d_l, d_r, d_runs, d_off, m1, total, d_dense);
+    KERNEL_CHECK(c);
+    return SMJ_OK;
+}
+
 size_t smj_join_num_tiles(u64 total) { return (size_t)((total + JN_TILE - 1) / JN_TILE); }
 size_t smj_join_tile_size(void) { return JN_TILE; }
 
@@ -410,7 +511,7 @@ int smj_launch_join_match(SmjCtx *c, const u64 *d_l, const u64 *d_r, const u64 *
     const u32 grid = tiles < (u32)(sms * 4) ? tiles : (u32)(sms * 4);   // 58 registers x 256 threads: 4 CTAs per SM
     if (mode == SMJ_JOIN_ZIP) {
         join_match_kernel<SMJ_JOIN_ZIP><<<grid, JN_THREADS, 0, c->stream>>>(d_l, d_r, d_counts, m1_max, m2_max, d_part, d_runstart,
-                                                                           d_matches, d_tile_count, d_count);
+                                                                           d_matches, d_tile_count, d_count, nullptr);
         KERNEL_CHECK(c);
         join_scan_kernel<<<1, JS_THREADS, 0, c->stream>>>(d_tile_count, tiles, d_tile_off, d_count);
         if (d_dense) {
@@ -419,8 +520,9 @@ int smj_launch_join_match(SmjCtx *c, const u64 *d_l, const u64 *d_r, const u64 *
             join_compact_kernel<<<cgrid, 256, 0, c->stream>>>(d_matches, d_tile_count, d_tile_off, tiles, d_dense);
         }
     } else {
+        // many-to-many: d_matches (if given) receives one (first right position, run length) entry per LEFT element
         join_match_kernel<SMJ_JOIN_MANY><<<grid, JN_THREADS, 0, c->stream>>>(d_l, d_r, d_counts, m1_max, m2_max, d_part, d_runstart,
-                                                                            d_matches, d_tile_count, d_count);
+                                                                            nullptr, d_tile_count, d_count, d_matches);
     }
     KERNEL_CHECK(c);
     return SMJ_OK;

@@ -172,6 +172,28 @@ def test_join_many_count(smj, port):
         assert smj.join_count(l, r, 0, 0, mode=smj.JOIN_MANY) == want
 
 
+@pytest.mark.parametrize("n1,n2,hi,c1,c2,k1,k2", [
+    (0, 10, 5, 2, 2, 0, 0), (10, 0, 5, 2, 2, 0, 0), (1, 1, 1, 1, 1, 0, 0), (5000, 4000, 50, 2, 3, 0, 1), (100_000, 80_000, 100_000, 4, 4, 0, 0),
+    (20_000, 20_000, 5, 3, 2, 2, 0), (3, 70_000, 2, 2, 2, 1, 1), (70_000, 3, 2, 5, 5, 4, 4),
+])
+def test_join_many_materialised(smj, port, n1, n2, hi, c1, c2, k1, k2):
+    """True many-to-many equi-join (extension): every pair of equal keys, order (key, left row, right row)."""
+    rng = np.random.default_rng(n1 + 7 * n2 + hi)
+    l, r = sorted_pair(port, rng, n1, n2, c1, c2, k1, k2, 0, hi)
+    want = port.join(l, r, k1, k2, mode=1)
+    got = smj.join(l, r, k1, k2, mode=smj.JOIN_MANY)
+    assert_same(got, want, f"many join {n1}x{n2} hi={hi}")
+    assert smj.join_count(l, r, k1, k2, mode=smj.JOIN_MANY) == want.shape[0]
+
+
+def test_join_many_refuses_what_cannot_be_held(smj, port):
+    k = np.zeros((3_000_000, 1), np.int32)           # 9e12 pairs
+    with pytest.raises(smj.SmjError) as e:
+        smj.join(k, k, 0, 0, mode=smj.JOIN_MANY)
+    assert e.value.code == -5
+    assert smj.join_count(k, k, 0, 0, mode=smj.JOIN_MANY) == 9_000_000_000_000
+
+
 # ------------------------------------------------------------------ whole pipeline
 @pytest.mark.parametrize("case", ["g1", "g2", "kat2", "kat3", "kat4"])
 def test_run_golden(smj, port, golden, golden_csv, case, tmp_path):
@@ -202,6 +224,17 @@ def test_run_random_knobs(smj, port, seed):
     got, st = smj.run(t1, t2, **kn)
     assert st["rows_selected"] == list(sel)
     assert_same(got, want, f"run seed={seed} knobs={kn}")
+
+
+def test_run_many_to_many_mode(smj, port):
+    """smj_run with join_mode = SMJ_JOIN_MANY (extension): select -> sort -> every pair of equal keys."""
+    rng = np.random.default_rng(77)
+    t1, t2 = rand_table(rng, 40_000, 3, -30, 400), rand_table(rng, 25_000, 4, -30, 400)
+    kn = dict(select_col1=1, select_val1=0, select_col2=0, select_val2=10, join_key1=2, join_key2=3)
+    want, sel, _ = port.run(t1, t2, 1, 0, 0, 10, 2, 3, mode=1)
+    got, st = smj.run(t1, t2, join_mode=smj.JOIN_MANY, **kn)
+    assert st["rows_selected"] == list(sel) and st["rows_joined"] == want.shape[0]
+    assert_same(got, want, "run many-to-many")
 
 
 def test_run_zipf_heavy_duplicates(smj, port):
