@@ -117,7 +117,13 @@ select_pairs_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int sel
 // all stall samples waiting for that look-back's L2 round trips, with DRAM at 19 % of peak.  Here the offsets come
 // from a separate scan over the tile counts (tile_scan_kernel, microseconds) and a compaction copy of the survivors
 // (8 B per survivor, L2-resident at the 10M-row config), and the table scan itself is a pure stream.
-constexpr int SEL_STAGES = 3;
+#ifndef SMJ_SEL_STAGES
+#define SMJ_SEL_STAGES 2
+#endif
+#ifndef SMJ_SEL_CTAS
+#define SMJ_SEL_CTAS 2
+#endif
+constexpr int SEL_STAGES = SMJ_SEL_STAGES;
 constexpr int SEL_STAGE_BYTES = 32768;
 constexpr int SEL_MAX_COLS_TMA = SEL_STAGE_BYTES / 4 / SEL_THREADS;   // 32 columns: at least one row per thread
 constexpr int SELW_THREADS = SEL_THREADS + 32;                         // + producer warp
@@ -325,7 +331,7 @@ int smj_launch_select_pairs(SmjCtx *c, const int32_t *d_in, int64_t n, int cols,
         }
         u64 *d_offsets = d_status;                                   // [tiles]
         u32 *d_counts = reinterpret_cast<u32 *>(d_status + tiles);   // [tiles]
-        const u32 grid = tiles < (u32)(sms * 2) ? tiles : (u32)(sms * 2);
+        const u32 grid = tiles < (u32)(sms * SMJ_SEL_CTAS) ? tiles : (u32)(sms * SMJ_SEL_CTAS);
         if (d_hist)
             select_tma_kernel<true><<<grid, SELW_THREADS, smem, c->stream>>>(d_in, n, cols, ipt, sel_col, (int32_t)sel_val, select_all,
                                                                             key_col, rowid_base, d_tmp, d_counts, d_hist, tiles);

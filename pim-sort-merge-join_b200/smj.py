@@ -60,7 +60,8 @@ _lib = None
 
 
 def lib_path():
-    return os.path.join(HERE, "libsmj.so")
+    # SMJ_LIB: an alternative build of the same library (kernel-variant experiments; tools/bin/)
+    return os.environ.get("SMJ_LIB") or os.path.join(HERE, "libsmj.so")
 
 
 def build(verbose=False):
