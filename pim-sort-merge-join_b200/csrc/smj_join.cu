@@ -20,6 +20,9 @@
 
 namespace {
 
+#ifndef SMJ_JN_GRID
+#define SMJ_JN_GRID 4
+#endif
 constexpr int JN_THREADS = 256;
 constexpr int JN_VT = 8;
 constexpr int JN_TILE = JN_THREADS * JN_VT;   // merged elements per tile
@@ -296,7 +299,17 @@ join_compact_kernel(const uint2 *__restrict__ slots, const u32 *__restrict__ til
     }
 }
 
+#ifndef SMJ_MT_ILP
+#define SMJ_MT_ILP 8
+#endif
+#ifndef SMJ_MT_RPB
+#define SMJ_MT_RPB 1024
+#endif
+#ifndef SMJ_MT_GRID
+#define SMJ_MT_GRID 6
+#endif
 constexpr int MT_THREADS = 256;
+constexpr int MT_ILP = SMJ_MT_ILP;   // gather tasks in flight per thread
 constexpr int MT_SMEM_CELLS = 8192;   // 32 KB staging: rows per block = MT_SMEM_CELLS / c_out (<= 1024)
 
 // out[o] = t1[matches[o].x][0..c1) ++ t2[matches[o].y][c != key2]   (cpu_app.c:240-251, join.c:214-229)
@@ -321,17 +334,17 @@ join_materialize_kernel(const uint2 *__restrict__ matches, const u64 *__restrict
         const int64_t row0 = blk * rows_per_block;
         const int nrows = (int)((nj - row0 < rows_per_block) ? (nj - row0) : rows_per_block);
         __syncthreads();   // previous block's copy-out is done with s_out
-        // 2 * nrows gather tasks: task i < nrows is the left row of match i, the others the right rows.  Four tasks
+        // 2 * nrows gather tasks: task i < nrows is the left row of match i, the others the right rows.  MT_ILP tasks
         // per thread are in flight at once (match entries first, then the dependent row loads): the random 16..32-byte
         // row reads are latency-bound, so memory-level parallelism per thread is what sets the rate.
-        for (int task0 = threadIdx.x; task0 < 2 * nrows; task0 += 4 * MT_THREADS) {
-            uint2 m[4];
-            const int32_t *src[4];
-            int32_t *dst[4];
-            int cc[4];
-            bool right[4], live[4];
+        for (int task0 = threadIdx.x; task0 < 2 * nrows; task0 += MT_ILP * MT_THREADS) {
+            uint2 m[MT_ILP];
+            const int32_t *src[MT_ILP];
+            int32_t *dst[MT_ILP];
+            int cc[MT_ILP];
+            bool right[MT_ILP], live[MT_ILP];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < MT_ILP; u++) {
                 const int task = task0 + u * MT_THREADS;
                 live[u] = task < 2 * nrows;
                 right[u] = task >= nrows;
@@ -340,17 +353,17 @@ join_materialize_kernel(const uint2 *__restrict__ matches, const u64 *__restrict
                 dst[u] = s_out + r * c_out + (right[u] ? c1 : 0);
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < MT_ILP; u++) {
                 cc[u] = right[u] ? c2 : c1;
                 src[u] = right[u] ? t2 + (size_t)m[u].y * c2 : t1 + (size_t)m[u].x * c1;
             }
             if (VEC) {
-                int4 v[4];
+                int4 v[MT_ILP];
 #pragma unroll
-                for (int u = 0; u < 4; u++)
+                for (int u = 0; u < MT_ILP; u++)
                     if (live[u]) v[u] = __ldg(reinterpret_cast<const int4 *>(src[u]));
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < MT_ILP; u++) {
                     if (!live[u]) continue;
                     const int skip = right[u] ? key2 : -1;      // right rows drop column key2
                     for (int q = 0;;) {
@@ -366,7 +379,7 @@ join_materialize_kernel(const uint2 *__restrict__ matches, const u64 *__restrict
                 }
             } else {
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < MT_ILP; u++) {
                     if (!live[u]) continue;
                     const int skip = right[u] ? key2 : -1;
                     for (int q = 0; q < cc[u]; q++)
@@ -508,7 +521,7 @@ int smj_launch_join_match(SmjCtx *c, const u64 *d_l, const u64 *d_r, const u64 *
     join_partition_kernel<<<(tiles + 1 + 7) / 8, 256, 0, c->stream>>>(d_l, d_r, d_counts, m1_max, m2_max, d_part, d_runstart);
     KERNEL_CHECK(c);
     const int sms = sm_count(c);
-    const u32 grid = tiles < (u32)(sms * 4) ? tiles : (u32)(sms * 4);   // 58 registers x 256 threads: 4 CTAs per SM
+    const u32 grid = tiles < (u32)(sms * SMJ_JN_GRID) ? tiles : (u32)(sms * SMJ_JN_GRID);   // ~60 registers x 256 threads: 4 CTAs per SM
     if (mode == SMJ_JOIN_ZIP) {
         join_match_kernel<SMJ_JOIN_ZIP><<<grid, JN_THREADS, 0, c->stream>>>(d_l, d_r, d_counts, m1_max, m2_max, d_part, d_runstart,
                                                                            d_matches, d_tile_count, d_count, nullptr);
@@ -536,10 +549,10 @@ int smj_launch_join_materialize(SmjCtx *c, const uint2 *d_dense, const u64 *d_nj
     const int c_out = c1 + c2 - 1;
     if (c_out > MT_SMEM_CELLS) return smj_set_error(SMJ_EINVAL, "joined rows of %d columns exceed the %d-cell staging tile", c_out, MT_SMEM_CELLS);
     int rpb = MT_SMEM_CELLS / c_out;
-    if (rpb > 1024) rpb = 1024;
+    if (rpb > SMJ_MT_RPB) rpb = SMJ_MT_RPB;
     const int64_t nblocks = (nj_max + rpb - 1) / rpb;
     const int sms = sm_count(c);
-    const u32 grid = (u32)(nblocks < (int64_t)sms * 6 ? nblocks : (int64_t)sms * 6);
+    const u32 grid = (u32)(nblocks < (int64_t)sms * SMJ_MT_GRID ? nblocks : (int64_t)sms * SMJ_MT_GRID);
     const bool vec = (c1 % 4 == 0) && (c2 % 4 == 0) && ((((uintptr_t)d_t1) | ((uintptr_t)d_t2)) & 15) == 0;
     if (vec)
         join_materialize_kernel<true><<<grid, MT_THREADS, 0, c->stream>>>(d_dense, d_nj, nj_max, d_t1, c1, d_t2, c2, key2, d_out, d_out_indirect, rpb);
