@@ -28,12 +28,28 @@ elif case == "dups":
     n1, n2, c1, c2 = 150_000, 120_000, 3, 5
     t1 = rng.integers(-50, 400, size=(n1, c1)).astype(np.int32); t2 = rng.integers(-50, 400, size=(n2, c2)).astype(np.int32)
     kn = dict(select_col1=1, select_val1=-5, select_col2=2, select_val2=0, join_key1=2, join_key2=1)
+elif case == "zipf":   # one key holds ~10 % of the rows: its whole run must land on one rank
+    n1, n2, c1, c2 = 200_000, 150_000, 4, 4
+    t1 = smj_b200.datagen.zipf_table(n1, c1, 31); t2 = smj_b200.datagen.zipf_table(n2, c2, 32)
+    kn = dict(select_col1=0, select_val1=5000, select_col2=0, select_val2=5000, join_key1=0, join_key2=0)
 else:   # tiny and skewed: some ranks own nothing
     n1, n2, c1, c2 = 37, 11, 2, 2
     t1 = rng.integers(0, 5, size=(n1, c1)).astype(np.int32); t2 = rng.integers(0, 5, size=(n2, c2)).astype(np.int32)
     kn = dict(select_col1=0, select_val1=-1, select_col2=0, select_val2=-1, join_key1=0, join_key2=0)
 b1 = t1[rank * n1 // world:(rank + 1) * n1 // world]
 b2 = t2[rank * n2 // world:(rank + 1) * n2 // world]
+if case == "unique":
+    # a smaller problem first: the second run needs larger receive buffers on every rank, so the peer mappings of the
+    # first one are stale and must be re-exchanged (CUDA-IPC path)
+    s1, s2 = smj_b200.datagen.table(20_000, c1, 5), smj_b200.datagen.table(10_000, c2, 6, total_rows=20_000)
+    sk = dict(select_col1=0, select_val1=100, select_col2=0, select_val2=100, join_key1=0, join_key2=0)
+    shard, _ = smj_b200.run(s1[rank * 20_000 // world:(rank + 1) * 20_000 // world], s2[rank * 10_000 // world:(rank + 1) * 10_000 // world],
+                            nr_gpus=world, **sk)
+    parts = [None] * world
+    dist.all_gather_object(parts, shard)
+    if rank == 0:
+        want, _, _ = oracle.Port().run(s1, s2, 0, 100, 0, 100, 0, 0)
+        assert np.array_equal(np.concatenate(parts), want), "small warm-up problem"
 for on_device in (False, True):
     if on_device:
         a, b = smj_b200.device_table(b1), smj_b200.device_table(b2)
@@ -63,7 +79,7 @@ def _ngpus():
 # path: default = select+partition, exchange fused into the compaction kernel over CUDA-IPC peer memory;
 #       "nccl" = same partitioning, send buffer + grouped ncclSend/ncclRecv; "merge" = sort first, exchange, merge-path merge tree
 @pytest.mark.parametrize("world,path", [(2, "peer"), (2, "nccl"), (2, "merge"), (4, "peer"), (4, "merge")])
-@pytest.mark.parametrize("case", ["unique", "dups", "tiny"])
+@pytest.mark.parametrize("case", ["unique", "dups", "zipf", "tiny"])
 def test_key_range_join_matches_single_process_oracle(case, world, path, tmp_path):
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
