@@ -249,7 +249,9 @@ def main():
     m_avg = (st["rows_selected"][0] + st["rows_selected"][1]) / 2.0
     m_launch = st["rows_selected"][0] + st["rows_selected"][1]     # one pass launch sorts a digit of BOTH tables' pairs
     pass_avg_ms = pass_ms / max(passes, 1)
-    achieved = 16.0 * m_launch / (pass_avg_ms * 1e-3) / 1e9 if pass_avg_ms > 0 else 0.0
+    # bytes of an average executed pass launch: the sort runs ceil(bits(key range) / 8) passes per table (device sort plan)
+    pass_bytes = st.get("sort_pass_bytes_avg", 0.0) or 16.0 * m_launch
+    achieved = pass_bytes / (pass_avg_ms * 1e-3) / 1e9 if pass_avg_ms > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "radix_pass_traffic.json")
     if os.path.exists(tp):
@@ -257,9 +259,9 @@ def main():
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             pass
-    roofline = {"bound": "hbm", "kernel": "radix_pass_kernel (onesweep scatter pass; 4 launches per step, each over both tables' pairs)", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": f"radix_pass_kernel (onesweep scatter pass; {st['sort_passes']} launches with work per step, each over both tables' pairs)", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": 16.0 * m_launch, "avg_launch_ms": pass_avg_ms,
+                "algorithmic_bytes_per_launch": pass_bytes, "avg_launch_ms": pass_avg_ms,
                 "pipeline_model_bytes": st["bytes_model"], "pipeline_model_gbs": st["bytes_model"] / (ms * 1e-3) / 1e9,
                 "pipeline_frac_of_peak": st["bytes_model"] / (ms * 1e-3) / 1e9 / peak,
                 "note": (f"pair arrays of this workload ({8e-6 * m_avg:.0f} MB each) " +

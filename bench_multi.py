@@ -94,7 +94,8 @@ def run_multi(args, w, name):
         peak, peak_src = peaks()
         m_launch = (sel[0] + sel[1]) / G                 # one pass launch sorts a digit of both tables' pairs on one GPU
         pass_avg_ms = pass_ms / max(passes, 1)
-        achieved = 16.0 * m_launch / (pass_avg_ms * 1e-3) / 1e9 if pass_avg_ms > 0 else 0.0
+        pass_bytes = st.get("sort_pass_bytes_avg", 0.0) or 16.0 * m_launch   # rank 0's executed passes (sort plan)
+        achieved = pass_bytes / (pass_avg_ms * 1e-3) / 1e9 if pass_avg_ms > 0 else 0.0
         line = {
             "metric": "select+sort+merge-join throughput", "value": value, "unit": "Mrows/s", "n_gpus": G, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
@@ -104,9 +105,9 @@ def run_multi(args, w, name):
                        "rows_selected": sel, "rows_joined": joined, "parallelism": f"key-range x{G}",
                        "l2": "per-GPU inputs (2 x 160 MB) larger than the 126 MB L2; no explicit flush"},
             "stage_ms": stage_max, "wall_ms_per_step": wall_ms, "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "radix_pass_kernel (onesweep scatter pass; 4 launches per step, each over both tables' pairs)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": f"radix_pass_kernel (onesweep scatter pass; {st['sort_passes']} launches with work per step, each over both tables' pairs)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": 16.0 * m_launch, "avg_launch_ms": pass_avg_ms,
+                         "algorithmic_bytes_per_launch": pass_bytes, "avg_launch_ms": pass_avg_ms,
                          "nvlink_bytes_sent_per_gpu": nvlink_max,
                          "nvlink_gbs_per_gpu": nvlink_max / (stage_max["exchange_ms"] * 1e-3) / 1e9 if stage_max["exchange_ms"] > 0 else None,
                          "nvlink_peak_gbs": 770.0},

@@ -81,6 +81,9 @@ typedef struct {
     int64_t kernel_launches;              /* kernels this call launched */
     /* average device time of the radix-sort scatter pass (the dominant kernel) and its launch count */
     double  sort_pass_ms_avg; int32_t sort_passes; int32_t reserved;
+    /* algorithmic bytes (16 B per pair the launch sorts) of an average executed pass launch: the sort runs
+     * ceil(bits(max key - min key) / 8) passes per table, decided on the device */
+    double  sort_pass_bytes_avg;
 } smj_stats_t;
 
 /* fills *cfg from the user.h macros this library was compiled with (include/user.h) */

@@ -368,6 +368,7 @@ struct ScratchHeader {
     u64 jcount;
     u64 pad0;
     u32 counter[16];     // 0,1: select tickets; 2: join ticket
+    SmjSortPlan plan[2]; // smj_run: key range of each table's survivors -> radix passes to run
 };
 
 // (key,rowid) pairs of every row of a device table (no predicate): used by sort / merge / join entry points.
@@ -732,7 +733,9 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
     WS_TRY(pong1, u64 *, c, WS_PAIRS_B2, (size_t)n[1] * 8);
     u64 *ping[2] = {ping0, ping1}, *pong[2] = {pong0, pong1};
     const int64_t j_max = n[0] < n[1] ? n[0] : n[1];
-    WS_TRY(mm, uint2 *, c, WS_MATCH, jt * smj_join_tile_size() * 8);
+    // the join's per-tile match slots; before the sort the same bytes hold the select kernels' per-tile pair slots
+    const size_t mm_bytes = jt * smj_join_tile_size() * 8 > (size_t)(n[0] + n[1]) * 8 ? jt * smj_join_tile_size() * 8 : (size_t)(n[0] + n[1]) * 8;
+    WS_TRY(mm, uint2 *, c, WS_MATCH, mm_bytes);
     WS_TRY(md, uint2 *, c, WS_MATCH_DENSE, (size_t)j_max * 8);
     smj_table_t dev_out = {nullptr, 0, c_out, 1};
     SMJ_TRY(smj_alloc_out(c, &dev_out, j_max, c_out));   // upper bound; rows is set once the count is known
@@ -766,7 +769,16 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
 #define PIPE_CUDA(x) if (cudaError_t e_ = (x)) { rc = smj_cuda_fail(e_, #x, __FILE__, __LINE__); break; }
             // select (+ digit histograms), both tables
             PIPE_CUDA(cudaMemsetAsync(scr, 0, zero_bytes, c->stream));
-            for (int t = 0; t < 2 && rc == SMJ_OK; t++)
+            bool planned = true;
+            {
+                SmjSelectJob job[2];
+                for (int t = 0; t < 2; t++)
+                    job[t] = {d_t[t], n[t], cc[t], sel_col[t], sel_val[t], 0, key[t], {ping[t], pong[t]}, (u64 *)mm + (t ? n[0] : 0),
+                              (u64 *)(scr + off_sel + (t ? stiles[0] * 8 : 0)), h->hist[t], &h->count[t], &h->plan[t]};
+                rc = smj_launch_select_plan2(c, job);
+                if (rc == 1) { planned = false; rc = SMJ_OK; }   // a table the TMA path cannot take: histograms in the select kernel, four passes
+            }
+            for (int t = 0; t < 2 && rc == SMJ_OK && !planned; t++)
                 rc = smj_launch_select_pairs(c, d_t[t], n[t], cc[t], sel_col[t], sel_val[t], 0, key[t], 0, ping[t], pong[t],
                                              (u64 *)(scr + off_sel + (t ? stiles[0] * 8 : 0)), &h->counter[t], h->hist[t], &h->count[t]);
             if (rc != SMJ_OK) break;
@@ -777,7 +789,9 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
                 const u32 nm[2] = {(u32)n[0], (u32)n[1]};
                 const u32 *hs[2] = {h->hist[0], h->hist[1]};
                 u32 *sc[2] = {(u32 *)(scr + off_radix), (u32 *)(scr + off_radix + rb[0])};
-                rc = smj_radix_sort_pairs_n(c, 2, ping, pong, dn, nm, hs, sc);
+                const SmjSortPlan *pl[2] = {&h->plan[0], &h->plan[1]};
+                rc = smj_radix_sort_pairs_n(c, 2, ping, pong, dn, nm, hs, sc, planned ? pl : nullptr);
+                c->run_planned = planned;
             }
             if (rc != SMJ_OK) break;
             PIPE_CUDA(smj_event_record(c->ev[E_SORT], c->stream));
@@ -856,8 +870,15 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
         stats->kernel_launches = c->launches - launches0;
         double sum = 0;
         for (int p = 0; p < c->pass_count; p++) sum += ev_ms(c->pass_ev[2 * p], c->pass_ev[2 * p + 1]);
-        stats->sort_passes = c->pass_count * SMJ_KEY_PASSES;   // each timed group is four pass launches (both tables in each)
-        stats->sort_pass_ms_avg = c->pass_count ? sum / (c->pass_count * SMJ_KEY_PASSES) : 0;
+        // each timed group is four pass launches (both tables in each); with a sort plan only the first
+        // max(npass) of them have tiles, and table t takes part in npass[t] of those
+        u32 np[2] = {SMJ_KEY_PASSES, SMJ_KEY_PASSES};
+        if (c->run_planned) { np[0] = hh->plan[0].npass; np[1] = hh->plan[1].npass; }
+        const u32 np_max = np[0] > np[1] ? np[0] : np[1];
+        stats->sort_passes = c->pass_count * (int)np_max;
+        stats->sort_pass_ms_avg = stats->sort_passes ? sum / stats->sort_passes : 0;
+        stats->sort_pass_bytes_avg = np_max ? 16.0 * ((double)m[0] * np[0] + (double)m[1] * np[1]) / np_max : 0;
+        stats->bytes_model -= 16.0 * ((double)m[0] * (SMJ_KEY_PASSES - np[0]) + (double)m[1] * (SMJ_KEY_PASSES - np[1]));
     }
     return SMJ_OK;
 }

@@ -35,6 +35,7 @@ struct SmjCtx {
     int pass_count = 0;
     bool radix_attr_set = false;
     bool select_attr_set = false;
+    bool run_planned = false;        // the last smj_run_single pipeline ran with device sort plans
     // CUDA-graph replay of the smj_run device pipeline (same tables, shapes and knobs as the previous call)
     u64 ws_gen = 0;                  // bumped whenever a workspace slot is (re)allocated
     u64 graph_key[16] = {};
@@ -87,6 +88,24 @@ int smj_launch_select_pairs(SmjCtx *c, const int32_t *d_in, int64_t n, int cols,
                             u64 *d_status /*[smj_select_num_tiles(n)], zero*/, u32 *d_tile_counter /*zero*/,
                             u32 *d_hist /*[4*256] zero, may be null*/, u64 *d_count /*out*/);
 
+// Sort plan of one table, device-resident (lives in the zeroed scratch arena): the select kernel accumulates the
+// surviving keys' range in kmin_inv (= ~min, so that zero means "none yet") and kmax; the scan kernel derives kmin and
+// npass = ceil(bits(kmax - kmin) / 8).  The radix passes sort digits of (key - kmin) and passes >= npass exit at once.
+struct SmjSortPlan { u32 kmin, npass, kmin_inv, kmax; };
+
+// smj_run's select stage over both tables (smj_select.cu): see smj_launch_select_plan2.
+struct SmjSelectJob {
+    const int32_t *d_in; int64_t n; int cols, sel_col; int64_t sel_val; int select_all, key_col;
+    u64 *buf[2];          // ping / pong pair arrays (n pairs each); the dense pairs go to buf[plan->npass & 1]
+    u64 *slots;           // n pairs of scratch: the select kernel's per-tile slots
+    u64 *d_status;        // [smj_select_num_tiles(n)] zeroed words: tile offsets + tile counts
+    u32 *d_hist;          // [4 * 256] zero: digit histogram of key - kmin, passes < npass
+    u64 *d_count;         // out: survivors
+    SmjSortPlan *plan;    // zeroed
+};
+// returns 1 (nothing launched) when a table cannot take the TMA path
+int smj_launch_select_plan2(SmjCtx *c, const SmjSelectJob job[2]);
+
 // ------------------------------------------------------------------ radix sort (smj_radix.cu)
 size_t smj_radix_num_tiles(u32 n);
 size_t smj_radix_status_words(u32 n);          // per pass
@@ -100,8 +119,11 @@ int smj_launch_radix_pass(SmjCtx *c, const u64 *d_in, u64 *d_out, const u64 *d_n
 int smj_radix_sort_pairs(SmjCtx *c, u64 *buf_a, u64 *buf_b, const u64 *d_n, u32 n_max, const u32 *d_hist,
                          u32 *d_scratch /*smj_radix_scratch_bytes(n_max), zero*/);
 // the same for one or two pair arrays in the same four launches (their tiles share the CTAs of each launch)
+// d_plan (may be null, or hold nulls): device sort plans.  With a plan, problem i's unsorted pairs are expected in
+// (plan->npass & 1 ? buf_b : buf_a)[i], d_hist[i] holds the digits of key - plan->kmin, and only npass passes do work;
+// the result is in buf_a[i] either way.
 int smj_radix_sort_pairs_n(SmjCtx *c, int nprob, u64 *const *buf_a, u64 *const *buf_b, const u64 *const *d_n, const u32 *n_max,
-                           const u32 *const *d_hist, u32 *const *d_scratch);
+                           const u32 *const *d_hist, u32 *const *d_scratch, const SmjSortPlan *const *d_plan = nullptr);
 size_t smj_radix_scratch_bytes(u32 n);         // bases + status(4 passes) + counters, all zero-initialised by caller
 
 // ------------------------------------------------------------------ gather (smj_gather.cu)

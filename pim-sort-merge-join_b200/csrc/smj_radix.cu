@@ -36,8 +36,8 @@ constexpr int RS_LB = 8;   // predecessors examined per look-back round
 constexpr size_t RS_SMEM = (size_t)RS_TILE * 8 + (size_t)RS_WARPS * SMJ_RADIX * 4 + (size_t)RS_WARPS * SMJ_RADIX * 4 +
                            SMJ_RADIX * 4 + 32 * 4;
 
-// digit `pass` (0..3) of the key half of a pair: one PRMT
-__device__ __forceinline__ u32 pair_digit(u64 p, u32 sel) { return __byte_perm((u32)(p >> 32), 0u, sel); }
+// digit `pass` (0..3) of the key half of a pair, relative to the table's smallest key (sort plan): one IADD + one PRMT
+__device__ __forceinline__ u32 pair_digit(u64 p, u32 sel, u32 kmin) { return __byte_perm((u32)(p >> 32) - kmin, 0u, sel); }
 
 // Why not __match_any_sync: MATCH.ANY runs on the SM-wide ADU pipe at ~61 cycles per warp instruction on sm_100
 // (profiles/r01_ubench_primitives.txt) and made the first version of this kernel ADU-bound (54 % pipe utilisation,
@@ -49,22 +49,22 @@ __device__ __forceinline__ u32 pair_digit(u64 p, u32 sel) { return __byte_perm((
 // the tile's 256 counts EARLY -> rank and reorder into shared memory -> batched look-back -> coalesced copy-out while
 // the next tile's loads are already in flight.
 template <bool FULL>
-__device__ __forceinline__ void radix_count_tile(const u64 (&item)[RS_IPT], u32 sel, u32 *my_cnt, u32 rel0, u32 valid)
+__device__ __forceinline__ void radix_count_tile(const u64 (&item)[RS_IPT], u32 sel, u32 kmin, u32 *my_cnt, u32 rel0, u32 valid)
 {
 #pragma unroll
     for (int j = 0; j < RS_IPT; j++) {
-        const u32 d = pair_digit(item[j], sel);
+        const u32 d = pair_digit(item[j], sel, kmin);
         if (FULL || rel0 + j * 32 < valid) atomicAdd(&my_cnt[d], 1u);
     }
 }
 
 template <bool FULL>
-__device__ __forceinline__ void radix_rank_tile(const u64 (&item)[RS_IPT], u32 sel, u32 *my_cnt, u32 *my_mask, u64 *s_items,
+__device__ __forceinline__ void radix_rank_tile(const u64 (&item)[RS_IPT], u32 sel, u32 kmin, u32 *my_cnt, u32 *my_mask, u64 *s_items,
                                                 u32 rel0, u32 valid, u32 lane, u32 lt)
 {
 #pragma unroll
     for (int j = 0; j < RS_IPT; j++) {
-        const u32 d = pair_digit(item[j], sel);
+        const u32 d = pair_digit(item[j], sel, kmin);
         const bool ok = FULL || rel0 + j * 32 < valid;
         u32 *mk = my_mask + d;
         if (ok) atomicOr(mk, 1u << lane);
@@ -86,13 +86,15 @@ __device__ __forceinline__ void radix_rank_tile(const u64 (&item)[RS_IPT], u32 s
 // One sort problem of a pass (one table's pair array).  A launch covers up to two of them: their tiles share one
 // ticket space (table 1's tiles first), so the CTAs run 2x as many tiles per launch and the wave-quantisation loss
 // (2.06 tiles per CTA = 3 tile times at the 10M-row config) is halved; every problem keeps its own look-back chain.
+// Pass p of a problem with npass planned passes reads buf[(npass - p) & 1] and writes the other buffer, so the last
+// pass always lands in buf[0]; passes >= npass have no tiles.  Without a plan: four passes from key 0.
 struct RadixProblem {
-    const u64 *in;
-    u64 *out;
+    u64 *buf[2];
     const u64 *n_dev;      // device count or null
     u32 n_max;
     const u32 *bin_base;   // [256] first output slot of each digit
     u32 *status, *status_next;
+    const SmjSortPlan *plan;   // device, or null
 };
 struct RadixLaunch { RadixProblem p[2]; int nprob; };
 
@@ -106,6 +108,9 @@ radix_pass_kernel(const RadixLaunch L, int pass, u32 *tile_counter, u32 *err)
     u32 *s_goff = s_mask + RS_WARPS * SMJ_RADIX;                   // [256] global slot minus local slot per digit
     u32 *s_wsum = s_goff + SMJ_RADIX;                              // warp totals of the bin scan
     __shared__ u32 s_tile[2];
+    __shared__ const u64 *s_in[2];   // per problem: this pass's source and destination buffers, smallest key
+    __shared__ u64 *s_out[2];
+    __shared__ u32 s_kmin[2];
 
     const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
     const u32 lt = lanemask_lt();
@@ -113,11 +118,25 @@ radix_pass_kernel(const RadixLaunch L, int pass, u32 *tile_counter, u32 *err)
     // sizes of both problems (device-resident counts), and the shared ticket space [0, tiles0) [tiles0, tiles0 + tiles1)
     u32 n0, n1 = 0;
     {
+        u32 np0 = SMJ_KEY_PASSES, np1 = SMJ_KEY_PASSES, km0 = 0, km1 = 0;
         const u64 v = L.p[0].n_dev ? *L.p[0].n_dev : (u64)L.p[0].n_max;
         n0 = v < (u64)L.p[0].n_max ? (u32)v : L.p[0].n_max;
+        if (L.p[0].plan) { np0 = L.p[0].plan->npass; km0 = L.p[0].plan->kmin; }
+        if ((u32)pass >= np0) n0 = 0;
         if (L.nprob > 1) {
             const u64 v1 = L.p[1].n_dev ? *L.p[1].n_dev : (u64)L.p[1].n_max;
             n1 = v1 < (u64)L.p[1].n_max ? (u32)v1 : L.p[1].n_max;
+            if (L.p[1].plan) { np1 = L.p[1].plan->npass; km1 = L.p[1].plan->kmin; }
+            if ((u32)pass >= np1) n1 = 0;
+        }
+        if (tid == 0) {
+            const bool odd0 = (np0 - (u32)pass) & 1u, odd1 = (np1 - (u32)pass) & 1u;
+            s_in[0] = odd0 ? L.p[0].buf[1] : L.p[0].buf[0];
+            s_out[0] = odd0 ? L.p[0].buf[0] : L.p[0].buf[1];
+            s_in[1] = odd1 ? L.p[1].buf[1] : L.p[1].buf[0];
+            s_out[1] = odd1 ? L.p[1].buf[0] : L.p[1].buf[1];
+            s_kmin[0] = km0;
+            s_kmin[1] = km1;
         }
     }
     const u32 tiles0 = (n0 + RS_TILE - 1) / RS_TILE;
@@ -134,7 +153,7 @@ radix_pass_kernel(const RadixLaunch L, int pass, u32 *tile_counter, u32 *err)
     u64 item[RS_IPT];
     if (ticket < all_tiles) {
         const bool second = ticket >= tiles0;
-        const u64 *src_in = second ? L.p[1].in : L.p[0].in;
+        const u64 *src_in = s_in[second];
         const u32 nn = second ? n1 : n0;
         const u32 g0 = (second ? ticket - tiles0 : ticket) * RS_TILE + rel0;
 #pragma unroll
@@ -149,7 +168,8 @@ radix_pass_kernel(const RadixLaunch L, int pass, u32 *tile_counter, u32 *err)
         const RadixProblem &P = second ? L.p[1] : L.p[0];
         const u32 n = second ? n1 : n0;
         const u32 tile = second ? ticket - tiles0 : ticket;
-        u64 *__restrict__ out = P.out;
+        u64 *__restrict__ out = s_out[second];
+        const u32 kmin = s_kmin[second];
         const u32 *__restrict__ bin_base = P.bin_base;
         u32 *status = P.status, *status_next = P.status_next;
         const u32 base = tile * RS_TILE;
@@ -162,8 +182,8 @@ radix_pass_kernel(const RadixLaunch L, int pass, u32 *tile_counter, u32 *err)
         PHASE(0);   // zero counters (+ wait for this tile's loads to be issued)
 
         // ---- early counts: per-warp digit histogram
-        if (full) radix_count_tile<true>(item, sel, my_cnt, rel0, valid);
-        else radix_count_tile<false>(item, sel, my_cnt, rel0, valid);
+        if (full) radix_count_tile<true>(item, sel, kmin, my_cnt, rel0, valid);
+        else radix_count_tile<false>(item, sel, kmin, my_cnt, rel0, valid);
         __syncthreads();
         PHASE(1);   // load latency + count
 
@@ -194,8 +214,8 @@ radix_pass_kernel(const RadixLaunch L, int pass, u32 *tile_counter, u32 *err)
         PHASE(2);   // digit totals, publish, scan
 
         // ---- rank (stable: lanes in order, rows in order, warps in order) and reorder into shared memory
-        if (full) radix_rank_tile<true>(item, sel, my_cnt, my_mask, s_items, rel0, valid, lane, lt);
-        else radix_rank_tile<false>(item, sel, my_cnt, my_mask, s_items, rel0, valid, lane, lt);
+        if (full) radix_rank_tile<true>(item, sel, kmin, my_cnt, my_mask, s_items, rel0, valid, lane, lt);
+        else radix_rank_tile<false>(item, sel, kmin, my_cnt, my_mask, s_items, rel0, valid, lane, lt);
 
         PHASE(3);   // rank + reorder (thread 0's view)
         // ---- next ticket, then this tile's look-back (predecessors published before they started ranking)
@@ -242,7 +262,7 @@ radix_pass_kernel(const RadixLaunch L, int pass, u32 *tile_counter, u32 *err)
         par ^= 1;
         if (next < all_tiles) {
             const bool nsecond = next >= tiles0;
-            const u64 *src_in = nsecond ? L.p[1].in : L.p[0].in;
+            const u64 *src_in = s_in[nsecond];
             const u32 nn = nsecond ? n1 : n0;
             const u32 g0 = (nsecond ? next - tiles0 : next) * RS_TILE + rel0;
 #pragma unroll
@@ -253,7 +273,7 @@ radix_pass_kernel(const RadixLaunch L, int pass, u32 *tile_counter, u32 *err)
             const u32 idx = tid + k * RS_THREADS;
             if (full || idx < valid) {
                 const u64 it = s_items[idx];
-                out[s_goff[pair_digit(it, sel)] + idx] = it;
+                out[s_goff[pair_digit(it, sel, kmin)] + idx] = it;
             }
         }
         PHASE(6);   // next loads issued + copy-out
@@ -283,9 +303,12 @@ __global__ void __launch_bounds__(256) radix_hist_kernel(const u64 *__restrict__
 }
 
 // bases[p][b] = number of keys whose digit p is < b (exclusive scan per pass); one CTA of 4 x 256 threads.
-__global__ void __launch_bounds__(SMJ_KEY_PASSES * SMJ_RADIX) radix_scan_kernel(const u32 *__restrict__ hist, u32 *bases)
+struct RadixScanArgs { const u32 *hist[2]; u32 *bases[2]; };
+__global__ void __launch_bounds__(SMJ_KEY_PASSES * SMJ_RADIX) radix_scan_kernel(const RadixScanArgs A)
 {
     __shared__ u32 s_w[SMJ_KEY_PASSES * SMJ_RADIX / 32];
+    const u32 *__restrict__ hist = A.hist[blockIdx.x];
+    u32 *bases = A.bases[blockIdx.x];
     const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
     const u32 v = hist[tid];
     const u32 inc = warp_incl_scan(v);
@@ -320,7 +343,8 @@ int smj_launch_radix_hist(SmjCtx *c, const u64 *d_pairs, u32 n, u32 *d_hist)
 
 int smj_launch_radix_scan(SmjCtx *c, const u32 *d_hist, u32 *d_bases)
 {
-    radix_scan_kernel<<<1, SMJ_KEY_PASSES * SMJ_RADIX, 0, c->stream>>>(d_hist, d_bases);
+    RadixScanArgs A = {{d_hist, nullptr}, {d_bases, nullptr}};
+    radix_scan_kernel<<<1, SMJ_KEY_PASSES * SMJ_RADIX, 0, c->stream>>>(A);
     KERNEL_CHECK(c);
     return SMJ_OK;
 }
@@ -347,7 +371,9 @@ int smj_launch_radix_pass(SmjCtx *c, const u64 *d_in, u64 *d_out, const u64 *d_n
 {
     RadixLaunch L = {};
     L.nprob = 1;
-    L.p[0] = {d_in, d_out, d_n, n_max, d_bases_pass, d_status, d_status_next};
+    // plan-less pass p reads buf[p & 1]
+    if (pass & 1) L.p[0] = {{d_out, const_cast<u64 *>(d_in)}, d_n, n_max, d_bases_pass, d_status, d_status_next, nullptr};
+    else L.p[0] = {{const_cast<u64 *>(d_in), d_out}, d_n, n_max, d_bases_pass, d_status, d_status_next, nullptr};
     return launch_radix_pass(c, L, pass, d_tile_counter);
 }
 
@@ -356,11 +382,11 @@ int smj_launch_radix_pass(SmjCtx *c, const u64 *d_in, u64 *d_out, const u64 *d_n
 // Four passes, so each result is back in buf_a[i].  Nothing here waits for the host: the pair counts are read on the
 // device, and a digit every key shares costs one identity-permutation pass instead of a host round trip.
 int smj_radix_sort_pairs_n(SmjCtx *c, int nprob, u64 *const *buf_a, u64 *const *buf_b, const u64 *const *d_n, const u32 *n_max,
-                           const u32 *const *d_hist, u32 *const *d_scratch)
+                           const u32 *const *d_hist, u32 *const *d_scratch, const SmjSortPlan *const *d_plan)
 {
     if (nprob < 1 || nprob > 2) return smj_set_error(SMJ_EINVAL, "radix sort of %d arrays at once (1 or 2)", nprob);
     u32 *d_bases[2], *d_counters[2], *d_status[2][2];
-    u64 *src[2], *dst[2];
+    RadixScanArgs SA = {};
     int live = 0, idx[2];
     for (int i = 0; i < nprob; i++) {
         if (n_max[i] > SMJ_MAX_SORT_ROWS) return smj_set_error(SMJ_ETOOBIG, "radix sort of %u pairs exceeds 2^30 - 1", n_max[i]);
@@ -369,11 +395,13 @@ int smj_radix_sort_pairs_n(SmjCtx *c, int nprob, u64 *const *buf_a, u64 *const *
         d_counters[live] = d_scratch[i] + SMJ_KEY_PASSES * SMJ_RADIX;
         d_status[live][0] = d_counters[live] + 16;
         d_status[live][1] = d_counters[live] + 16 + smj_radix_status_words(n_max[i]);
-        src[live] = buf_a[i]; dst[live] = buf_b[i];
-        SMJ_TRY(smj_launch_radix_scan(c, d_hist[i], d_bases[live]));
+        SA.hist[live] = d_hist[i];
+        SA.bases[live] = d_bases[live];
         idx[live++] = i;
     }
     if (live == 0) return SMJ_OK;
+    radix_scan_kernel<<<live, SMJ_KEY_PASSES * SMJ_RADIX, 0, c->stream>>>(SA);   // one CTA per problem
+    KERNEL_CHECK(c);
     // one event pair around the four back-to-back passes (per-pass event records cost more stream time than they measure)
     const bool timed = c->pass_count < SmjCtx::kMaxTimedPasses;
     if (timed) CUDA_TRY(smj_event_record(c->pass_ev[2 * c->pass_count], c->stream));
@@ -382,10 +410,10 @@ int smj_radix_sort_pairs_n(SmjCtx *c, int nprob, u64 *const *buf_a, u64 *const *
         L.nprob = live;
         for (int k = 0; k < live; k++) {
             const int i = idx[k];
-            L.p[k] = {src[k], dst[k], d_n[i], n_max[i], d_bases[k] + p * SMJ_RADIX, d_status[k][p & 1], d_status[k][(p + 1) & 1]};
+            L.p[k] = {{buf_a[i], buf_b[i]}, d_n[i], n_max[i], d_bases[k] + p * SMJ_RADIX, d_status[k][p & 1], d_status[k][(p + 1) & 1],
+                      d_plan ? d_plan[i] : nullptr};
         }
         SMJ_TRY(launch_radix_pass(c, L, p, d_counters[0] + p));   // the shared ticket counter lives in the first problem's scratch
-        for (int k = 0; k < live; k++) { u64 *t = src[k]; src[k] = dst[k]; dst[k] = t; }
     }
     if (timed) {
         CUDA_TRY(smj_event_record(c->pass_ev[2 * c->pass_count + 1], c->stream));

@@ -8,6 +8,7 @@
 // (late materialisation), so the select pass reads the table exactly once and writes 8 B per survivor.
 #include "smj_internal.h"
 #include "smj_dev.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -129,11 +130,16 @@ constexpr int SEL_MAX_COLS_TMA = SEL_STAGE_BYTES / 4 / SEL_THREADS;   // 32 colu
 constexpr int SELW_THREADS = SEL_THREADS + 32;                         // + producer warp
 constexpr size_t SELW_SMEM = (size_t)SEL_STAGES * SEL_STAGE_BYTES;
 
-template <bool HIST>
+// MODE 0: pairs only; 1: + 4 x 256 digit histogram of the surviving keys; 2: + min / max of the surviving keys into
+// *plan (the sort then runs only the passes the key RANGE needs, smj_radix.cu; the histogram of (key - min) digits is
+// built by the compaction copy, once the minimum is known).
+template <int MODE>
 __global__ void __launch_bounds__(SELW_THREADS)
 select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, int sel_col, int32_t sel_val, int select_all,
-                  int key_col, u32 rowid_base, u64 *__restrict__ slots, u32 *__restrict__ tile_count, u32 *hist, u32 num_tiles)
+                  int key_col, u32 rowid_base, u64 *__restrict__ slots, u32 *__restrict__ tile_count, u32 *hist, u32 num_tiles,
+                  SmjSortPlan *plan)
 {
+    constexpr bool HIST = MODE == 1;
     extern __shared__ __align__(128) unsigned char sel_smem[];      // stage ring
     __shared__ __align__(8) u64 s_full[SEL_STAGES], s_empty[SEL_STAGES];
     __shared__ u32 s_cnt[2][SEL_IPT * SEL_WARPS];
@@ -179,6 +185,7 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
     // ---------------------------------------------------- compute warps
     const u32 lt = lanemask_lt();
     u32 stage = 0, parity = 0, it = 0;
+    u32 tmin = 0xffffffffu, tmax = 0u;   // MODE 2: this thread's surviving flipped keys
     for (u32 tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
         mbar_wait(&s_full[stage], parity);
         const int64_t tile_base = (int64_t)tile * tile_rows;
@@ -234,6 +241,11 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
                     for (int d = 0; d < SMJ_KEY_PASSES; d++)
                         atomicAdd(&s_hist[d * SMJ_RADIX + ((k >> (d * SMJ_RADIX_BITS)) & (SMJ_RADIX - 1))], 1u);
                 }
+                if (MODE == 2) {
+                    const u32 k = pair_key(p);
+                    tmin = k < tmin ? k : tmin;
+                    tmax = k > tmax ? k : tmax;
+                }
             }
         }
         if (++stage == SEL_STAGES) { stage = 0; parity ^= 1u; }
@@ -243,6 +255,14 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
         for (u32 i = tid; i < SMJ_KEY_PASSES * SMJ_RADIX; i += SEL_THREADS) {
             const u32 v = s_hist[i];
             if (v) atomicAdd(&hist[i], v);
+        }
+    }
+    if (MODE == 2) {
+        // the arena is zeroed, so the minimum is accumulated as the maximum of the complement
+        const u32 wmin = __reduce_min_sync(FULL_MASK, tmin), wmax = __reduce_max_sync(FULL_MASK, tmax);
+        if (lane == 0 && wmin <= wmax) {
+            atomicMax(&plan->kmin_inv, ~wmin);
+            atomicMax(&plan->kmax, wmax);
         }
     }
 }
@@ -290,6 +310,92 @@ select_compact_kernel(const u64 *__restrict__ slots, const u32 *__restrict__ cou
     }
 }
 
+// ---- smj_run's variant of the two kernels above: both tables per launch, and the sort plan.
+// plan_scan_kernel (one CTA per table): tile offsets and the survivor count as in tile_scan_kernel, then the sort plan
+// from the key range the select kernel left in *plan: LSD passes run over (key - kmin), so a table whose surviving keys
+// span R values needs ceil(log2(R) / 8) passes instead of four (the reference draws its keys from [1, 3n],
+// data/generate_data.py:9).  full_passes forces four passes from key 0 (A/B measurements, SMJ_FULL_PASSES=1).
+struct PlanScanJob { const u32 *counts; u32 num_tiles; u64 *offsets; u64 *total; SmjSortPlan *plan; };
+struct PlanScanArgs { PlanScanJob t[2]; int full_passes; };
+
+__global__ void __launch_bounds__(TS_THREADS) plan_scan_kernel(const PlanScanArgs A)
+{
+    __shared__ u64 s_w[TS_THREADS / 32];
+    const PlanScanJob J = blockIdx.x ? A.t[1] : A.t[0];   // (a dynamic index would copy the parameters to local memory)
+    const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+    const u32 num_tiles = J.num_tiles;
+    const u32 chunk = (num_tiles + TS_THREADS - 1) / TS_THREADS;
+    const u32 lo = tid * chunk < num_tiles ? tid * chunk : num_tiles;
+    const u32 hi = lo + chunk < num_tiles ? lo + chunk : num_tiles;
+    u64 sum = 0;
+    for (u32 i = lo; i < hi; i++) sum += J.counts[i];
+    u64 inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u64 t = __shfl_up_sync(FULL_MASK, inc, o);
+        if (lane >= (u32)o) inc += t;
+    }
+    if (lane == 31) s_w[w] = inc;
+    __syncthreads();
+    u64 run = inc - sum;
+    for (u32 ww = 0; ww < w; ww++) run += s_w[ww];
+    if (tid == TS_THREADS - 1) {
+        const u64 total = run + sum;
+        *J.total = total;
+        u32 kmin = ~J.plan->kmin_inv, npass = 0;
+        const u32 kmax = J.plan->kmax;
+        if (total >= 2 && kmax > kmin) npass = (32u - (u32)__clz(kmax - kmin) + 7u) / 8u;
+        if (total == 0) kmin = 0;
+        if (A.full_passes) { kmin = 0; npass = SMJ_KEY_PASSES; }
+        J.plan->kmin = kmin;
+        J.plan->npass = npass;
+    }
+    for (u32 i = lo; i < hi; i++) { J.offsets[i] = run; run += J.counts[i]; }
+}
+
+// The compaction copy of both tables in one launch (one warp per tile, table 1's tiles first), fused with the digit
+// histograms of (key - kmin) for the passes the plan runs.  The dense pairs land in buf[npass & 1]: pass p reads
+// buf[(npass - p) & 1] and writes the other one, so the sorted pairs always end in buf[0].
+struct PlanCompactJob { const u64 *slots; const u32 *counts; const u64 *offsets; u32 num_tiles, tile_rows; u64 *buf[2];
+                        const SmjSortPlan *plan; u32 *hist; };
+struct PlanCompactArgs { PlanCompactJob t[2]; };
+
+__global__ void __launch_bounds__(256) plan_compact_kernel(const PlanCompactArgs A)
+{
+    __shared__ u32 s_hist[2][SMJ_KEY_PASSES * SMJ_RADIX];
+    const u32 tid = threadIdx.x, lane = tid & 31u;
+    for (u32 i = tid; i < 2 * SMJ_KEY_PASSES * SMJ_RADIX; i += 256) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    const u32 tiles0 = A.t[0].num_tiles, all_tiles = tiles0 + A.t[1].num_tiles;
+    const u32 warps = gridDim.x * 8u;
+    for (u32 g = blockIdx.x * 8u + (tid >> 5); g < all_tiles; g += warps) {
+        const bool tb = g >= tiles0;
+        const u32 t = tb ? g - tiles0 : g;
+        const SmjSortPlan *plan = tb ? A.t[1].plan : A.t[0].plan;
+        const u32 kmin = plan->kmin, npass = plan->npass;
+        const u32 cnt = (tb ? A.t[1].counts : A.t[0].counts)[t];
+        const u64 *src = (tb ? A.t[1].slots : A.t[0].slots) + (size_t)t * (tb ? A.t[1].tile_rows : A.t[0].tile_rows);
+        u64 *dst = (tb ? ((npass & 1u) ? A.t[1].buf[1] : A.t[1].buf[0]) : ((npass & 1u) ? A.t[0].buf[1] : A.t[0].buf[0])) +
+                   (tb ? A.t[1].offsets : A.t[0].offsets)[t];
+        u32 *h = s_hist[tb];
+#pragma unroll 4
+        for (u32 i = lane; i < cnt; i += 32) {
+            const u64 p = src[i];
+            dst[i] = p;
+            const u32 d = pair_key(p) - kmin;
+            if (npass > 0) atomicAdd(&h[d & 255u], 1u);
+            if (npass > 1) atomicAdd(&h[SMJ_RADIX + ((d >> 8) & 255u)], 1u);
+            if (npass > 2) atomicAdd(&h[2 * SMJ_RADIX + ((d >> 16) & 255u)], 1u);
+            if (npass > 3) atomicAdd(&h[3 * SMJ_RADIX + (d >> 24)], 1u);
+        }
+    }
+    __syncthreads();
+    for (u32 i = tid; i < 2 * SMJ_KEY_PASSES * SMJ_RADIX; i += 256) {
+        const u32 v = (&s_hist[0][0])[i];
+        if (v) atomicAdd(&(i >= SMJ_KEY_PASSES * SMJ_RADIX ? A.t[1].hist : A.t[0].hist)[i % (SMJ_KEY_PASSES * SMJ_RADIX)], v);
+    }
+}
+
 }  // namespace
 
 // rows per thread per tile for the TMA path: the largest power-of-two count (<= 8) whose tile fits one stage
@@ -302,6 +408,15 @@ static int select_ipt(int cols)
 static bool select_use_tma(const int32_t *d_in, int cols)
 {
     return cols <= SEL_MAX_COLS_TMA && (((uintptr_t)d_in) & 15) == 0;
+}
+
+static int select_set_attrs(SmjCtx *c)   // function attributes are per device
+{
+    CUDA_TRY(cudaFuncSetAttribute(select_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SELW_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(select_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SELW_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(select_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SELW_SMEM));
+    c->select_attr_set = true;
+    return SMJ_OK;
 }
 
 // scratch words (u64) per table: look-back status (fallback kernel) or tile offsets + tile counts (TMA path);
@@ -325,19 +440,17 @@ int smj_launch_select_pairs(SmjCtx *c, const int32_t *d_in, int64_t n, int cols,
         const u32 tiles = (u32)((n + tile_rows - 1) / tile_rows);
         const size_t smem = SELW_SMEM;
         if (!c->select_attr_set) {
-            CUDA_TRY(cudaFuncSetAttribute(select_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CUDA_TRY(cudaFuncSetAttribute(select_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            c->select_attr_set = true;
+            SMJ_TRY(select_set_attrs(c));
         }
         u64 *d_offsets = d_status;                                   // [tiles]
         u32 *d_counts = reinterpret_cast<u32 *>(d_status + tiles);   // [tiles]
         const u32 grid = tiles < (u32)(sms * SMJ_SEL_CTAS) ? tiles : (u32)(sms * SMJ_SEL_CTAS);
         if (d_hist)
-            select_tma_kernel<true><<<grid, SELW_THREADS, smem, c->stream>>>(d_in, n, cols, ipt, sel_col, (int32_t)sel_val, select_all,
-                                                                            key_col, rowid_base, d_tmp, d_counts, d_hist, tiles);
+            select_tma_kernel<1><<<grid, SELW_THREADS, smem, c->stream>>>(d_in, n, cols, ipt, sel_col, (int32_t)sel_val, select_all,
+                                                                         key_col, rowid_base, d_tmp, d_counts, d_hist, tiles, nullptr);
         else
-            select_tma_kernel<false><<<grid, SELW_THREADS, smem, c->stream>>>(d_in, n, cols, ipt, sel_col, (int32_t)sel_val, select_all,
-                                                                             key_col, rowid_base, d_tmp, d_counts, nullptr, tiles);
+            select_tma_kernel<0><<<grid, SELW_THREADS, smem, c->stream>>>(d_in, n, cols, ipt, sel_col, (int32_t)sel_val, select_all,
+                                                                         key_col, rowid_base, d_tmp, d_counts, nullptr, tiles, nullptr);
         KERNEL_CHECK(c);
         tile_scan_kernel<<<1, TS_THREADS, 0, c->stream>>>(d_counts, tiles, d_offsets, d_count);
         KERNEL_CHECK(c);
@@ -357,5 +470,53 @@ int smj_launch_select_pairs(SmjCtx *c, const int32_t *d_in, int64_t n, int cols,
                                                                        select_all, key_col, rowid_base, d_pairs, d_status,
                                                                        d_tile_counter, nullptr, d_count, tiles, c->d_err);
     KERNEL_CHECK(c);
+    return SMJ_OK;
+}
+
+// smj_run's select stage, both tables: select (key min / max instead of histograms) per table, ONE scan launch (tile
+// offsets, survivor counts, sort plans), ONE compaction launch (dense pairs into the buffer the plan names + digit
+// histograms of key - kmin).  Returns 1 without launching anything when a table cannot take the TMA path (the caller
+// then uses smj_launch_select_pairs and a plan-less four-pass sort).
+int smj_launch_select_plan2(SmjCtx *c, const SmjSelectJob job[2])
+{
+    for (int t = 0; t < 2; t++)
+        if (job[t].n > 0 && !select_use_tma(job[t].d_in, job[t].cols)) return 1;
+    static const int full_passes = (getenv("SMJ_FULL_PASSES") && atoi(getenv("SMJ_FULL_PASSES")) != 0) ? 1 : 0;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    if (!c->select_attr_set) SMJ_TRY(select_set_attrs(c));
+    PlanScanArgs SA = {};
+    PlanCompactArgs CA = {};
+    SA.full_passes = full_passes;
+    u32 all_tiles = 0;
+    for (int t = 0; t < 2; t++) {
+        const SmjSelectJob &J = job[t];
+        int select_all = J.select_all;
+        int64_t sel_val = J.sel_val;
+        // cell is int32: cell > val is always true below INT32_MIN and never true from INT32_MAX up (cpu_app.c:88)
+        if (sel_val < (int64_t)INT32_MIN) select_all = 1;
+        const bool none = J.n <= 0 || (!select_all && sel_val >= (int64_t)INT32_MAX);
+        const int ipt = select_ipt(J.cols);
+        const int64_t tile_rows = (int64_t)ipt * SEL_THREADS;
+        const u32 tiles = none ? 0u : (u32)((J.n + tile_rows - 1) / tile_rows);
+        u64 *d_offsets = J.d_status;                                   // [tiles]
+        u32 *d_counts = reinterpret_cast<u32 *>(J.d_status + tiles);   // [tiles]
+        if (tiles) {
+            const u32 grid = tiles < (u32)(sms * SMJ_SEL_CTAS) ? tiles : (u32)(sms * SMJ_SEL_CTAS);
+            select_tma_kernel<2><<<grid, SELW_THREADS, SELW_SMEM, c->stream>>>(J.d_in, J.n, J.cols, ipt, J.sel_col, (int32_t)sel_val, select_all,
+                                                                              J.key_col, 0u, J.slots, d_counts, nullptr, tiles, J.plan);
+            KERNEL_CHECK(c);
+        }
+        SA.t[t] = {d_counts, tiles, d_offsets, J.d_count, J.plan};
+        CA.t[t] = {J.slots, d_counts, d_offsets, tiles, (u32)tile_rows, {J.buf[0], J.buf[1]}, J.plan, J.d_hist};
+        all_tiles += tiles;
+    }
+    plan_scan_kernel<<<2, TS_THREADS, 0, c->stream>>>(SA);
+    KERNEL_CHECK(c);
+    if (all_tiles) {
+        const u32 cgrid = (all_tiles + 7) / 8 < (u32)(sms * 8) ? (all_tiles + 7) / 8 : (u32)(sms * 8);
+        plan_compact_kernel<<<cgrid, 256, 0, c->stream>>>(CA);
+        KERNEL_CHECK(c);
+    }
     return SMJ_OK;
 }

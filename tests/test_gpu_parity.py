@@ -226,6 +226,38 @@ def test_run_random_knobs(smj, port, seed):
     assert_same(got, want, f"run seed={seed} knobs={kn}")
 
 
+@pytest.mark.parametrize("lo1,hi1,lo2,hi2", [
+    (7, 8, 7, 8),                          # every key equal: no radix pass runs at all
+    (100, 300, 150, 330),                  # one pass (range < 256)
+    (-200, 60_000, 10, 40_000),            # two passes, negative keys, different minima
+    (1_000_000, 16_000_000, 5, 250),       # three passes left, one pass right (tables take part in different launches)
+    (I32MIN, I32MIN + 70_000, I32MAX - 70_000, I32MAX),   # disjoint ranges at the int32 extremes
+    (I32MIN, I32MAX, -5, 5),               # the full 32-bit range: four passes
+    (0, 1 << 24, 1, (1 << 24) + 2),        # ranges straddling the 3 / 4 pass boundary
+])
+def test_run_key_range_sort_plans(smj, port, lo1, hi1, lo2, hi2):
+    """smj_run sorts digits of (key - smallest surviving key) and runs ceil(bits(range) / 8) passes per table, decided
+    on the device (smj_select.cu plan_scan_kernel): every pass count, and the result must not depend on it."""
+    rng = np.random.default_rng(abs(lo1) % 1000 + 3)
+    n1, n2 = 70_001, 50_003
+    t1, t2 = rand_table(rng, n1, 3, 0, 1000), rand_table(rng, n2, 4, 0, 1000)
+    t1[:, 1] = rng.integers(lo1, hi1, size=n1, dtype=np.int64, endpoint=(hi1 == I32MAX)).astype(np.int32)
+    t2[:, 2] = rng.integers(lo2, hi2, size=n2, dtype=np.int64, endpoint=(hi2 == I32MAX)).astype(np.int32)
+    # a shared band of keys so that the join is not empty when the ranges overlap at all
+    if max(lo1, lo2) < min(hi1, hi2):
+        band = rng.integers(max(lo1, lo2), min(hi1, hi2), size=5000, dtype=np.int64).astype(np.int32)
+        t1[:5000, 1] = band
+        t2[100:5100, 2] = band[::-1]
+    kn = dict(select_col1=0, select_val1=100, select_col2=1, select_val2=200, join_key1=1, join_key2=2)
+    want, sel, _ = port.run(t1, t2, 0, 100, 1, 200, 1, 2)
+    for _ in range(3):   # eager, graph capture, graph replay
+        got, st = smj.run(t1, t2, **kn)
+        assert st["rows_selected"] == list(sel)
+        assert_same(got, want, f"run key ranges [{lo1},{hi1}) x [{lo2},{hi2})")
+    passes = lambda lo, hi: (int(hi - lo).bit_length() + 7) // 8   # an upper bound of the passes the plan may run
+    assert 0 <= st["sort_passes"] <= max(passes(lo1, hi1), passes(lo2, hi2))
+
+
 def test_run_many_to_many_mode(smj, port):
     """smj_run with join_mode = SMJ_JOIN_MANY (extension): select -> sort -> every pair of equal keys."""
     rng = np.random.default_rng(77)
