@@ -144,6 +144,54 @@ __device__ __forceinline__ u64 lookback_warp(u64 *status, u32 tile, u64 aggregat
 }
 
 
+// ---- one-CTA exclusive scan of per-tile counts (1024 threads): offsets[t] = sum of counts[0..t), returns the total to
+// every thread.  Up to SCAN1_STAGE counts are staged in shared memory with eight independent coalesced loads in flight
+// per thread (one L2/DRAM round trip), each thread then scans its contiguous chunk out of shared memory; the first
+// version walked its chunk straight from global memory, one dependent round trip per element.
+#define SCAN1_THREADS 1024
+#define SCAN1_STAGE 8192
+__device__ __forceinline__ u64 scan1_counts(const u32 *__restrict__ counts, u32 num_tiles, u64 *offsets, u32 *s_stage /*[SCAN1_STAGE]*/,
+                                            u64 *s_w /*[32]*/)
+{
+    const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+    const bool staged = num_tiles <= SCAN1_STAGE;
+    if (staged) {
+        u32 v[SCAN1_STAGE / SCAN1_THREADS];
+#pragma unroll
+        for (int k = 0; k < SCAN1_STAGE / SCAN1_THREADS; k++) {
+            const u32 i = k * SCAN1_THREADS + tid;
+            v[k] = i < num_tiles ? counts[i] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < SCAN1_STAGE / SCAN1_THREADS; k++) s_stage[k * SCAN1_THREADS + tid] = v[k];
+        __syncthreads();
+    }
+    const u32 chunk = (num_tiles + SCAN1_THREADS - 1) / SCAN1_THREADS;
+    const u32 lo = tid * chunk < num_tiles ? tid * chunk : num_tiles;
+    const u32 hi = lo + chunk < num_tiles ? lo + chunk : num_tiles;
+    u64 sum = 0;
+    if (staged) for (u32 i = lo; i < hi; i++) sum += s_stage[i];
+    else for (u32 i = lo; i < hi; i++) sum += counts[i];
+    u64 inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u64 t = __shfl_up_sync(FULL_MASK, inc, o);
+        if (lane >= (u32)o) inc += t;
+    }
+    if (lane == 31) s_w[w] = inc;
+    __syncthreads();
+    u64 run = inc - sum, total = 0;
+#pragma unroll
+    for (u32 ww = 0; ww < SCAN1_THREADS / 32; ww++) {
+        const u64 x = s_w[ww];
+        if (ww < w) run += x;
+        total += x;
+    }
+    if (staged) for (u32 i = lo; i < hi; i++) { offsets[i] = run; run += s_stage[i]; }
+    else for (u32 i = lo; i < hi; i++) { offsets[i] = run; run += counts[i]; }
+    return total;
+}
+
 // ---- mbarrier / bulk-copy (TMA) / named-barrier primitives for the warp-specialised pipelines (sm_90+ PTX)
 __device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(u64 *bar, u32 count)

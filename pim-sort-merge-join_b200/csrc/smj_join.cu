@@ -259,29 +259,14 @@ join_match_kernel(const u64 *__restrict__ L, const u64 *__restrict__ R, const u6
 }
 
 // Exclusive scan of per-tile counts (one CTA): offsets[t] = sum of counts[0..t), *total = sum of all.
-constexpr int JS_THREADS = 1024;
+constexpr int JS_THREADS = SCAN1_THREADS;
 __global__ void __launch_bounds__(JS_THREADS)
 join_scan_kernel(const u32 *__restrict__ tile_count, u32 num_tiles, u64 *offsets, u64 *total)
 {
+    __shared__ u32 s_stage[SCAN1_STAGE];
     __shared__ u64 s_w[JS_THREADS / 32];
-    const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
-    const u32 chunk = (num_tiles + JS_THREADS - 1) / JS_THREADS;
-    const u32 lo = tid * chunk < num_tiles ? tid * chunk : num_tiles;
-    const u32 hi = lo + chunk < num_tiles ? lo + chunk : num_tiles;
-    u64 sum = 0;
-    for (u32 i = lo; i < hi; i++) sum += tile_count[i];
-    u64 inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const u64 t = __shfl_up_sync(FULL_MASK, inc, o);
-        if (lane >= (u32)o) inc += t;
-    }
-    if (lane == 31) s_w[w] = inc;
-    __syncthreads();
-    u64 run = inc - sum;
-    for (u32 ww = 0; ww < w; ww++) run += s_w[ww];
-    if (tid == JS_THREADS - 1) *total = run + sum;
-    for (u32 i = lo; i < hi; i++) { offsets[i] = run; run += tile_count[i]; }
+    const u64 t = scan1_counts(tile_count, num_tiles, offsets, s_stage, s_w);
+    if (threadIdx.x == 0) *total = t;
 }
 
 // dense[offsets[t] + i] = slots[t * JN_TILE + i], i < tile_count[t]: the matches in result order, contiguous.

@@ -269,28 +269,13 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
 
 // Exclusive scan of per-tile counts (one CTA): offsets[t] = sum of counts[0..t), *total = sum of all.
 // Each thread owns a contiguous chunk, so the block-level part is one scan of 1024 partial sums.
-constexpr int TS_THREADS = 1024;
+constexpr int TS_THREADS = SCAN1_THREADS;
 __global__ void __launch_bounds__(TS_THREADS) tile_scan_kernel(const u32 *__restrict__ counts, u32 num_tiles, u64 *offsets, u64 *total)
 {
+    __shared__ u32 s_stage[SCAN1_STAGE];
     __shared__ u64 s_w[TS_THREADS / 32];
-    const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
-    const u32 chunk = (num_tiles + TS_THREADS - 1) / TS_THREADS;
-    const u32 lo = tid * chunk < num_tiles ? tid * chunk : num_tiles;
-    const u32 hi = lo + chunk < num_tiles ? lo + chunk : num_tiles;
-    u64 sum = 0;
-    for (u32 i = lo; i < hi; i++) sum += counts[i];
-    u64 inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const u64 t = __shfl_up_sync(FULL_MASK, inc, o);
-        if (lane >= (u32)o) inc += t;
-    }
-    if (lane == 31) s_w[w] = inc;
-    __syncthreads();
-    u64 run = inc - sum;
-    for (u32 ww = 0; ww < w; ww++) run += s_w[ww];
-    if (tid == TS_THREADS - 1) *total = run + sum;
-    for (u32 i = lo; i < hi; i++) { offsets[i] = run; run += counts[i]; }
+    const u64 t = scan1_counts(counts, num_tiles, offsets, s_stage, s_w);
+    if (threadIdx.x == 0) *total = t;
 }
 
 // pairs[offsets[t] + i] = slots[t * tile_rows + i], i < counts[t]: the survivors in table order, contiguous.
@@ -320,27 +305,11 @@ struct PlanScanArgs { PlanScanJob t[2]; int full_passes; };
 
 __global__ void __launch_bounds__(TS_THREADS) plan_scan_kernel(const PlanScanArgs A)
 {
+    __shared__ u32 s_stage[SCAN1_STAGE];
     __shared__ u64 s_w[TS_THREADS / 32];
     const PlanScanJob J = blockIdx.x ? A.t[1] : A.t[0];   // (a dynamic index would copy the parameters to local memory)
-    const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
-    const u32 num_tiles = J.num_tiles;
-    const u32 chunk = (num_tiles + TS_THREADS - 1) / TS_THREADS;
-    const u32 lo = tid * chunk < num_tiles ? tid * chunk : num_tiles;
-    const u32 hi = lo + chunk < num_tiles ? lo + chunk : num_tiles;
-    u64 sum = 0;
-    for (u32 i = lo; i < hi; i++) sum += J.counts[i];
-    u64 inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const u64 t = __shfl_up_sync(FULL_MASK, inc, o);
-        if (lane >= (u32)o) inc += t;
-    }
-    if (lane == 31) s_w[w] = inc;
-    __syncthreads();
-    u64 run = inc - sum;
-    for (u32 ww = 0; ww < w; ww++) run += s_w[ww];
-    if (tid == TS_THREADS - 1) {
-        const u64 total = run + sum;
+    const u64 total = scan1_counts(J.counts, J.num_tiles, J.offsets, s_stage, s_w);
+    if (threadIdx.x == 0) {
         *J.total = total;
         u32 kmin = ~J.plan->kmin_inv, npass = 0;
         const u32 kmax = J.plan->kmax;
@@ -350,7 +319,6 @@ __global__ void __launch_bounds__(TS_THREADS) plan_scan_kernel(const PlanScanArg
         J.plan->kmin = kmin;
         J.plan->npass = npass;
     }
-    for (u32 i = lo; i < hi; i++) { J.offsets[i] = run; run += J.counts[i]; }
 }
 
 // The compaction copy of both tables in one launch (one warp per tile, table 1's tiles first), fused with the digit
@@ -359,6 +327,7 @@ __global__ void __launch_bounds__(TS_THREADS) plan_scan_kernel(const PlanScanArg
 struct PlanCompactJob { const u64 *slots; const u32 *counts; const u64 *offsets; u32 num_tiles, tile_rows; u64 *buf[2];
                         const SmjSortPlan *plan; u32 *hist; };
 struct PlanCompactArgs { PlanCompactJob t[2]; };
+constexpr int PC_UNROLL = 8;
 
 __global__ void __launch_bounds__(256) plan_compact_kernel(const PlanCompactArgs A)
 {
@@ -378,15 +347,27 @@ __global__ void __launch_bounds__(256) plan_compact_kernel(const PlanCompactArgs
         u64 *dst = (tb ? ((npass & 1u) ? A.t[1].buf[1] : A.t[1].buf[0]) : ((npass & 1u) ? A.t[0].buf[1] : A.t[0].buf[0])) +
                    (tb ? A.t[1].offsets : A.t[0].offsets)[t];
         u32 *h = s_hist[tb];
-#pragma unroll 4
-        for (u32 i = lane; i < cnt; i += 32) {
-            const u64 p = src[i];
-            dst[i] = p;
-            const u32 d = pair_key(p) - kmin;
-            if (npass > 0) atomicAdd(&h[d & 255u], 1u);
-            if (npass > 1) atomicAdd(&h[SMJ_RADIX + ((d >> 8) & 255u)], 1u);
-            if (npass > 2) atomicAdd(&h[2 * SMJ_RADIX + ((d >> 16) & 255u)], 1u);
-            if (npass > 3) atomicAdd(&h[3 * SMJ_RADIX + (d >> 24)], 1u);
+        // eight independent 256-byte loads in flight per warp before the first dependent store: the first version
+        // (load, store, atomics per iteration, no __restrict__) exposed one DRAM round trip per 32 pairs
+        for (u32 i0 = 0; i0 < cnt; i0 += 32 * PC_UNROLL) {
+            u64 v[PC_UNROLL];
+#pragma unroll
+            for (int k = 0; k < PC_UNROLL; k++) {
+                const u32 i = i0 + k * 32 + lane;
+                v[k] = i < cnt ? __ldg(src + i) : 0ull;
+            }
+#pragma unroll
+            for (int k = 0; k < PC_UNROLL; k++) {
+                const u32 i = i0 + k * 32 + lane;
+                if (i < cnt) {
+                    dst[i] = v[k];
+                    const u32 d = pair_key(v[k]) - kmin;
+                    if (npass > 0) atomicAdd(&h[d & 255u], 1u);
+                    if (npass > 1) atomicAdd(&h[SMJ_RADIX + ((d >> 8) & 255u)], 1u);
+                    if (npass > 2) atomicAdd(&h[2 * SMJ_RADIX + ((d >> 16) & 255u)], 1u);
+                    if (npass > 3) atomicAdd(&h[3 * SMJ_RADIX + (d >> 24)], 1u);
+                }
+            }
         }
     }
     __syncthreads();
