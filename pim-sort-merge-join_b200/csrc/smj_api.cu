@@ -24,6 +24,20 @@ int smj_set_error(int code, const char *fmt, ...)
     return code;
 }
 
+// SMJ_STAGE_EVENTS=0 drops the event records between the stages (and around the radix passes) from the pipeline, so
+// that the whole chain of kernels is linked by programmatic dependencies; the per-stage times of smj_stats_t are then 0.
+bool smj_stage_events(void)
+{
+    static const bool on = !(getenv("SMJ_STAGE_EVENTS") && atoi(getenv("SMJ_STAGE_EVENTS")) == 0);
+    return on;
+}
+
+bool smj_pdl_enabled(void)
+{
+    static const bool on = !(getenv("SMJ_PDL") && atoi(getenv("SMJ_PDL")) == 0);
+    return on;
+}
+
 int smj_cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 {
     const char *base = strrchr(file, '/');
@@ -763,6 +777,7 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
     if (!replay) {
         const int64_t l0 = c->launches;
         if (capture) CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        c->capturing = capture;
         int rc = SMJ_OK;
         do {
 #define PIPE_TRY(x) if ((rc = (x)) != SMJ_OK) break
@@ -782,7 +797,6 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
                 rc = smj_launch_select_pairs(c, d_t[t], n[t], cc[t], sel_col[t], sel_val[t], 0, key[t], 0, ping[t], pong[t],
                                              (u64 *)(scr + off_sel + (t ? stiles[0] * 8 : 0)), &h->counter[t], h->hist[t], &h->count[t]);
             if (rc != SMJ_OK) break;
-            PIPE_CUDA(smj_event_record(c->ev[E_SELECT], c->stream));
             // sort: 4 onesweep passes per table over the device-resident survivor counts
             {   // both tables in the same four launches
                 const u64 *dn[2] = {&h->count[0], &h->count[1]};
@@ -794,7 +808,13 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
                 c->run_planned = planned;
             }
             if (rc != SMJ_OK) break;
-            PIPE_CUDA(smj_event_record(c->ev[E_SORT], c->stream));
+            // the event pair around the radix passes doubles as the select | sort | join boundaries: every event-record
+            // node inside the graph costs ~3.5 us of stream time (0.489 vs 0.475 ms per step with four / no records)
+            c->stage_from_pass = c->pass_count > 0;
+            if (!c->stage_from_pass && smj_stage_events()) {
+                PIPE_CUDA(smj_event_record(c->ev[E_SELECT], c->stream));
+                PIPE_CUDA(smj_event_record(c->ev[E_SORT], c->stream));
+            }
             // join: co-rank, count, scan, compact the matches; then materialise rows straight from the input tables
             const JoinScratch jsr = join_scratch(scr + off_join, jt);
             PIPE_TRY(smj_launch_join_match(c, ping[0], ping[1], &h->count[0], (u32)n[0], (u32)n[1], SMJ_JOIN_ZIP, jsr.part, jsr.tile_count,
@@ -803,6 +823,7 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
 #undef PIPE_TRY
 #undef PIPE_CUDA
         } while (0);
+        c->capturing = false;
         if (capture) {
             cudaGraph_t g = nullptr;
             cudaError_t e = cudaStreamEndCapture(c->stream, &g);
@@ -820,7 +841,7 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
     if (replay || capture) {
         CUDA_TRY(cudaGraphLaunch(c->graph_exec, c->stream));
         c->launches += c->graph_launches;
-        c->pass_count = 1;   // the timed sort group (both tables, four launches) is a pair of event-record nodes of the graph
+        c->pass_count = c->stage_from_pass ? 1 : 0;   // the timed sort group (both tables, four launches) is a pair of event-record nodes of the graph
     }
     CUDA_TRY(cudaEventRecord(c->ev[E_JOIN], c->stream));
 
@@ -859,9 +880,12 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
     if (stats) {
         memset(stats, 0, sizeof *stats);
         stats->h2d_ms = ev_ms(c->ev[E_START], c->ev[E_H2D]);
-        stats->select_ms = ev_ms(c->ev[E_H2D], c->ev[E_SELECT]);
-        stats->sort_ms = ev_ms(c->ev[E_SELECT], c->ev[E_SORT]);
-        stats->join_ms = ev_ms(c->ev[E_SORT], c->ev[E_JOIN]);
+        if (smj_stage_events()) {   // select = through the histogram scan; sort = the radix pass launches
+            cudaEvent_t es = c->stage_from_pass ? c->pass_ev[0] : c->ev[E_SELECT], eo = c->stage_from_pass ? c->pass_ev[1] : c->ev[E_SORT];
+            stats->select_ms = ev_ms(c->ev[E_H2D], es);
+            stats->sort_ms = ev_ms(es, eo);
+            stats->join_ms = ev_ms(eo, c->ev[E_JOIN]);
+        }
         stats->d2h_ms = ev_ms(c->ev[E_JOIN], c->ev[E_D2H]);
         stats->total_device_ms = ev_ms(c->ev[E_H2D], c->ev[E_JOIN]);
         for (int t = 0; t < 2; t++) { stats->rows_in[t] = n[t]; stats->rows_selected[t] = m[t]; }
@@ -869,6 +893,7 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
         stats->bytes_model = bytes_model(n, cc, m, j);
         stats->kernel_launches = c->launches - launches0;
         double sum = 0;
+        if (!smj_stage_events()) c->pass_count = 0;
         for (int p = 0; p < c->pass_count; p++) sum += ev_ms(c->pass_ev[2 * p], c->pass_ev[2 * p + 1]);
         // each timed group is four pass launches (both tables in each); with a sort plan only the first
         // max(npass) of them have tiles, and table t takes part in npass[t] of those

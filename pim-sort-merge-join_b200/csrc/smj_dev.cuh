@@ -192,6 +192,18 @@ __device__ __forceinline__ u64 scan1_counts(const u32 *__restrict__ counts, u32 
     return total;
 }
 
+// ---- programmatic dependent launch (sm_90+): every kernel of the smj_run pipeline starts with PDL_ENTER().  When the
+// launch carries cudaLaunchAttributeProgrammaticStreamSerialization, `wait` blocks until the preceding kernel has
+// completed and its writes are visible, and `launch_dependents` lets the NEXT kernel's CTAs become resident (and park
+// at their own wait) as this kernel's CTAs retire, so launch latency and ramp-up overlap the tail.  Because the trigger
+// comes after the wait, at most two kernels are ever co-resident.  Without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_enter()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#define PDL_ENTER() pdl_enter()
+
 // ---- mbarrier / bulk-copy (TMA) / named-barrier primitives for the warp-specialised pipelines (sm_90+ PTX)
 __device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(u64 *bar, u32 count)

@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(256)
 join_partition_kernel(const u64 *__restrict__ L, const u64 *__restrict__ R, const u64 *__restrict__ counts, u32 m1_max,
                       u32 m2_max, u32 *part, u32 *runstart)
 {
+    PDL_ENTER();
     u32 m1, m2;
     load_counts(counts, m1_max, m2_max, m1, m2);
     const u64 total = (u64)m1 + m2;
@@ -102,6 +103,7 @@ join_match_kernel(const u64 *__restrict__ L, const u64 *__restrict__ R, const u6
                   u32 m2_max, const u32 *__restrict__ part, const u32 *__restrict__ runstart, uint2 *__restrict__ matches,
                   u32 *__restrict__ tile_count, u64 *count, uint2 *__restrict__ many_runs)
 {
+    PDL_ENTER();
     u32 m1, m2;
     load_counts(counts, m1_max, m2_max, m1, m2);
     const u32 num_tiles = (m1 == 0 || m2 == 0) ? 0u : (u32)(((u64)m1 + m2 + JN_TILE - 1) / JN_TILE);
@@ -265,6 +267,7 @@ join_scan_kernel(const u32 *__restrict__ tile_count, u32 num_tiles, u64 *offsets
 {
     __shared__ u32 s_stage[SCAN1_STAGE];
     __shared__ u64 s_w[JS_THREADS / 32];
+    PDL_ENTER();
     const u64 t = scan1_counts(tile_count, num_tiles, offsets, s_stage, s_w);
     if (threadIdx.x == 0) *total = t;
 }
@@ -274,6 +277,7 @@ __global__ void __launch_bounds__(256)
 join_compact_kernel(const uint2 *__restrict__ slots, const u32 *__restrict__ tile_count, const u64 *__restrict__ tile_off, u32 num_tiles,
                     uint2 *__restrict__ dense)
 {
+    PDL_ENTER();
     const u32 lane = threadIdx.x & 31u;
     const u32 warps = gridDim.x * (blockDim.x >> 5);
     for (u32 t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < num_tiles; t += warps) {   // one warp per tile
@@ -308,6 +312,7 @@ join_materialize_kernel(const uint2 *__restrict__ matches, const u64 *__restrict
                         int32_t *__restrict__ out_direct, int32_t *const *__restrict__ out_indirect, int rows_per_block)
 {
     __shared__ __align__(16) int32_t s_out[MT_SMEM_CELLS];
+    PDL_ENTER();
     int32_t *__restrict__ out = out_indirect ? *out_indirect : out_direct;
     int64_t nj = nj_max;
     if (nj_dev) { const u64 v = *nj_dev; nj = v < (u64)nj_max ? (int64_t)v : nj_max; }
@@ -503,24 +508,24 @@ int smj_launch_join_match(SmjCtx *c, const u64 *d_l, const u64 *d_r, const u64 *
     if (m1_max == 0 || m2_max == 0) return SMJ_OK;   // caller zeroed *d_count
     const u32 tiles = (u32)smj_join_num_tiles((u64)m1_max + m2_max);   // upper bound; the kernels use the device counts
     u32 *d_runstart = d_part + (tiles + 1);
-    join_partition_kernel<<<(tiles + 1 + 7) / 8, 256, 0, c->stream>>>(d_l, d_r, d_counts, m1_max, m2_max, d_part, d_runstart);
+    smj_launch(c, join_partition_kernel, (tiles + 1 + 7) / 8, 256, 0, d_l, d_r, d_counts, m1_max, m2_max, d_part, d_runstart);
     KERNEL_CHECK(c);
     const int sms = sm_count(c);
     const u32 grid = tiles < (u32)(sms * SMJ_JN_GRID) ? tiles : (u32)(sms * SMJ_JN_GRID);   // ~60 registers x 256 threads: 4 CTAs per SM
     if (mode == SMJ_JOIN_ZIP) {
-        join_match_kernel<SMJ_JOIN_ZIP><<<grid, JN_THREADS, 0, c->stream>>>(d_l, d_r, d_counts, m1_max, m2_max, d_part, d_runstart,
-                                                                           d_matches, d_tile_count, d_count, nullptr);
+        smj_launch(c, join_match_kernel<SMJ_JOIN_ZIP>, grid, JN_THREADS, 0, d_l, d_r, d_counts, m1_max, m2_max, d_part, d_runstart,
+                   d_matches, d_tile_count, d_count, (uint2 *)nullptr);
         KERNEL_CHECK(c);
-        join_scan_kernel<<<1, JS_THREADS, 0, c->stream>>>(d_tile_count, tiles, d_tile_off, d_count);
+        smj_launch(c, join_scan_kernel, 1, JS_THREADS, 0, d_tile_count, tiles, d_tile_off, d_count);
         if (d_dense) {
             KERNEL_CHECK(c);
             const u32 cgrid = (tiles + 7) / 8 < (u32)(sms * 8) ? (tiles + 7) / 8 : (u32)(sms * 8);
-            join_compact_kernel<<<cgrid, 256, 0, c->stream>>>(d_matches, d_tile_count, d_tile_off, tiles, d_dense);
+            smj_launch(c, join_compact_kernel, cgrid, 256, 0, d_matches, d_tile_count, d_tile_off, tiles, d_dense);
         }
     } else {
         // many-to-many: d_matches (if given) receives one (first right position, run length) entry per LEFT element
-        join_match_kernel<SMJ_JOIN_MANY><<<grid, JN_THREADS, 0, c->stream>>>(d_l, d_r, d_counts, m1_max, m2_max, d_part, d_runstart,
-                                                                            nullptr, d_tile_count, d_count, d_matches);
+        smj_launch(c, join_match_kernel<SMJ_JOIN_MANY>, grid, JN_THREADS, 0, d_l, d_r, d_counts, m1_max, m2_max, d_part, d_runstart,
+                   (uint2 *)nullptr, d_tile_count, d_count, d_matches);
     }
     KERNEL_CHECK(c);
     return SMJ_OK;
@@ -540,9 +545,9 @@ int smj_launch_join_materialize(SmjCtx *c, const uint2 *d_dense, const u64 *d_nj
     const u32 grid = (u32)(nblocks < (int64_t)sms * SMJ_MT_GRID ? nblocks : (int64_t)sms * SMJ_MT_GRID);
     const bool vec = (c1 % 4 == 0) && (c2 % 4 == 0) && ((((uintptr_t)d_t1) | ((uintptr_t)d_t2)) & 15) == 0;
     if (vec)
-        join_materialize_kernel<true><<<grid, MT_THREADS, 0, c->stream>>>(d_dense, d_nj, nj_max, d_t1, c1, d_t2, c2, key2, d_out, d_out_indirect, rpb);
+        smj_launch(c, join_materialize_kernel<true>, grid, MT_THREADS, 0, d_dense, d_nj, nj_max, d_t1, c1, d_t2, c2, key2, d_out, d_out_indirect, rpb);
     else
-        join_materialize_kernel<false><<<grid, MT_THREADS, 0, c->stream>>>(d_dense, d_nj, nj_max, d_t1, c1, d_t2, c2, key2, d_out, d_out_indirect, rpb);
+        smj_launch(c, join_materialize_kernel<false>, grid, MT_THREADS, 0, d_dense, d_nj, nj_max, d_t1, c1, d_t2, c2, key2, d_out, d_out_indirect, rpb);
     KERNEL_CHECK(c);
     return SMJ_OK;
 }

@@ -112,6 +112,7 @@ radix_pass_kernel(const RadixLaunch L, int pass, u32 *tile_counter, u32 *err)
     __shared__ u64 *s_out[2];
     __shared__ u32 s_kmin[2];
 
+    PDL_ENTER();
     const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
     const u32 lt = lanemask_lt();
     const u32 sel = 0x4440u | (u32)pass;
@@ -307,8 +308,9 @@ struct RadixScanArgs { const u32 *hist[2]; u32 *bases[2]; };
 __global__ void __launch_bounds__(SMJ_KEY_PASSES * SMJ_RADIX) radix_scan_kernel(const RadixScanArgs A)
 {
     __shared__ u32 s_w[SMJ_KEY_PASSES * SMJ_RADIX / 32];
-    const u32 *__restrict__ hist = A.hist[blockIdx.x];
-    u32 *bases = A.bases[blockIdx.x];
+    PDL_ENTER();
+    const u32 *__restrict__ hist = blockIdx.x ? A.hist[1] : A.hist[0];
+    u32 *bases = blockIdx.x ? A.bases[1] : A.bases[0];
     const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
     const u32 v = hist[tid];
     const u32 inc = warp_incl_scan(v);
@@ -361,7 +363,7 @@ static int launch_radix_pass(SmjCtx *c, const RadixLaunch &L, int pass, u32 *d_t
     for (int i = 0; i < L.nprob; i++) tiles += smj_radix_num_tiles(L.p[i].n_max);
     if (tiles == 0) return SMJ_OK;
     const u32 grid = tiles < (size_t)(sms * 2) ? (u32)tiles : (u32)(sms * 2);
-    radix_pass_kernel<<<grid, RS_THREADS, RS_SMEM, c->stream>>>(L, pass, d_tile_counter, c->d_err);
+    smj_launch(c, radix_pass_kernel, grid, RS_THREADS, RS_SMEM, L, pass, d_tile_counter, c->d_err);
     KERNEL_CHECK(c);
     return SMJ_OK;
 }
@@ -400,10 +402,10 @@ int smj_radix_sort_pairs_n(SmjCtx *c, int nprob, u64 *const *buf_a, u64 *const *
         idx[live++] = i;
     }
     if (live == 0) return SMJ_OK;
-    radix_scan_kernel<<<live, SMJ_KEY_PASSES * SMJ_RADIX, 0, c->stream>>>(SA);   // one CTA per problem
+    smj_launch(c, radix_scan_kernel, live, SMJ_KEY_PASSES * SMJ_RADIX, 0, SA);   // one CTA per problem
     KERNEL_CHECK(c);
     // one event pair around the four back-to-back passes (per-pass event records cost more stream time than they measure)
-    const bool timed = c->pass_count < SmjCtx::kMaxTimedPasses;
+    const bool timed = smj_stage_events() && c->pass_count < SmjCtx::kMaxTimedPasses;
     if (timed) CUDA_TRY(smj_event_record(c->pass_ev[2 * c->pass_count], c->stream));
     for (int p = 0; p < SMJ_KEY_PASSES; p++) {
         RadixLaunch L = {};

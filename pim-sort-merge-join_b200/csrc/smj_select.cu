@@ -140,6 +140,7 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
                   SmjSortPlan *plan)
 {
     constexpr bool HIST = MODE == 1;
+    PDL_ENTER();
     extern __shared__ __align__(128) unsigned char sel_smem[];      // stage ring
     __shared__ __align__(8) u64 s_full[SEL_STAGES], s_empty[SEL_STAGES];
     __shared__ u32 s_cnt[2][SEL_IPT * SEL_WARPS];
@@ -274,6 +275,7 @@ __global__ void __launch_bounds__(TS_THREADS) tile_scan_kernel(const u32 *__rest
 {
     __shared__ u32 s_stage[SCAN1_STAGE];
     __shared__ u64 s_w[TS_THREADS / 32];
+    PDL_ENTER();
     const u64 t = scan1_counts(counts, num_tiles, offsets, s_stage, s_w);
     if (threadIdx.x == 0) *total = t;
 }
@@ -285,6 +287,7 @@ __global__ void __launch_bounds__(256)
 select_compact_kernel(const u64 *__restrict__ slots, const u32 *__restrict__ counts, const u64 *__restrict__ offsets, u32 num_tiles,
                       u32 tile_rows, u64 *__restrict__ pairs)
 {
+    PDL_ENTER();
     const u32 lane = threadIdx.x & 31u;
     const u32 warps = gridDim.x * (blockDim.x >> 5);
     for (u32 t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < num_tiles; t += warps) {
@@ -307,6 +310,7 @@ __global__ void __launch_bounds__(TS_THREADS) plan_scan_kernel(const PlanScanArg
 {
     __shared__ u32 s_stage[SCAN1_STAGE];
     __shared__ u64 s_w[TS_THREADS / 32];
+    PDL_ENTER();
     const PlanScanJob J = blockIdx.x ? A.t[1] : A.t[0];   // (a dynamic index would copy the parameters to local memory)
     const u64 total = scan1_counts(J.counts, J.num_tiles, J.offsets, s_stage, s_w);
     if (threadIdx.x == 0) {
@@ -332,6 +336,7 @@ constexpr int PC_UNROLL = 8;
 __global__ void __launch_bounds__(256) plan_compact_kernel(const PlanCompactArgs A)
 {
     __shared__ u32 s_hist[2][SMJ_KEY_PASSES * SMJ_RADIX];
+    PDL_ENTER();
     const u32 tid = threadIdx.x, lane = tid & 31u;
     for (u32 i = tid; i < 2 * SMJ_KEY_PASSES * SMJ_RADIX; i += 256) (&s_hist[0][0])[i] = 0;
     __syncthreads();
@@ -484,19 +489,19 @@ int smj_launch_select_plan2(SmjCtx *c, const SmjSelectJob job[2])
         u32 *d_counts = reinterpret_cast<u32 *>(J.d_status + tiles);   // [tiles]
         if (tiles) {
             const u32 grid = tiles < (u32)(sms * SMJ_SEL_CTAS) ? tiles : (u32)(sms * SMJ_SEL_CTAS);
-            select_tma_kernel<2><<<grid, SELW_THREADS, SELW_SMEM, c->stream>>>(J.d_in, J.n, J.cols, ipt, J.sel_col, (int32_t)sel_val, select_all,
-                                                                              J.key_col, 0u, J.slots, d_counts, nullptr, tiles, J.plan);
+            smj_launch(c, select_tma_kernel<2>, grid, SELW_THREADS, SELW_SMEM, J.d_in, J.n, J.cols, ipt, J.sel_col, (int32_t)sel_val, select_all,
+                       J.key_col, 0u, J.slots, d_counts, (u32 *)nullptr, tiles, J.plan);
             KERNEL_CHECK(c);
         }
         SA.t[t] = {d_counts, tiles, d_offsets, J.d_count, J.plan};
         CA.t[t] = {J.slots, d_counts, d_offsets, tiles, (u32)tile_rows, {J.buf[0], J.buf[1]}, J.plan, J.d_hist};
         all_tiles += tiles;
     }
-    plan_scan_kernel<<<2, TS_THREADS, 0, c->stream>>>(SA);
+    smj_launch(c, plan_scan_kernel, 2, TS_THREADS, 0, SA);
     KERNEL_CHECK(c);
     if (all_tiles) {
         const u32 cgrid = (all_tiles + 7) / 8 < (u32)(sms * 8) ? (all_tiles + 7) / 8 : (u32)(sms * 8);
-        plan_compact_kernel<<<cgrid, 256, 0, c->stream>>>(CA);
+        smj_launch(c, plan_compact_kernel, cgrid, 256, 0, CA);
         KERNEL_CHECK(c);
     }
     return SMJ_OK;
