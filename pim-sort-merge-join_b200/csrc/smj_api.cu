@@ -383,6 +383,8 @@ struct ScratchHeader {
     u64 pad0;
     u32 counter[16];     // 0,1: select tickets; 2: join ticket
     SmjSortPlan plan[2]; // smj_run: key range of each table's survivors -> radix passes to run
+    u64 sel_count[2];    // smj_run: rows that passed the predicate (count[] = those that also passed the semi-join filter)
+    u64 kept_count[2];   // smj_run: rows of the table selected second that passed the in-select bitmap probe
 };
 
 // (key,rowid) pairs of every row of a device table (no predicate): used by sort / merge / join entry points.
@@ -751,6 +753,8 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
     const size_t mm_bytes = jt * smj_join_tile_size() * 8 > (size_t)(n[0] + n[1]) * 8 ? jt * smj_join_tile_size() * 8 : (size_t)(n[0] + n[1]) * 8;
     WS_TRY(mm, uint2 *, c, WS_MATCH, mm_bytes);
     WS_TRY(md, uint2 *, c, WS_MATCH_DENSE, (size_t)j_max * 8);
+    WS_TRY(bloom_ws, char *, c, WS_BLOOM, smj_bloom_bytes(n[0], n[1]));   // sized here: no allocation inside a graph capture
+    (void)bloom_ws;
     smj_table_t dev_out = {nullptr, 0, c_out, 1};
     SMJ_TRY(smj_alloc_out(c, &dev_out, j_max, c_out));   // upper bound; rows is set once the count is known
     CUDA_TRY(cudaEventRecord(c->ev[E_H2D], c->stream));
@@ -789,7 +793,7 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
                 SmjSelectJob job[2];
                 for (int t = 0; t < 2; t++)
                     job[t] = {d_t[t], n[t], cc[t], sel_col[t], sel_val[t], 0, key[t], {ping[t], pong[t]}, (u64 *)mm + (t ? n[0] : 0),
-                              (u64 *)(scr + off_sel + (t ? stiles[0] * 8 : 0)), h->hist[t], &h->count[t], &h->plan[t]};
+                              (u64 *)(scr + off_sel + (t ? stiles[0] * 8 : 0)), h->hist[t], &h->count[t], &h->plan[t], &h->sel_count[t], &h->kept_count[t]};
                 rc = smj_launch_select_plan2(c, job);
                 if (rc == 1) { planned = false; rc = SMJ_OK; }   // a table the TMA path cannot take: histograms in the select kernel, four passes
             }
@@ -852,7 +856,9 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
         int r = smj_check_device_flag(c);
         if (r != SMJ_OK) { smj_table_free(&dev_out); return r; }
     }
+    // m: pairs that were sorted and joined; m_sel: rows that passed the predicate (more, when the semi-join filter ran)
     const int64_t m[2] = {(int64_t)hh->count[0], (int64_t)hh->count[1]};
+    const int64_t m_sel[2] = {c->run_planned ? (int64_t)hh->sel_count[0] : m[0], c->run_planned ? (int64_t)hh->sel_count[1] : m[1]};
     const int64_t j = (int64_t)hh->jcount;
     dev_out.rows = j;
     if (j == 0) smj_table_free(&dev_out), dev_out.data = nullptr;
@@ -869,7 +875,7 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (cfg->debug) {   // app.c:294-305, 379-400, 694-717 print one line per DPU and stage; one GPU here
         printf("==================\n#    select.cu   #\n==================\n");
-        for (int t = 0; t < 2; t++) printf("Table %d : select %lld rows\n", t, (long long)m[t]);
+        for (int t = 0; t < 2; t++) printf("Table %d : select %lld rows\n", t, (long long)m_sel[t]);
         printf("####################\n\n==================\n#     sort.cu    #\n==================\n");
         for (int t = 0; t < 2; t++) printf("Table %d - GPU %d sort %lld rows\n", t, c->device, (long long)m[t]);
         printf("####################\n\n==================\n#     join.cu    #\n==================\n");
@@ -888,9 +894,9 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
         }
         stats->d2h_ms = ev_ms(c->ev[E_JOIN], c->ev[E_D2H]);
         stats->total_device_ms = ev_ms(c->ev[E_H2D], c->ev[E_JOIN]);
-        for (int t = 0; t < 2; t++) { stats->rows_in[t] = n[t]; stats->rows_selected[t] = m[t]; }
+        for (int t = 0; t < 2; t++) { stats->rows_in[t] = n[t]; stats->rows_selected[t] = m_sel[t]; }
         stats->rows_joined = j;
-        stats->bytes_model = bytes_model(n, cc, m, j);
+        stats->bytes_model = bytes_model(n, cc, m_sel, j);
         stats->kernel_launches = c->launches - launches0;
         double sum = 0;
         if (!smj_stage_events()) c->pass_count = 0;
@@ -903,7 +909,8 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
         stats->sort_passes = c->pass_count * (int)np_max;
         stats->sort_pass_ms_avg = stats->sort_passes ? sum / stats->sort_passes : 0;
         stats->sort_pass_bytes_avg = np_max ? 16.0 * ((double)m[0] * np[0] + (double)m[1] * np[1]) / np_max : 0;
-        stats->bytes_model -= 16.0 * ((double)m[0] * (SMJ_KEY_PASSES - np[0]) + (double)m[1] * (SMJ_KEY_PASSES - np[1]));
+        // the model's sort term (16 B x 4 passes x selected rows) restated for the passes and pairs this run's plan sorted
+        stats->bytes_model += 16.0 * ((double)m[0] * np[0] + (double)m[1] * np[1]) - 16.0 * SMJ_KEY_PASSES * ((double)m_sel[0] + (double)m_sel[1]);
     }
     return SMJ_OK;
 }

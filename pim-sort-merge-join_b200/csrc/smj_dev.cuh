@@ -192,6 +192,10 @@ __device__ __forceinline__ u64 scan1_counts(const u32 *__restrict__ counts, u32 
     return total;
 }
 
+// ---- semi-join key bitmaps (smj_select.cu): bit bloom_hash(key) of a table's bitmap is set iff some surviving row of
+// that table hashes there.  One multiplicative hash, 2^(32 - shift) bits.
+__device__ __forceinline__ u32 bloom_hash(u32 flipped_key, u32 shift) { return (flipped_key * 0x9E3779B1u) >> shift; }
+
 // ---- programmatic dependent launch (sm_90+): every kernel of the smj_run pipeline starts with PDL_ENTER().  When the
 // launch carries cudaLaunchAttributeProgrammaticStreamSerialization, `wait` blocks until the preceding kernel has
 // completed and its writes are visible, and `launch_dependents` lets the NEXT kernel's CTAs become resident (and park

@@ -56,7 +56,7 @@ enum SmjSlot {
     WS_MATCH,                        // matched (left rowid, right rowid)
     WS_TMP_ROWS, WS_TMP_ROWS2,       // staging for in-place sort / host outputs
     WS_XCHG_SEND1, WS_XCHG_SEND2, WS_XCHG_RECV1, WS_XCHG_RECV2, WS_SAMPLES,
-    WS_MERGE_A, WS_MERGE_B, WS_RADIX, WS_MATCH_DENSE,
+    WS_MERGE_A, WS_MERGE_B, WS_RADIX, WS_MATCH_DENSE, WS_BLOOM,
 };
 
 int   smj_set_error(int code, const char *fmt, ...);
@@ -115,6 +115,19 @@ int smj_launch_select_pairs(SmjCtx *c, const int32_t *d_in, int64_t n, int cols,
 // npass = ceil(bits(kmax - kmin) / 8).  The radix passes sort digits of (key - kmin) and passes >= npass exit at once.
 struct SmjSortPlan { u32 kmin, npass, kmin_inv, kmax; };
 
+// Semi-join reduction between select and sort (smj_run, zip mode): a row whose key no surviving row of the OTHER table
+// carries can never be joined, and dropping it changes neither the matches nor their order, so it need not be sorted.
+// Each table's select kernel sets one bit per surviving key in its own bitmap; the table that is selected second probes
+// the first one's bitmap inside its select kernel, the first one is filtered by a pass over its pair slots.  A hash
+// collision only keeps a row that the join then rejects.
+struct SmjBloom {
+    u32 *set = nullptr;           // bitmap this launch inserts into (or null)
+    const u32 *probe = nullptr;   // bitmap of the other table to probe (or null)
+    u32 shift = 0;                // 32 - log2(bits)
+    u64 *sel_count = nullptr;     // += rows that passed the predicate (before the probe)
+    u64 *kept_count = nullptr;    // += rows that also passed the probe (probing launches only)
+};
+
 // smj_run's select stage over both tables (smj_select.cu): see smj_launch_select_plan2.
 struct SmjSelectJob {
     const int32_t *d_in; int64_t n; int cols, sel_col; int64_t sel_val; int select_all, key_col;
@@ -122,11 +135,14 @@ struct SmjSelectJob {
     u64 *slots;           // n pairs of scratch: the select kernel's per-tile slots
     u64 *d_status;        // [smj_select_num_tiles(n)] zeroed words: tile offsets + tile counts
     u32 *d_hist;          // [4 * 256] zero: digit histogram of key - kmin, passes < npass
-    u64 *d_count;         // out: survivors
+    u64 *d_count;         // out: pairs that go on to the sort (survivors that passed the semi-join filter)
     SmjSortPlan *plan;    // zeroed
+    u64 *d_sel_count;     // zeroed; out: rows that passed the predicate (smj_stats_t.rows_selected)
+    u64 *d_kept_count;    // zeroed; out: of those, the rows whose key bit was set in the other table's bitmap
 };
 // returns 1 (nothing launched) when a table cannot take the TMA path
 int smj_launch_select_plan2(SmjCtx *c, const SmjSelectJob job[2]);
+size_t smj_bloom_bytes(int64_t n0, int64_t n1);   // WS_BLOOM bytes the call above uses (0: no semi-join filter)
 
 // ------------------------------------------------------------------ radix sort (smj_radix.cu)
 size_t smj_radix_num_tiles(u32 n);

@@ -133,11 +133,11 @@ constexpr size_t SELW_SMEM = (size_t)SEL_STAGES * SEL_STAGE_BYTES;
 // MODE 0: pairs only; 1: + 4 x 256 digit histogram of the surviving keys; 2: + min / max of the surviving keys into
 // *plan (the sort then runs only the passes the key RANGE needs, smj_radix.cu; the histogram of (key - min) digits is
 // built by the compaction copy, once the minimum is known).
-template <int MODE>
-__global__ void __launch_bounds__(SELW_THREADS)
+template <int MODE, bool PROBE = false>
+__global__ void __launch_bounds__(SELW_THREADS, PROBE ? 2 : 3)   // shared memory allows 3 CTAs per SM; the launch uses SMJ_SEL_CTAS
 select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, int sel_col, int32_t sel_val, int select_all,
                   int key_col, u32 rowid_base, u64 *__restrict__ slots, u32 *__restrict__ tile_count, u32 *hist, u32 num_tiles,
-                  SmjSortPlan *plan)
+                  SmjSortPlan *plan, SmjBloom bloom)
 {
     constexpr bool HIST = MODE == 1;
     PDL_ENTER();
@@ -185,18 +185,20 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
 
     // ---------------------------------------------------- compute warps
     const u32 lt = lanemask_lt();
-    u32 stage = 0, parity = 0, it = 0;
     u32 tmin = 0xffffffffu, tmax = 0u;   // MODE 2: this thread's surviving flipped keys
-    for (u32 tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
-        mbar_wait(&s_full[stage], parity);
+    u32 nsel = 0;                        // MODE 2: rows of this thread that passed the predicate (before the semi-join probe)
+    u32 nkept = 0;                       // PROBE: pairs written (thread SEL_THREADS - 1 sums the tile totals)
+
+    // what a thread keeps of a tile once the ring stage has been released
+    struct TileRegs { int32_t key[SEL_IPT]; u32 probe[PROBE ? SEL_IPT : 1]; u32 passmask; u32 tile; };
+
+    // predicate on the tile in ring stage `stage`; with PROBE also issues the loads of the other table's bitmap words
+    auto load_tile = [&](u32 tile, u32 stage, TileRegs &T) {
         const int64_t tile_base = (int64_t)tile * tile_rows;
         const u32 rows_valid = (u32)((n - tile_base < (int64_t)tile_rows) ? (n - tile_base) : (int64_t)tile_rows);
         const int32_t *s_rows = reinterpret_cast<const int32_t *>(sel_smem + (size_t)stage * SEL_STAGE_BYTES);
-        u32 *cntbuf = s_cnt[it & 1u];
-
-        int32_t key[SEL_IPT];
-        u32 rank[SEL_IPT];
-        u32 passmask = 0;
+        T.tile = tile;
+        T.passmask = 0;
 #pragma unroll
         for (int j = 0; j < SEL_IPT; j++) {
             if (j < ipt) {
@@ -208,24 +210,43 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
                     kv = (key_col == sel_col) ? sv : s_rows[row * cols + key_col];
                 }
                 const bool pass = valid && (select_all || sv > sel_val);
-                key[j] = kv;
-                const u32 b = __ballot_sync(FULL_MASK, pass);
-                if (lane == 0) cntbuf[j * SEL_WARPS + w] = __popc(b);
-                rank[j] = __popc(b & lt);
-                passmask |= (pass ? 1u : 0u) << j;
-            } else if (lane == 0) {
-                cntbuf[j * SEL_WARPS + w] = 0;
+                T.key[j] = kv;
+                T.passmask |= (pass ? 1u : 0u) << j;
+                if (PROBE) T.probe[j] = pass ? __ldg(bloom.probe + (bloom_hash((u32)kv ^ 0x80000000u, bloom.shift) >> 5)) : 0u;
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[stage]);   // this warp holds its cells in registers: stage can be refilled
+        if (MODE == 2) nsel += __popc(T.passmask);
+    };
+
+    // ranks, the tile's count, the survivors written compacted into the tile's slot (`it` = tiles finished so far)
+    auto finish_tile = [&](const TileRegs &T, u32 it) {
+        const int64_t tile_base = (int64_t)T.tile * tile_rows;
+        u32 *cntbuf = s_cnt[it & 1u];
+        u32 rank[SEL_IPT];
+        u32 passmask = T.passmask;
+#pragma unroll
+        for (int j = 0; j < SEL_IPT; j++) {
+            if (j < ipt) {
+                if (PROBE) {   // no row of the other table hashes to this key's bit: the row cannot be joined
+                    const u32 h = bloom_hash((u32)T.key[j] ^ 0x80000000u, bloom.shift);
+                    if (!((T.probe[j] >> (h & 31u)) & 1u)) passmask &= ~(1u << j);
+                }
+                const u32 b = __ballot_sync(FULL_MASK, (passmask >> j) & 1u);
+                if (lane == 0) cntbuf[j * SEL_WARPS + w] = __popc(b);
+                rank[j] = __popc(b & lt);
+            } else if (lane == 0) {
+                cntbuf[j * SEL_WARPS + w] = 0;
+            }
+        }
         named_bar_sync(1, SEL_THREADS);                // counts complete (double-buffered: one barrier per tile)
 
         // every warp scans the 64 (row group, warp) counts itself: no second barrier, no broadcast
         const u32 v0 = cntbuf[2 * lane], v1 = cntbuf[2 * lane + 1];
         const u32 inc = warp_incl_scan(v0 + v1);
         const u32 ex0 = inc - (v0 + v1);               // exclusive prefix of entry 2*lane; entry 2*lane+1 adds v0
-        if (tid == SEL_THREADS - 1) tile_count[tile] = inc;   // lane 31: the tile total
+        if (tid == SEL_THREADS - 1) { tile_count[T.tile] = inc; nkept += inc; }   // lane 31: the tile total
         u64 *dst = slots + (size_t)tile_base;
 #pragma unroll
         for (int j = 0; j < SEL_IPT; j++) {
@@ -234,7 +255,7 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
             const u32 add = __shfl_sync(FULL_MASK, v0, e >> 1);
             if (e & 1u) off += add;
             if ((passmask >> j) & 1u) {
-                const u64 p = make_pair(key[j], rowid_base + (u32)(tile_base + j * SEL_THREADS + tid));
+                const u64 p = make_pair(T.key[j], rowid_base + (u32)(tile_base + j * SEL_THREADS + tid));
                 dst[off + rank[j]] = p;
                 if (HIST) {
                     const u32 k = pair_key(p);
@@ -246,10 +267,35 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
                     const u32 k = pair_key(p);
                     tmin = k < tmin ? k : tmin;
                     tmax = k > tmax ? k : tmax;
+                    if (bloom.set) {
+                        const u32 h = bloom_hash(k, bloom.shift);
+                        atomicOr(bloom.set + (h >> 5), 1u << (h & 31u));
+                    }
                 }
             }
         }
-        if (++stage == SEL_STAGES) { stage = 0; parity ^= 1u; }
+    };
+
+    {
+        u32 stage = 0, parity = 0, it = 0;
+        TileRegs prev;
+        bool have_prev = false;
+        for (u32 tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(&s_full[stage], parity);
+            TileRegs cur;
+            load_tile(tile, stage, cur);
+            if (PROBE) {
+                // software pipeline: tile i's bitmap words travel while tile i-1 is ranked and written and tile i+1 is
+                // waited for, so the probe's L2 round trip is off the per-tile critical path
+                if (have_prev) finish_tile(prev, it++);
+                prev = cur;
+                have_prev = true;
+            } else {
+                finish_tile(cur, it++);
+            }
+            if (++stage == SEL_STAGES) { stage = 0; parity ^= 1u; }
+        }
+        if (PROBE && have_prev) finish_tile(prev, it++);
     }
     if (HIST) {
         named_bar_sync(1, SEL_THREADS);
@@ -265,6 +311,9 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
             atomicMax(&plan->kmin_inv, ~wmin);
             atomicMax(&plan->kmax, wmax);
         }
+        const u32 wsel = __reduce_add_sync(FULL_MASK, nsel);
+        if (lane == 0 && wsel) atomicAdd(bloom.sel_count, (u64)wsel);
+        if (PROBE && tid == SEL_THREADS - 1 && nkept) atomicAdd(bloom.kept_count, (u64)nkept);
     }
 }
 
@@ -382,6 +431,53 @@ __global__ void __launch_bounds__(256) plan_compact_kernel(const PlanCompactArgs
     }
 }
 
+// Semi-join filter of the table that was selected FIRST (its partner's bitmap did not exist yet): one warp per tile
+// compacts the tile's pair slot in place, keeping the pairs whose key bit is set in the other table's bitmap.  A chunk
+// of 8 x 32 pairs and its 8 bitmap words are in registers before the first store, and the write cursor never passes
+// the chunk's first element, so no pair is overwritten before it has been read.
+// The pass is skipped when more than 3/4 of the OTHER table's selected rows found their key in this table's bitmap:
+// the two key sets then largely coincide and the filter would keep almost everything.
+struct BloomFilterArgs { u64 *slots; u32 *counts; u32 num_tiles, tile_rows; const u32 *probe; u32 shift; const u64 *other_sel, *other_kept; };
+
+__global__ void __launch_bounds__(256) bloom_filter_kernel(const BloomFilterArgs A)
+{
+    PDL_ENTER();
+    if (*A.other_kept * 4 > *A.other_sel * 3) return;
+    const u32 lane = threadIdx.x & 31u;
+    const u32 lt = lanemask_lt();
+    const u32 warps = gridDim.x * 8u;
+    for (u32 t = blockIdx.x * 8u + (threadIdx.x >> 5); t < A.num_tiles; t += warps) {
+        const u32 cnt = A.counts[t];
+        u64 *slot = A.slots + (size_t)t * A.tile_rows;
+        u32 wpos = 0;
+        for (u32 i0 = 0; i0 < cnt; i0 += 32 * PC_UNROLL) {
+            u64 v[PC_UNROLL];
+            u32 word[PC_UNROLL];
+#pragma unroll
+            for (int k = 0; k < PC_UNROLL; k++) {
+                const u32 i = i0 + k * 32 + lane;
+                v[k] = i < cnt ? slot[i] : 0ull;
+            }
+#pragma unroll
+            for (int k = 0; k < PC_UNROLL; k++) {
+                const u32 i = i0 + k * 32 + lane;
+                word[k] = i < cnt ? __ldg(A.probe + (bloom_hash(pair_key(v[k]), A.shift) >> 5)) : 0u;
+            }
+            __syncwarp();   // every lane holds its part of the chunk before any lane stores
+#pragma unroll
+            for (int k = 0; k < PC_UNROLL; k++) {
+                const u32 i = i0 + k * 32 + lane;
+                const bool keep = i < cnt && ((word[k] >> (bloom_hash(pair_key(v[k]), A.shift) & 31u)) & 1u);
+                const u32 b = __ballot_sync(FULL_MASK, keep);
+                if (keep) slot[wpos + __popc(b & lt)] = v[k];
+                wpos += __popc(b);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) A.counts[t] = wpos;
+    }
+}
+
 }  // namespace
 
 // rows per thread per tile for the TMA path: the largest power-of-two count (<= 8) whose tile fits one stage
@@ -401,6 +497,7 @@ static int select_set_attrs(SmjCtx *c)   // function attributes are per device
     CUDA_TRY(cudaFuncSetAttribute(select_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SELW_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(select_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SELW_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(select_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SELW_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(select_tma_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SELW_SMEM));
     c->select_attr_set = true;
     return SMJ_OK;
 }
@@ -433,10 +530,10 @@ int smj_launch_select_pairs(SmjCtx *c, const int32_t *d_in, int64_t n, int cols,
         const u32 grid = tiles < (u32)(sms * SMJ_SEL_CTAS) ? tiles : (u32)(sms * SMJ_SEL_CTAS);
         if (d_hist)
             select_tma_kernel<1><<<grid, SELW_THREADS, smem, c->stream>>>(d_in, n, cols, ipt, sel_col, (int32_t)sel_val, select_all,
-                                                                         key_col, rowid_base, d_tmp, d_counts, d_hist, tiles, nullptr);
+                                                                         key_col, rowid_base, d_tmp, d_counts, d_hist, tiles, nullptr, SmjBloom());
         else
             select_tma_kernel<0><<<grid, SELW_THREADS, smem, c->stream>>>(d_in, n, cols, ipt, sel_col, (int32_t)sel_val, select_all,
-                                                                         key_col, rowid_base, d_tmp, d_counts, nullptr, tiles, nullptr);
+                                                                         key_col, rowid_base, d_tmp, d_counts, nullptr, tiles, nullptr, SmjBloom());
         KERNEL_CHECK(c);
         tile_scan_kernel<<<1, TS_THREADS, 0, c->stream>>>(d_counts, tiles, d_offsets, d_count);
         KERNEL_CHECK(c);
@@ -459,6 +556,21 @@ int smj_launch_select_pairs(SmjCtx *c, const int32_t *d_in, int64_t n, int cols,
     return SMJ_OK;
 }
 
+// log2 of the bits per semi-join bitmap, or 0 when the filter is not used for these table sizes
+static int bloom_log2_bits(int64_t n0, int64_t n1)
+{
+    const int64_t n_first = n0 <= n1 ? n0 : n1;
+    if (n0 <= 0 || n1 <= 0 || 4 * n_first > (1ll << 29)) return 0;
+    int lb = 16;
+    while (lb < 28 && (1ll << lb) < 4 * n_first) lb++;
+    return lb;
+}
+size_t smj_bloom_bytes(int64_t n0, int64_t n1)
+{
+    const int lb = bloom_log2_bits(n0, n1);
+    return lb ? 2 * ((size_t)1 << (lb - 3)) : 0;
+}
+
 // smj_run's select stage, both tables: select (key min / max instead of histograms) per table, ONE scan launch (tile
 // offsets, survivor counts, sort plans), ONE compaction launch (dense pairs into the buffer the plan names + digit
 // histograms of key - kmin).  Returns 1 without launching anything when a table cannot take the TMA path (the caller
@@ -468,14 +580,35 @@ int smj_launch_select_plan2(SmjCtx *c, const SmjSelectJob job[2])
     for (int t = 0; t < 2; t++)
         if (job[t].n > 0 && !select_use_tma(job[t].d_in, job[t].cols)) return 1;
     static const int full_passes = (getenv("SMJ_FULL_PASSES") && atoi(getenv("SMJ_FULL_PASSES")) != 0) ? 1 : 0;
+    static const bool semijoin_on = !(getenv("SMJ_SEMIJOIN") && atoi(getenv("SMJ_SEMIJOIN")) == 0);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     if (!c->select_attr_set) SMJ_TRY(select_set_attrs(c));
+
+    // Semi-join bitmaps: the smaller table goes first (it is the one that needs the extra filter pass), 4 bits per input
+    // row of it, at most 2^28 bits (32 MB) per table so that both bitmaps stay L2-resident while they are probed.
+    const int first = job[0].n <= job[1].n ? 0 : 1, second = first ^ 1;
+    const int lb = bloom_log2_bits(job[0].n, job[1].n);
+    const bool semijoin = semijoin_on && lb > 0;
+    u32 *bm[2] = {nullptr, nullptr};
+    if (semijoin) {
+        const size_t words = (size_t)1 << (lb - 5);
+        u32 *base = (u32 *)smj_ws(c, WS_BLOOM, 2 * words * 4);   // (already sized by the caller: smj_bloom_bytes)
+        if (!base) return SMJ_ENOMEM;
+        bm[0] = base; bm[1] = base + words;
+        CUDA_TRY(cudaMemsetAsync(base, 0, 2 * words * 4, c->stream));
+    }
+
     PlanScanArgs SA = {};
     PlanCompactArgs CA = {};
     SA.full_passes = full_passes;
     u32 all_tiles = 0;
-    for (int t = 0; t < 2; t++) {
+    u32 tiles_of[2] = {0, 0};
+    u32 *counts_of[2] = {nullptr, nullptr};
+    int64_t tile_rows_of[2] = {0, 0};
+    const int order[2] = {first, second};
+    for (int o = 0; o < 2; o++) {
+        const int t = order[o];
         const SmjSelectJob &J = job[t];
         int select_all = J.select_all;
         int64_t sel_val = J.sel_val;
@@ -488,14 +621,34 @@ int smj_launch_select_plan2(SmjCtx *c, const SmjSelectJob job[2])
         u64 *d_offsets = J.d_status;                                   // [tiles]
         u32 *d_counts = reinterpret_cast<u32 *>(J.d_status + tiles);   // [tiles]
         if (tiles) {
+            SmjBloom B;
+            B.sel_count = J.d_sel_count;
+            B.kept_count = J.d_kept_count;
+            if (semijoin) {
+                B.set = bm[t];
+                B.probe = (t == second) ? bm[first] : nullptr;
+                B.shift = 32u - (u32)lb;
+            }
             const u32 grid = tiles < (u32)(sms * SMJ_SEL_CTAS) ? tiles : (u32)(sms * SMJ_SEL_CTAS);
-            smj_launch(c, select_tma_kernel<2>, grid, SELW_THREADS, SELW_SMEM, J.d_in, J.n, J.cols, ipt, J.sel_col, (int32_t)sel_val, select_all,
-                       J.key_col, 0u, J.slots, d_counts, (u32 *)nullptr, tiles, J.plan);
+            if (B.probe)
+                smj_launch(c, select_tma_kernel<2, true>, grid, SELW_THREADS, SELW_SMEM, J.d_in, J.n, J.cols, ipt, J.sel_col, (int32_t)sel_val, select_all,
+                           J.key_col, 0u, J.slots, d_counts, (u32 *)nullptr, tiles, J.plan, B);
+            else
+                smj_launch(c, select_tma_kernel<2, false>, grid, SELW_THREADS, SELW_SMEM, J.d_in, J.n, J.cols, ipt, J.sel_col, (int32_t)sel_val, select_all,
+                           J.key_col, 0u, J.slots, d_counts, (u32 *)nullptr, tiles, J.plan, B);
             KERNEL_CHECK(c);
         }
+        tiles_of[t] = tiles; counts_of[t] = d_counts; tile_rows_of[t] = tile_rows;
         SA.t[t] = {d_counts, tiles, d_offsets, J.d_count, J.plan};
         CA.t[t] = {J.slots, d_counts, d_offsets, tiles, (u32)tile_rows, {J.buf[0], J.buf[1]}, J.plan, J.d_hist};
         all_tiles += tiles;
+    }
+    if (semijoin && tiles_of[first]) {
+        BloomFilterArgs FA = {job[first].slots, counts_of[first], tiles_of[first], (u32)tile_rows_of[first], bm[second], 32u - (u32)lb,
+                              job[second].d_sel_count, job[second].d_kept_count};
+        const u32 fgrid = (tiles_of[first] + 7) / 8 < (u32)(sms * 8) ? (tiles_of[first] + 7) / 8 : (u32)(sms * 8);
+        smj_launch(c, bloom_filter_kernel, fgrid, 256, 0, FA);
+        KERNEL_CHECK(c);
     }
     smj_launch(c, plan_scan_kernel, 2, TS_THREADS, 0, SA);
     KERNEL_CHECK(c);
