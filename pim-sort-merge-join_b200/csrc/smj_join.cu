@@ -263,11 +263,17 @@ join_match_kernel(const u64 *__restrict__ L, const u64 *__restrict__ R, const u6
 // Exclusive scan of per-tile counts (one CTA): offsets[t] = sum of counts[0..t), *total = sum of all.
 constexpr int JS_THREADS = SCAN1_THREADS;
 __global__ void __launch_bounds__(JS_THREADS)
-join_scan_kernel(const u32 *__restrict__ tile_count, u32 num_tiles, u64 *offsets, u64 *total)
+join_scan_kernel(const u32 *__restrict__ tile_count, u32 num_tiles, u64 *offsets, u64 *total, const u64 *__restrict__ counts,
+                 u32 m1_max, u32 m2_max)
 {
     __shared__ u32 s_stage[SCAN1_STAGE];
     __shared__ u64 s_w[JS_THREADS / 32];
     PDL_ENTER();
+    // the tiles the match kernel actually used (device-resident sizes), not the host's upper bound
+    u32 m1, m2;
+    load_counts(counts, m1_max, m2_max, m1, m2);
+    const u32 used = (m1 == 0 || m2 == 0) ? 0u : (u32)(((u64)m1 + m2 + JN_TILE - 1) / JN_TILE);
+    if (used < num_tiles) num_tiles = used;
     const u64 t = scan1_counts(tile_count, num_tiles, offsets, s_stage, s_w);
     if (threadIdx.x == 0) *total = t;
 }
@@ -275,9 +281,15 @@ join_scan_kernel(const u32 *__restrict__ tile_count, u32 num_tiles, u64 *offsets
 // dense[offsets[t] + i] = slots[t * JN_TILE + i], i < tile_count[t]: the matches in result order, contiguous.
 __global__ void __launch_bounds__(256)
 join_compact_kernel(const uint2 *__restrict__ slots, const u32 *__restrict__ tile_count, const u64 *__restrict__ tile_off, u32 num_tiles,
-                    uint2 *__restrict__ dense)
+                    uint2 *__restrict__ dense, const u64 *__restrict__ counts, u32 m1_max, u32 m2_max)
 {
     PDL_ENTER();
+    {
+        u32 m1, m2;
+        load_counts(counts, m1_max, m2_max, m1, m2);
+        const u32 used = (m1 == 0 || m2 == 0) ? 0u : (u32)(((u64)m1 + m2 + JN_TILE - 1) / JN_TILE);
+        if (used < num_tiles) num_tiles = used;
+    }
     const u32 lane = threadIdx.x & 31u;
     const u32 warps = gridDim.x * (blockDim.x >> 5);
     for (u32 t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < num_tiles; t += warps) {   // one warp per tile
@@ -516,11 +528,11 @@ int smj_launch_join_match(SmjCtx *c, const u64 *d_l, const u64 *d_r, const u64 *
         smj_launch(c, join_match_kernel<SMJ_JOIN_ZIP>, grid, JN_THREADS, 0, d_l, d_r, d_counts, m1_max, m2_max, d_part, d_runstart,
                    d_matches, d_tile_count, d_count, (uint2 *)nullptr);
         KERNEL_CHECK(c);
-        smj_launch(c, join_scan_kernel, 1, JS_THREADS, 0, d_tile_count, tiles, d_tile_off, d_count);
+        smj_launch(c, join_scan_kernel, 1, JS_THREADS, 0, d_tile_count, tiles, d_tile_off, d_count, d_counts, m1_max, m2_max);
         if (d_dense) {
             KERNEL_CHECK(c);
             const u32 cgrid = (tiles + 7) / 8 < (u32)(sms * 8) ? (tiles + 7) / 8 : (u32)(sms * 8);
-            smj_launch(c, join_compact_kernel, cgrid, 256, 0, d_matches, d_tile_count, d_tile_off, tiles, d_dense);
+            smj_launch(c, join_compact_kernel, cgrid, 256, 0, d_matches, d_tile_count, d_tile_off, tiles, d_dense, d_counts, m1_max, m2_max);
         }
     } else {
         // many-to-many: d_matches (if given) receives one (first right position, run length) entry per LEFT element

@@ -361,11 +361,12 @@ __global__ void __launch_bounds__(TS_THREADS) plan_scan_kernel(const PlanScanArg
     __shared__ u64 s_w[TS_THREADS / 32];
     PDL_ENTER();
     const PlanScanJob J = blockIdx.x ? A.t[1] : A.t[0];   // (a dynamic index would copy the parameters to local memory)
+    u32 kmin_inv = 0, kmax = 0;
+    if (threadIdx.x == 0) { kmin_inv = J.plan->kmin_inv; kmax = J.plan->kmax; }   // in flight during the scan
     const u64 total = scan1_counts(J.counts, J.num_tiles, J.offsets, s_stage, s_w);
     if (threadIdx.x == 0) {
         *J.total = total;
-        u32 kmin = ~J.plan->kmin_inv, npass = 0;
-        const u32 kmax = J.plan->kmax;
+        u32 kmin = ~kmin_inv, npass = 0;
         if (total >= 2 && kmax > kmin) npass = (32u - (u32)__clz(kmax - kmin) + 7u) / 8u;
         if (total == 0) kmin = 0;
         if (A.full_passes) { kmin = 0; npass = SMJ_KEY_PASSES; }
@@ -450,20 +451,25 @@ __global__ void __launch_bounds__(256) bloom_filter_kernel(const BloomFilterArgs
         const u32 cnt = A.counts[t];
         u64 *slot = A.slots + (size_t)t * A.tile_rows;
         u32 wpos = 0;
+        u64 v[PC_UNROLL], vn[PC_UNROLL];
+#pragma unroll
+        for (int k = 0; k < PC_UNROLL; k++) {
+            const u32 i = k * 32 + lane;
+            v[k] = i < cnt ? slot[i] : 0ull;
+        }
         for (u32 i0 = 0; i0 < cnt; i0 += 32 * PC_UNROLL) {
-            u64 v[PC_UNROLL];
             u32 word[PC_UNROLL];
 #pragma unroll
-            for (int k = 0; k < PC_UNROLL; k++) {
-                const u32 i = i0 + k * 32 + lane;
-                v[k] = i < cnt ? slot[i] : 0ull;
+            for (int k = 0; k < PC_UNROLL; k++) {   // the next chunk's pairs travel while this chunk is probed
+                const u32 i = i0 + 32 * PC_UNROLL + k * 32 + lane;
+                vn[k] = i < cnt ? slot[i] : 0ull;
             }
 #pragma unroll
             for (int k = 0; k < PC_UNROLL; k++) {
                 const u32 i = i0 + k * 32 + lane;
                 word[k] = i < cnt ? __ldg(A.probe + (bloom_hash(pair_key(v[k]), A.shift) >> 5)) : 0u;
             }
-            __syncwarp();   // every lane holds its part of the chunk before any lane stores
+            __syncwarp();   // every lane holds its part of this chunk and of the next one before any lane stores
 #pragma unroll
             for (int k = 0; k < PC_UNROLL; k++) {
                 const u32 i = i0 + k * 32 + lane;
@@ -473,6 +479,8 @@ __global__ void __launch_bounds__(256) bloom_filter_kernel(const BloomFilterArgs
                 wpos += __popc(b);
             }
             __syncwarp();
+#pragma unroll
+            for (int k = 0; k < PC_UNROLL; k++) v[k] = vn[k];
         }
         if (lane == 0) A.counts[t] = wpos;
     }
