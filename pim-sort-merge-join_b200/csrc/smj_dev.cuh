@@ -249,6 +249,39 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// ---- L2 residency hints.  The table scan is read exactly once: its bulk copies carry an evict_first policy so that the
+// 160 MB+ stream does not push the pair slots the same kernel writes, or the semi-join bitmaps it probes, out of the
+// 126 MB L2; bitmap words are read and set with evict_last.
+__device__ __forceinline__ u64 l2_policy_evict_first()
+{
+    u64 p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ u64 l2_policy_evict_last()
+{
+    u64 p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gmem, u32 bytes, u64 *bar, u64 policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ u32 ld_nc_hint(const u32 *p, u64 policy)
+{
+    u32 v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ void red_or_hint(u32 *p, u32 v, u64 policy)
+{
+    asm volatile("red.global.or.b32.L2::cache_hint [%0], %1, %2;" ::"l"(p), "r"(v), "l"(policy) : "memory");
+}
+
 // barrier among a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(u32 id, u32 nthreads)
 {

@@ -161,6 +161,7 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
         // ------------------------------------------------ producer (one lane); tiles are dealt round-robin
         if (lane != 0) return;
         const size_t row_bytes = (size_t)cols * 4;
+        const u64 stream_policy = l2_policy_evict_first();
         u32 stage = 0, parity = 0;
         for (u32 t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             mbar_wait(&s_empty[stage], parity ^ 1u);      // passes at once the first time round the ring
@@ -174,7 +175,7 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
                 *reinterpret_cast<int32_t *>(dst + b) = *reinterpret_cast<const int32_t *>(src + b);
             if (b16) {
                 mbar_expect_tx(&s_full[stage], b16);
-                bulk_g2s(dst, src, b16, &s_full[stage]);
+                bulk_g2s_hint(dst, src, b16, &s_full[stage], stream_policy);
             } else {
                 mbar_arrive(&s_full[stage]);
             }
@@ -185,6 +186,7 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
 
     // ---------------------------------------------------- compute warps
     const u32 lt = lanemask_lt();
+    const u64 keep_policy = l2_policy_evict_last();   // bitmap words
     u32 tmin = 0xffffffffu, tmax = 0u;   // MODE 2: this thread's surviving flipped keys
     u32 nsel = 0;                        // MODE 2: rows of this thread that passed the predicate (before the semi-join probe)
     u32 nkept = 0;                       // PROBE: pairs written (thread SEL_THREADS - 1 sums the tile totals)
@@ -212,7 +214,7 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
                 const bool pass = valid && (select_all || sv > sel_val);
                 T.key[j] = kv;
                 T.passmask |= (pass ? 1u : 0u) << j;
-                if (PROBE) T.probe[j] = pass ? __ldg(bloom.probe + (bloom_hash((u32)kv ^ 0x80000000u, bloom.shift) >> 5)) : 0u;
+                if (PROBE) T.probe[j] = pass ? ld_nc_hint(bloom.probe + (bloom_hash((u32)kv ^ 0x80000000u, bloom.shift) >> 5), keep_policy) : 0u;
             }
         }
         __syncwarp();
@@ -269,7 +271,7 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
                     tmax = k > tmax ? k : tmax;
                     if (bloom.set) {
                         const u32 h = bloom_hash(k, bloom.shift);
-                        atomicOr(bloom.set + (h >> 5), 1u << (h & 31u));
+                        red_or_hint(bloom.set + (h >> 5), 1u << (h & 31u), keep_policy);
                     }
                 }
             }
@@ -447,6 +449,7 @@ __global__ void __launch_bounds__(256) bloom_filter_kernel(const BloomFilterArgs
     const u32 lane = threadIdx.x & 31u;
     const u32 lt = lanemask_lt();
     const u32 warps = gridDim.x * 8u;
+    const u64 keep_policy = l2_policy_evict_last();
     for (u32 t = blockIdx.x * 8u + (threadIdx.x >> 5); t < A.num_tiles; t += warps) {
         const u32 cnt = A.counts[t];
         u64 *slot = A.slots + (size_t)t * A.tile_rows;
@@ -463,7 +466,7 @@ __global__ void __launch_bounds__(256) bloom_filter_kernel(const BloomFilterArgs
 #pragma unroll
             for (int k = 0; k < PC_UNROLL; k++) {
                 const u32 i = i0 + k * 32 + lane;
-                word[k] = i < cnt ? __ldg(A.probe + (bloom_hash(pair_key(v[k]), A.shift) >> 5)) : 0u;
+                word[k] = i < cnt ? ld_nc_hint(A.probe + (bloom_hash(pair_key(v[k]), A.shift) >> 5), keep_policy) : 0u;
             }
             __syncwarp();   // every lane holds its part of the chunk before any lane stores
 #pragma unroll
