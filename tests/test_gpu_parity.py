@@ -258,6 +258,48 @@ def test_run_key_range_sort_plans(smj, port, lo1, hi1, lo2, hi2):
     assert 0 <= st["sort_passes"] <= max(passes(lo1, hi1), passes(lo2, hi2))
 
 
+@pytest.mark.parametrize("n1,n2", [(90_000, 60_000), (50_000, 120_000)])
+@pytest.mark.parametrize("overlap", ["all", "none", "half", "dups_left", "dups_both", "fk"])
+def test_run_semijoin_filter_cases(smj, port, overlap, n1, n2):
+    """The semi-join bitmaps between select and sort (smj_select.cu): rows whose key the other table lacks are dropped
+    before the sort, which must not change a single output row.  Covers both table orders (the smaller table is selected
+    first and filtered by a separate pass, the larger one probes inside its select kernel), key sets that coincide (the
+    device skips the filter pass), disjoint key sets inside the same range (everything is dropped) and duplicate runs."""
+    rng = np.random.default_rng(n1 + len(overlap))
+    t1, t2 = rand_table(rng, n1, 3, 0, 1000), rand_table(rng, n2, 5, 0, 1000)
+    if overlap == "all":
+        keys = rng.permutation(max(n1, n2)).astype(np.int32) + 7
+        k1, k2 = keys[:n1], rng.permutation(keys)[:n2]
+    elif overlap == "none":
+        k1 = 2 * rng.permutation(n1).astype(np.int32)            # even keys
+        k2 = 2 * rng.permutation(n2).astype(np.int32) + 1        # odd keys, same range
+    elif overlap == "half":
+        k1 = rng.permutation(2 * n1)[:n1].astype(np.int32)
+        k2 = rng.permutation(2 * n1)[:n2].astype(np.int32) if 2 * n1 >= n2 else rng.permutation(n2).astype(np.int32)
+    elif overlap == "dups_left":
+        k1 = rng.integers(0, n1 // 20, size=n1).astype(np.int32)  # ~20 rows per key on the left
+        k2 = rng.permutation(n2).astype(np.int32)                 # unique on the right: min(cL, 1) rows per key
+    elif overlap == "dups_both":
+        k1 = rng.integers(0, 3000, size=n1).astype(np.int32)
+        k2 = rng.integers(1500, 4500, size=n2).astype(np.int32)   # long runs on both sides, half of the keys shared
+    else:   # foreign key: every row of the larger table refers to a key of the smaller one, > 3/4 of them survive its
+        # select, so the device skips the filter pass over the smaller table
+        small = rng.permutation(4 * min(n1, n2))[:min(n1, n2)].astype(np.int32)
+        large = rng.choice(small, size=max(n1, n2)).astype(np.int32)
+        k1, k2 = (small, large) if n1 <= n2 else (large, small)
+    t1[:, 2], t2[:, 0] = k1, k2
+    kn = dict(select_col1=0, select_val1=200, select_col2=1, select_val2=100, join_key1=2, join_key2=0)
+    if overlap == "fk":   # keep ~95 % of the smaller table so that > 3/4 of the larger one's rows find their key
+        kn["select_val1" if n1 <= n2 else "select_val2"] = 50
+    want, sel, _ = port.run(t1, t2, kn["select_col1"], kn["select_val1"], kn["select_col2"], kn["select_val2"], 2, 0)
+    for _ in range(3):   # eager, graph capture, graph replay
+        got, st = smj.run(t1, t2, **kn)
+        assert st["rows_selected"] == list(sel)               # the predicate's survivors, not the filter's
+        assert_same(got, want, f"run semijoin {overlap} {n1}x{n2}")
+    if overlap == "none":
+        assert got.shape[0] == 0
+
+
 def test_run_many_to_many_mode(smj, port):
     """smj_run with join_mode = SMJ_JOIN_MANY (extension): select -> sort -> every pair of equal keys."""
     rng = np.random.default_rng(77)
