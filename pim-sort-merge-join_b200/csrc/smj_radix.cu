@@ -4,11 +4,12 @@
 // merge tree) and cpu_app.c:172-202.  The reference sort is a STABLE ascending insertion sort; every pass
 // below is stable, so LSD over the key digits gives the identical order (ties stay in row-id order).
 //
-// One kernel per 8-bit digit: a CTA takes a tile through an atomic ticket, ranks its items with
-// warp-match (__match_any_sync) against per-warp digit counters in shared memory, publishes the tile's
-// 256 digit counts, resolves the global offset of each digit with a per-digit decoupled look-back over the
-// earlier tiles (chained scan), reorders the tile in shared memory and writes each digit's run contiguously.
-// Digit histograms for all passes come from the select kernel (or radix_hist_kernel) up front.
+// One kernel launch per 8-bit digit of (key - smallest key) -- a device-resident sort plan says how many of the four
+// the key range needs, the others exit at once: a CTA takes a tile through an atomic ticket, counts digits per warp in
+// shared memory, publishes the tile's 256 digit counts, ranks its items against shared-memory peer masks (atomicOr, not
+// __match_any_sync: see below), reorders the tile in shared memory, resolves the global offset of each digit with a
+// batched decoupled look-back over the earlier tiles and writes each digit's run contiguously.
+// Digit histograms for all passes come from the compaction copy (smj_select.cu) or radix_hist_kernel up front.
 #include "smj_internal.h"
 #include "smj_dev.cuh"
 

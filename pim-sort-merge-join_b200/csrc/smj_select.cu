@@ -1,11 +1,16 @@
-// smj_select.cu -- predicate evaluation fused with warp-ballot/popc stream compaction, a single-pass
-// decoupled look-back scan and (optionally) the 4 x 256 radix digit histogram of the surviving keys.
+// smj_select.cu -- predicate evaluation fused with warp-ballot/popc stream compaction into (key, row id) pairs, plus what
+// the sort needs from the same pass: the surviving keys' range (sort plan), their digit histograms, and the semi-join
+// key bitmaps that let smj_run drop rows the other table cannot match before they are sorted.
 //
 // Replaces the DPU select kernel (sort-merge-join/select.c:24-39 filter, :42-61 tasklet handshake prefix,
 // :125-185 block loop) and cpu_app.c:81-112.  Same contract: keep rows with cell[sel_col] > sel_val
 // (strict, signed), original order preserved.  Instead of compacting whole rows in place it emits
-// (flipped key << 32 | row id) pairs: the payload stays where it is and is gathered once, after the sort
+// (flipped key << 32 | row id) pairs: the payload stays where it is and is gathered once, after the join
 // (late materialisation), so the select pass reads the table exactly once and writes 8 B per survivor.
+//
+// Kernels: select_pairs_kernel (decoupled look-back, any table shape; the fallback), select_tma_kernel (TMA-fed,
+// warp-specialised, per-tile slots; the one smj_run uses), tile_scan / select_compact (slots -> dense pairs),
+// plan_scan / bloom_filter / plan_compact (smj_run: both tables per launch, sort plans, semi-join filter).
 #include "smj_internal.h"
 #include "smj_dev.cuh"
 #include <stdlib.h>
