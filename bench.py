@@ -264,8 +264,12 @@ def main():
                 "algorithmic_bytes_per_launch": pass_bytes, "avg_launch_ms": pass_avg_ms,
                 "launches_per_step": passes / max(args.steps, 1), "share_of_step": pass_ms / max(dev_ms, 1e-9),
                 "pairs_sorted_per_launch": pass_bytes / 16.0,
+                # B = the fixed algorithmic-bytes formula of the whole pipeline (four passes over every
+                # selected row); "planned" = the same formula for the passes and pairs the device plan actually sorted
                 "pipeline_model_bytes": st["bytes_model"], "pipeline_model_gbs": st["bytes_model"] / (ms * 1e-3) / 1e9,
                 "pipeline_frac_of_peak": st["bytes_model"] / (ms * 1e-3) / 1e9 / peak,
+                "pipeline_planned_bytes": st.get("bytes_planned", 0.0),
+                "pipeline_planned_frac_of_peak": st.get("bytes_planned", 0.0) / (ms * 1e-3) / 1e9 / peak,
                 "note": (f"pair arrays of this workload ({8e-6 * m_avg:.0f} MB each) " +
                          ("fit the 126 MB L2: the pass is not HBM-bound here (ncu: DRAM 11 %), the fraction is of the HBM roofline the model names"
                           if 16 * m_avg < 100e6 else "exceed the 126 MB L2: the pass streams from and to HBM"))}

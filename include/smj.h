@@ -84,6 +84,9 @@ typedef struct {
     /* algorithmic bytes (16 B per pair the launch sorts) of an average executed pass launch: the sort runs
      * ceil(bits(max key - min key) / 8) passes per table, decided on the device */
     double  sort_pass_bytes_avg;
+    /* bytes_model restated for the work this run's device plan did: the radix passes the key range needed, over the
+     * pairs that survived the semi-join filter (bytes_model itself is the fixed formula: four passes, every selected row) */
+    double  bytes_planned;
 } smj_stats_t;
 
 /* fills *cfg from the user.h macros this library was compiled with (include/user.h) */

@@ -910,7 +910,8 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
         stats->sort_pass_ms_avg = stats->sort_passes ? sum / stats->sort_passes : 0;
         stats->sort_pass_bytes_avg = np_max ? 16.0 * ((double)m[0] * np[0] + (double)m[1] * np[1]) / np_max : 0;
         // the model's sort term (16 B x 4 passes x selected rows) restated for the passes and pairs this run's plan sorted
-        stats->bytes_model += 16.0 * ((double)m[0] * np[0] + (double)m[1] * np[1]) - 16.0 * SMJ_KEY_PASSES * ((double)m_sel[0] + (double)m_sel[1]);
+        stats->bytes_planned = stats->bytes_model + 16.0 * ((double)m[0] * np[0] + (double)m[1] * np[1]) -
+                               16.0 * SMJ_KEY_PASSES * ((double)m_sel[0] + (double)m_sel[1]);
     }
     return SMJ_OK;
 }

@@ -31,7 +31,7 @@ def test_header_symbols_all_exported(smj):
 def test_struct_layouts_match_header(smj):
     assert ctypes.sizeof(smj.Table) == 24
     assert ctypes.sizeof(smj.Config) == 48
-    assert ctypes.sizeof(smj.Stats) == 8 * 8 + 5 * 8 + 2 * 8 + 8 + 8 + 8 + 8   # + sort_pass_bytes_avg
+    assert ctypes.sizeof(smj.Stats) == 8 * 8 + 5 * 8 + 2 * 8 + 8 + 8 + 8 + 8 + 8   # + sort_pass_bytes_avg, bytes_planned
 
 
 def test_defaults_are_the_reference_user_h(smj):
