@@ -388,7 +388,10 @@ __global__ void __launch_bounds__(TS_THREADS) plan_scan_kernel(const PlanScanArg
 struct PlanCompactJob { const u64 *slots; const u32 *counts; const u64 *offsets; u32 num_tiles, tile_rows; u64 *buf[2];
                         const SmjSortPlan *plan; u32 *hist; };
 struct PlanCompactArgs { PlanCompactJob t[2]; };
-constexpr int PC_UNROLL = 8;
+#ifndef SMJ_PC_UNROLL
+#define SMJ_PC_UNROLL 8
+#endif
+constexpr int PC_UNROLL = SMJ_PC_UNROLL;
 
 __global__ void __launch_bounds__(256) plan_compact_kernel(const PlanCompactArgs A)
 {
@@ -566,13 +569,16 @@ int smj_launch_select_pairs(SmjCtx *c, const int32_t *d_in, int64_t n, int cols,
     return SMJ_OK;
 }
 
+#ifndef SMJ_BLOOM_BITS_PER_ROW
+#define SMJ_BLOOM_BITS_PER_ROW 4
+#endif
 // log2 of the bits per semi-join bitmap, or 0 when the filter is not used for these table sizes
 static int bloom_log2_bits(int64_t n0, int64_t n1)
 {
     const int64_t n_first = n0 <= n1 ? n0 : n1;
     if (n0 <= 0 || n1 <= 0 || 4 * n_first > (1ll << 29)) return 0;
     int lb = 16;
-    while (lb < 28 && (1ll << lb) < 4 * n_first) lb++;
+    while (lb < 28 && (1ll << lb) < SMJ_BLOOM_BITS_PER_ROW * n_first) lb++;
     return lb;
 }
 size_t smj_bloom_bytes(int64_t n0, int64_t n1)
