@@ -198,6 +198,9 @@ def main():
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1 or args.gpus > 1:
+        # stdout carries the one JSON line: NCCL's own debug output (the "NCCL version" banner of NCCL_DEBUG=VERSION,
+        # the topology lines of NCCL_DEBUG=INFO) goes to stderr unless the caller chose a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         from bench_multi import run_multi   # one process per GPU over NCCL
         return run_multi(args, w, name)
 
