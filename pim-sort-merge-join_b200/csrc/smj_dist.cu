@@ -2,20 +2,28 @@
 //
 // Replaces the reference's host-mediated data movement between stages -- the per-DPU dpu_push_xfer gathers and
 // scatters (sort-merge-join/app.c:222-288), the log-depth merge tournament that round-trips whole tables through
-// host memory (app.c:413-547) and the host-side key-range split for the join (app.c:585-633) -- with ONE exchange:
+// host memory (app.c:413-547) and the host-side key-range split for the join (app.c:585-633) -- with ONE exchange.
 //
-//   1. every rank selects and sorts ITS contiguous row block of both tables (the single-GPU kernels) and
-//      materialises the sorted rows (payload gather);
-//   2. splitters: each rank contributes regular samples of both sorted key arrays (ncclAllGather); every rank
-//      derives the same G-1 key splitters from the gathered samples (smj_plan_splitters, plain host code);
-//   3. per-rank bucket boundaries = lower bounds of the splitters in the sorted keys (device), bucket sizes are
-//      all-gathered so every rank knows the G x G row-count matrix of both tables;
-//   4. both tables move with one grouped ncclSend/ncclRecv all-to-all over NVLink: after the local sort each bucket
-//      IS a contiguous slice of the sorted rows, so no scatter pass is needed;
-//   5. each rank merge-path-merges the G sorted runs it received per table (ties: lower source rank first, which is
-//      original row order because rank order = row-block order) and joins locally;
+// Default path, smj_run_multi (partition first):
+//   1. splitters: every rank contributes regular row samples of both tables with the predicate applied
+//      (ncclAllGather); every rank sorts the same gathered samples on the device and so derives the same G-1 key
+//      splitters (splitters_kernel, the device twin of smj_plan_splitters) -- no host round trip;
+//   2. select fused with key-range partitioning of the ROWS (smj_partition.cu): survivors grouped by destination rank
+//      inside their tile's slot, original order kept inside each bucket;
+//   3. the per-bucket totals (and every rank's receive capacity) are all-gathered: the G x G row-count matrix, the one
+//      host wait of this path (buffer sizing, smj_plan_exchange);
+//   4. exchange fused into the compaction kernel: each (tile, bucket) segment is stored straight into the destination
+//      rank's receive buffer through a CUDA-IPC mapping (NVLink stores from the SMs); SMJ_DIST_EXCHANGE=nccl uses a
+//      send buffer and one grouped ncclSend/ncclRecv all-to-all instead;
+//   5. the single-GPU pipeline (smj_run_single, select disabled) sorts and joins what arrived: runs sit in source-rank
+//      order with original order inside each, so the stable sort reproduces the reference's order;
 //   6. the result shards, concatenated in rank order, are the single-GPU result (splitters are key values, so all
 //      rows of one key meet on one rank and the zip pairing of equal keys is local).
+//
+// SMJ_DIST_MODE=merge, smj_run_multi_sorted (sort first; also the fallback for tables the partition kernel cannot
+// take): local select + sort + payload gather, splitters from samples of the sorted keys (host), bucket bounds by
+// binary search, one grouped ncclSend/ncclRecv of the contiguous sorted slices, a merge-path merge tree over the G
+// received runs per table (ties: lower source rank first = original row order), local join.
 //
 // NCCL is loaded lazily (dlopen of libnccl.so.2) so the single-GPU library has no hard dependency on it and a
 // process that already loaded torch's NCCL shares that copy.

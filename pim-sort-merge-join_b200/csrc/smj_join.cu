@@ -12,9 +12,10 @@
 // Work is split into equal tiles of the merged sequence by merge-path co-ranking (left first on ties), so
 // lower_bound(KR, k) is simply the right cursor when the left element is consumed; duplicates that straddle
 // a tile are resolved with lower-bound searches (one global search per tile, precomputed by the partition
-// kernel).  Count -> scan -> write: each tile counts its matches, a decoupled look-back gives the tile's
-// output offset, and the (left row id, right row id) matches are written coalesced; a second kernel
-// materialises the joined rows (all left columns, then right columns except key2: cpu_app.c:240-251).
+// kernel).  Count -> scan -> write: each tile writes its (left row id, right row id) matches into its own slot
+// and its count into tile_count[]; a one-CTA scan turns the counts into output offsets and a compaction copy makes
+// the dense match list (no CTA waits for another one); a last kernel materialises the joined rows (all left
+// columns, then right columns except key2: cpu_app.c:240-251) with coalesced stores.
 #include "smj_internal.h"
 #include "smj_dev.cuh"
 
