@@ -755,11 +755,6 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
     WS_TRY(md, uint2 *, c, WS_MATCH_DENSE, (size_t)j_max * 8);
     WS_TRY(bloom_ws, char *, c, WS_BLOOM, smj_bloom_bytes(n[0], n[1]));   // sized here: no allocation inside a graph capture
     (void)bloom_ws;
-    // row store of the table that is selected second: its surviving rows travel next to their pairs (smj_select.cu, STORE)
-    int rs_table = 1;
-    const size_t rs_bytes = smj_rowstore_bytes(n, cc, &rs_table);
-    int32_t *rowstore = nullptr;
-    if (rs_bytes) { WS_TRY(rs, int32_t *, c, WS_ROWSTORE, rs_bytes); rowstore = rs; }
     smj_table_t dev_out = {nullptr, 0, c_out, 1};
     SMJ_TRY(smj_alloc_out(c, &dev_out, j_max, c_out));   // upper bound; rows is set once the count is known
     CUDA_TRY(cudaEventRecord(c->ev[E_H2D], c->stream));
@@ -798,8 +793,7 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
                 SmjSelectJob job[2];
                 for (int t = 0; t < 2; t++)
                     job[t] = {d_t[t], n[t], cc[t], sel_col[t], sel_val[t], 0, key[t], {ping[t], pong[t]}, (u64 *)mm + (t ? n[0] : 0),
-                              (u64 *)(scr + off_sel + (t ? stiles[0] * 8 : 0)), h->hist[t], &h->count[t], &h->plan[t], &h->sel_count[t], &h->kept_count[t],
-                              t == rs_table ? rowstore : nullptr};
+                              (u64 *)(scr + off_sel + (t ? stiles[0] * 8 : 0)), h->hist[t], &h->count[t], &h->plan[t], &h->sel_count[t], &h->kept_count[t]};
                 rc = smj_launch_select_plan2(c, job);
                 if (rc == 1) { planned = false; rc = SMJ_OK; }   // a table the TMA path cannot take: histograms in the select kernel, four passes
             }
@@ -827,21 +821,9 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
             }
             // join: co-rank, count, scan, compact the matches; then materialise rows straight from the input tables
             const JoinScratch jsr = join_scratch(scr + off_join, jt);
-            // with a row store, that table's pairs carry row store positions and its payload is gathered from there
-            const int32_t *src_t[2] = {d_t[0], d_t[1]};
-            if (planned && rowstore) src_t[rs_table] = rowstore;
-            // SMJ_MT_TILES=1: rows materialised straight from the match kernel's tile slots (no scan, no dense match list)
-            static const bool mt_tiles = getenv("SMJ_MT_TILES") && atoi(getenv("SMJ_MT_TILES")) != 0;
-            if (mt_tiles) {
-                PIPE_TRY(smj_launch_join_match(c, ping[0], ping[1], &h->count[0], (u32)n[0], (u32)n[1], SMJ_JOIN_ZIP, jsr.part, jsr.tile_count,
-                                               nullptr, mm, nullptr, &h->jcount));
-                PIPE_TRY(smj_launch_join_materialize_tiles(c, mm, jsr.tile_count, &h->count[0], (u32)n[0], (u32)n[1], src_t[0], cc[0], src_t[1], cc[1],
-                                                           key[1], nullptr, c->d_out_ptr, &h->jcount));
-            } else {
-                PIPE_TRY(smj_launch_join_match(c, ping[0], ping[1], &h->count[0], (u32)n[0], (u32)n[1], SMJ_JOIN_ZIP, jsr.part, jsr.tile_count,
-                                               jsr.tile_off, mm, md, &h->jcount));
-                PIPE_TRY(smj_launch_join_materialize(c, md, &h->jcount, j_max, src_t[0], cc[0], src_t[1], cc[1], key[1], nullptr, c->d_out_ptr));
-            }
+            PIPE_TRY(smj_launch_join_match(c, ping[0], ping[1], &h->count[0], (u32)n[0], (u32)n[1], SMJ_JOIN_ZIP, jsr.part, jsr.tile_count,
+                                           jsr.tile_off, mm, md, &h->jcount));
+            PIPE_TRY(smj_launch_join_materialize(c, md, &h->jcount, j_max, d_t[0], cc[0], d_t[1], cc[1], key[1], nullptr, c->d_out_ptr));
 #undef PIPE_TRY
 #undef PIPE_CUDA
         } while (0);

@@ -282,12 +282,6 @@ __device__ __forceinline__ void red_or_hint(u32 *p, u32 v, u64 policy)
     asm volatile("red.global.or.b32.L2::cache_hint [%0], %1, %2;" ::"l"(p), "r"(v), "l"(policy) : "memory");
 }
 
-__device__ __forceinline__ void st_v4_hint(int4 *p, int4 v, u64 policy)
-{
-    asm volatile("st.global.L2::cache_hint.v4.s32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy)
-                 : "memory");
-}
-
 // barrier among a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(u32 id, u32 nthreads)
 {

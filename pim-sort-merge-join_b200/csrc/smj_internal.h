@@ -56,9 +56,8 @@ enum SmjSlot {
     WS_MATCH,                        // matched (left rowid, right rowid)
     WS_TMP_ROWS, WS_TMP_ROWS2,       // staging for in-place sort / host outputs
     WS_XCHG_SEND1, WS_XCHG_SEND2, WS_XCHG_RECV1, WS_XCHG_RECV2, WS_SAMPLES,
-    WS_MERGE_A, WS_MERGE_B, WS_RADIX, WS_MATCH_DENSE, WS_BLOOM, WS_ROWSTORE,
+    WS_MERGE_A, WS_MERGE_B, WS_RADIX, WS_MATCH_DENSE, WS_BLOOM,
 };
-static_assert(WS_ROWSTORE < SmjCtx::kSlots, "workspace slot table too small");
 
 int   smj_set_error(int code, const char *fmt, ...);
 int   smj_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
@@ -127,7 +126,6 @@ struct SmjBloom {
     u32 shift = 0;                // 32 - log2(bits)
     u64 *sel_count = nullptr;     // += rows that passed the predicate (before the probe)
     u64 *kept_count = nullptr;    // += rows that also passed the probe (probing launches only)
-    int32_t *rowstore = nullptr;  // probing launch of smj_run: surviving rows are copied here, entry = pair slot position (or null)
 };
 
 // smj_run's select stage over both tables (smj_select.cu): see smj_launch_select_plan2.
@@ -141,16 +139,10 @@ struct SmjSelectJob {
     SmjSortPlan *plan;    // zeroed
     u64 *d_sel_count;     // zeroed; out: rows that passed the predicate (smj_stats_t.rows_selected)
     u64 *d_kept_count;    // zeroed; out: of those, the rows whose key bit was set in the other table's bitmap
-    int32_t *rowstore;    // n * cols cells or null: see smj_rowstore_bytes
 };
 // returns 1 (nothing launched) when a table cannot take the TMA path
 int smj_launch_select_plan2(SmjCtx *c, const SmjSelectJob job[2]);
 size_t smj_bloom_bytes(int64_t n0, int64_t n1);   // WS_BLOOM bytes the call above uses (0: no semi-join filter)
-// Row store of the table that is selected second (the probing one): bytes smj_launch_select_plan2 wants in
-// job[*which].rowstore, or 0 when the store is not used for these shapes (no semi-join filter, table too large,
-// SMJ_ROWSTORE=0).  When it is used, that table's pairs carry row store positions instead of row ids, and the join
-// gathers that table's payload from the row store.
-size_t smj_rowstore_bytes(const int64_t n[2], const int cols[2], int *which);
 
 // ------------------------------------------------------------------ radix sort (smj_radix.cu)
 size_t smj_radix_num_tiles(u32 n);
@@ -205,12 +197,6 @@ int smj_launch_join_many_expand(SmjCtx *c, const u64 *d_l, const u64 *d_r, const
 // d_out_indirect (may be null): device cell holding the output pointer, read instead of d_out (graph replay)
 int smj_launch_join_materialize(SmjCtx *c, const uint2 *d_dense, const u64 *d_nj, int64_t nj_max, const int32_t *d_t1, int c1,
                                 const int32_t *d_t2, int c2, int key2, int32_t *d_out, int32_t *const *d_out_indirect = nullptr);
-
-// the joined rows straight from the match kernel's tile slots: call smj_launch_join_match with d_tile_off = d_dense = null
-// (no scan, no compaction), then this; *d_count receives the number of joined rows
-int smj_launch_join_materialize_tiles(SmjCtx *c, const uint2 *d_slots, const u32 *d_tile_count, const u64 *d_counts, u32 m1_max,
-                                      u32 m2_max, const int32_t *d_t1, int c1, const int32_t *d_t2, int c2, int key2, int32_t *d_out,
-                                      int32_t *const *d_out_indirect, u64 *d_count);
 
 // ------------------------------------------------------------------ synth (smj_synth.cu)
 int smj_launch_synth(SmjCtx *c, int32_t *d_out, int64_t row0, int64_t rows, int64_t total_rows, int cols,

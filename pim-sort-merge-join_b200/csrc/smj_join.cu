@@ -398,111 +398,6 @@ join_materialize_kernel(const uint2 *__restrict__ matches, const u64 *__restrict
     }
 }
 
-
-// The same rows straight from the match kernel's per-tile slots (smj_run): replaces join_scan_kernel + join_compact_kernel
-// + join_materialize_kernel, i.e. two launches and one write + one read of the dense match list.  Every block owns a
-// contiguous range of the used tiles and computes the output row of its first tile itself (a block-wide sum over the
-// counts of the tiles before it: a few thousand L2-resident words), so no block waits for another one; the block that
-// owns the last used tile writes the total.
-template <bool VEC>
-__global__ void __launch_bounds__(MT_THREADS)
-join_materialize_tiles_kernel(const uint2 *__restrict__ slots, const u32 *__restrict__ tile_count, const u64 *__restrict__ counts,
-                              u32 m1_max, u32 m2_max, const int32_t *__restrict__ t1, int c1, const int32_t *__restrict__ t2, int c2,
-                              int key2, int32_t *__restrict__ out_direct, int32_t *const *__restrict__ out_indirect, int rows_per_block,
-                              u64 *total)
-{
-    __shared__ __align__(16) int32_t s_out[MT_SMEM_CELLS];
-    __shared__ u64 s_red[MT_THREADS / 32];
-    PDL_ENTER();
-    int32_t *__restrict__ out = out_indirect ? *out_indirect : out_direct;
-    u32 m1, m2;
-    load_counts(counts, m1_max, m2_max, m1, m2);
-    const u32 used = (m1 == 0 || m2 == 0) ? 0u : (u32)(((u64)m1 + m2 + JN_TILE - 1) / JN_TILE);
-    const u32 per = (used + gridDim.x - 1) / gridDim.x;
-    const u64 tb64 = (u64)blockIdx.x * per;
-    const u32 tile_lo = tb64 < (u64)used ? (u32)tb64 : used;
-    const u32 tile_hi = (u64)tile_lo + per < (u64)used ? tile_lo + per : used;
-    if (tile_lo >= tile_hi) return;
-    const int c_out = c1 + c2 - 1;
-    const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-
-    // output row of this block's first tile
-    u64 row_base = 0;
-    {
-        u64 sum = 0;
-        for (u32 i = threadIdx.x; i < tile_lo; i += MT_THREADS) sum += tile_count[i];
-        sum = warp_sum(sum);
-        if (lane == 0) s_red[w] = sum;
-        __syncthreads();
-#pragma unroll
-        for (int ww = 0; ww < MT_THREADS / 32; ww++) row_base += s_red[ww];
-    }
-    for (u32 tile = tile_lo; tile < tile_hi; tile++) {
-        const u32 cnt = tile_count[tile];
-        const uint2 *matches = slots + (size_t)tile * JN_TILE;
-        for (u32 r0 = 0; r0 < cnt; r0 += (u32)rows_per_block) {
-            const int nrows = (int)((cnt - r0 < (u32)rows_per_block) ? (cnt - r0) : (u32)rows_per_block);
-            __syncthreads();   // previous copy-out is done with s_out
-            for (int task0 = threadIdx.x; task0 < 2 * nrows; task0 += MT_ILP * MT_THREADS) {
-                uint2 m[MT_ILP];
-                const int32_t *src[MT_ILP];
-                int32_t *dst[MT_ILP];
-                int cc[MT_ILP];
-                bool right[MT_ILP], live[MT_ILP];
-#pragma unroll
-                for (int u = 0; u < MT_ILP; u++) {
-                    const int task = task0 + u * MT_THREADS;
-                    live[u] = task < 2 * nrows;
-                    right[u] = task >= nrows;
-                    const int r = right[u] ? task - nrows : task;
-                    m[u] = live[u] ? matches[r0 + r] : make_uint2(0u, 0u);
-                    dst[u] = s_out + r * c_out + (right[u] ? c1 : 0);
-                }
-#pragma unroll
-                for (int u = 0; u < MT_ILP; u++) {
-                    cc[u] = right[u] ? c2 : c1;
-                    src[u] = right[u] ? t2 + (size_t)m[u].y * c2 : t1 + (size_t)m[u].x * c1;
-                }
-                if (VEC) {
-                    int4 v[MT_ILP];
-#pragma unroll
-                    for (int u = 0; u < MT_ILP; u++)
-                        if (live[u]) v[u] = __ldg(reinterpret_cast<const int4 *>(src[u]));
-#pragma unroll
-                    for (int u = 0; u < MT_ILP; u++) {
-                        if (!live[u]) continue;
-                        const int skip = right[u] ? key2 : -1;      // right rows drop column key2
-                        for (int q = 0;;) {
-                            const int32_t vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                const int col = 4 * q + e;
-                                if (col != skip) dst[u][col - ((skip >= 0 && col > skip) ? 1 : 0)] = vv[e];
-                            }
-                            if (++q >= cc[u] / 4) break;
-                            v[u] = __ldg(reinterpret_cast<const int4 *>(src[u]) + q);
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int u = 0; u < MT_ILP; u++) {
-                        if (!live[u]) continue;
-                        const int skip = right[u] ? key2 : -1;
-                        for (int q = 0; q < cc[u]; q++)
-                            if (q != skip) dst[u][q - ((skip >= 0 && q > skip) ? 1 : 0)] = __ldg(src[u] + q);
-                    }
-                }
-            }
-            __syncthreads();
-            const int ncell = nrows * c_out;
-            int32_t *o = out + (size_t)(row_base + r0) * c_out;
-            for (int cell = threadIdx.x; cell < ncell; cell += MT_THREADS) o[cell] = s_out[cell];
-        }
-        row_base += cnt;
-    }
-    if (tile_hi == used && threadIdx.x == 0) *total = row_base;
-}
-
 }  // namespace
 
 // ---- many-to-many expansion (SMJ_JOIN_MANY): runs[i] = (first right position, right run length) of left element i.
@@ -634,7 +529,6 @@ int smj_launch_join_match(SmjCtx *c, const u64 *d_l, const u64 *d_r, const u64 *
         smj_launch(c, join_match_kernel<SMJ_JOIN_ZIP>, grid, JN_THREADS, 0, d_l, d_r, d_counts, m1_max, m2_max, d_part, d_runstart,
                    d_matches, d_tile_count, d_count, (uint2 *)nullptr);
         KERNEL_CHECK(c);
-        if (!d_tile_off) return SMJ_OK;   // the caller materialises from the tile slots (smj_launch_join_materialize_tiles)
         smj_launch(c, join_scan_kernel, 1, JS_THREADS, 0, d_tile_count, tiles, d_tile_off, d_count, d_counts, m1_max, m2_max);
         if (d_dense) {
             KERNEL_CHECK(c);
@@ -667,31 +561,6 @@ int smj_launch_join_materialize(SmjCtx *c, const uint2 *d_dense, const u64 *d_nj
         smj_launch(c, join_materialize_kernel<true>, grid, MT_THREADS, 0, d_dense, d_nj, nj_max, d_t1, c1, d_t2, c2, key2, d_out, d_out_indirect, rpb);
     else
         smj_launch(c, join_materialize_kernel<false>, grid, MT_THREADS, 0, d_dense, d_nj, nj_max, d_t1, c1, d_t2, c2, key2, d_out, d_out_indirect, rpb);
-    KERNEL_CHECK(c);
-    return SMJ_OK;
-}
-
-// Joined rows straight from the per-tile match slots of smj_launch_join_match(..., d_tile_off = nullptr, d_dense = nullptr):
-// no scan, no dense match list; *d_count receives the number of joined rows.
-int smj_launch_join_materialize_tiles(SmjCtx *c, const uint2 *d_slots, const u32 *d_tile_count, const u64 *d_counts, u32 m1_max,
-                                      u32 m2_max, const int32_t *d_t1, int c1, const int32_t *d_t2, int c2, int key2, int32_t *d_out,
-                                      int32_t *const *d_out_indirect, u64 *d_count)
-{
-    if (m1_max == 0 || m2_max == 0) return SMJ_OK;   // caller zeroed *d_count
-    const int c_out = c1 + c2 - 1;
-    if (c_out > MT_SMEM_CELLS) return smj_set_error(SMJ_EINVAL, "joined rows of %d columns exceed the %d-cell staging tile", c_out, MT_SMEM_CELLS);
-    int rpb = MT_SMEM_CELLS / c_out;
-    if (rpb > SMJ_MT_RPB) rpb = SMJ_MT_RPB;
-    const size_t tiles = smj_join_num_tiles((u64)m1_max + m2_max);
-    const int sms = sm_count(c);
-    const u32 grid = (u32)(tiles < (size_t)sms * SMJ_MT_GRID ? tiles : (size_t)sms * SMJ_MT_GRID);
-    const bool vec = (c1 % 4 == 0) && (c2 % 4 == 0) && ((((uintptr_t)d_t1) | ((uintptr_t)d_t2)) & 15) == 0;
-    if (vec)
-        smj_launch(c, join_materialize_tiles_kernel<true>, grid, MT_THREADS, 0, d_slots, d_tile_count, d_counts, m1_max, m2_max, d_t1, c1, d_t2, c2,
-                   key2, d_out, d_out_indirect, rpb, d_count);
-    else
-        smj_launch(c, join_materialize_tiles_kernel<false>, grid, MT_THREADS, 0, d_slots, d_tile_count, d_counts, m1_max, m2_max, d_t1, c1, d_t2, c2,
-                   key2, d_out, d_out_indirect, rpb, d_count);
     KERNEL_CHECK(c);
     return SMJ_OK;
 }

@@ -134,31 +134,20 @@ constexpr int SEL_STAGE_BYTES = 32768;
 constexpr int SEL_MAX_COLS_TMA = SEL_STAGE_BYTES / 4 / SEL_THREADS;   // 32 columns: at least one row per thread
 constexpr int SELW_THREADS = SEL_THREADS + 32;                         // + producer warp
 constexpr size_t SELW_SMEM = (size_t)SEL_STAGES * SEL_STAGE_BYTES;
-constexpr int SEL_STORE_STAGES = 3;                                    // STORE variant: a tile stays in its stage one tile longer
-constexpr size_t SELW_SMEM_STORE = (size_t)SEL_STORE_STAGES * SEL_STAGE_BYTES;
 
 // MODE 0: pairs only; 1: + 4 x 256 digit histogram of the surviving keys; 2: + min / max of the surviving keys into
 // *plan (the sort then runs only the passes the key RANGE needs, smj_radix.cu; the histogram of (key - min) digits is
 // built by the compaction copy, once the minimum is known).
-//
-// STORE (with PROBE, smj_run only): the rows that pass the predicate AND the probe are also copied, payload and all, into
-// a row store laid out like the pair slots (row store entry = slot position), and the pair's row id becomes that
-// position (monotonic in the original row order, so the stable sort order is unchanged).  The join then gathers this
-// table's payload from the few tens of MB of L2-resident row store instead of re-reading the whole table at random
-// (ncu: the materialise kernel's 16-byte gathers touched 96 % of both tables' lines).  The tile has to stay in shared
-// memory until the probe's answer is back, i.e. one tile longer, hence a ring of three stages.
-template <int MODE, bool PROBE = false, bool STORE = false>
+template <int MODE, bool PROBE = false>
 __global__ void __launch_bounds__(SELW_THREADS, PROBE ? 2 : 3)   // shared memory allows 3 CTAs per SM; the launch uses SMJ_SEL_CTAS
 select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, int sel_col, int32_t sel_val, int select_all,
                   int key_col, u32 rowid_base, u64 *__restrict__ slots, u32 *__restrict__ tile_count, u32 *hist, u32 num_tiles,
                   SmjSortPlan *plan, SmjBloom bloom)
 {
     constexpr bool HIST = MODE == 1;
-    constexpr int NST = STORE ? SEL_STORE_STAGES : SEL_STAGES;
-    static_assert(!STORE || (PROBE && MODE == 2), "the row store belongs to the probing select of smj_run");
     PDL_ENTER();
     extern __shared__ __align__(128) unsigned char sel_smem[];      // stage ring
-    __shared__ __align__(8) u64 s_full[NST], s_empty[NST];
+    __shared__ __align__(8) u64 s_full[SEL_STAGES], s_empty[SEL_STAGES];
     __shared__ u32 s_cnt[2][SEL_IPT * SEL_WARPS];
     __shared__ u32 s_hist[HIST ? SMJ_KEY_PASSES * SMJ_RADIX : 1];
 
@@ -168,7 +157,7 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
     if (HIST)
         for (u32 i = tid; i < SMJ_KEY_PASSES * SMJ_RADIX; i += SELW_THREADS) s_hist[i] = 0;
     if (tid == 0) {
-        for (int st = 0; st < NST; st++) { mbar_init(&s_full[st], 1); mbar_init(&s_empty[st], SEL_WARPS); }
+        for (int st = 0; st < SEL_STAGES; st++) { mbar_init(&s_full[st], 1); mbar_init(&s_empty[st], SEL_WARPS); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -195,7 +184,7 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
             } else {
                 mbar_arrive(&s_full[stage]);
             }
-            if (++stage == NST) { stage = 0; parity ^= 1u; }
+            if (++stage == SEL_STAGES) { stage = 0; parity ^= 1u; }
         }
         return;
     }
@@ -208,11 +197,7 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
     u32 nkept = 0;                       // PROBE: pairs written (thread SEL_THREADS - 1 sums the tile totals)
 
     // what a thread keeps of a tile once the ring stage has been released
-    // (STORE: the tile stays in its stage, so the keys are re-read from there for the survivors; only the bit position
-    // of every row's hash inside its bitmap word is kept, 8 bits per row, which keeps two tiles' state within registers)
-    struct TileRegs { int32_t key[STORE ? 1 : SEL_IPT]; u32 probe[PROBE ? SEL_IPT : 1]; u32 hbit[STORE ? SEL_IPT / 4 : 1];
-                      u32 passmask; u32 tile; u32 stage; };
-    const bool store_vec = STORE && (cols % 4 == 0);   // 16-byte rows: the ring stages and the row store are 128-byte aligned
+    struct TileRegs { int32_t key[SEL_IPT]; u32 probe[PROBE ? SEL_IPT : 1]; u32 passmask; u32 tile; };
 
     // predicate on the tile in ring stage `stage`; with PROBE also issues the loads of the other table's bitmap words
     auto load_tile = [&](u32 tile, u32 stage, TileRegs &T) {
@@ -220,12 +205,7 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
         const u32 rows_valid = (u32)((n - tile_base < (int64_t)tile_rows) ? (n - tile_base) : (int64_t)tile_rows);
         const int32_t *s_rows = reinterpret_cast<const int32_t *>(sel_smem + (size_t)stage * SEL_STAGE_BYTES);
         T.tile = tile;
-        T.stage = stage;
         T.passmask = 0;
-        if (STORE) {
-#pragma unroll
-            for (int q = 0; q < (STORE ? SEL_IPT / 4 : 1); q++) T.hbit[q] = 0;
-        }
 #pragma unroll
         for (int j = 0; j < SEL_IPT; j++) {
             if (j < ipt) {
@@ -237,21 +217,13 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
                     kv = (key_col == sel_col) ? sv : s_rows[row * cols + key_col];
                 }
                 const bool pass = valid && (select_all || sv > sel_val);
+                T.key[j] = kv;
                 T.passmask |= (pass ? 1u : 0u) << j;
-                if (STORE) {
-                    const u32 h = bloom_hash((u32)kv ^ 0x80000000u, bloom.shift);
-                    T.probe[j] = pass ? ld_nc_hint(bloom.probe + (h >> 5), keep_policy) : 0u;
-                    T.hbit[(STORE ? j : 0) >> 2] |= (h & 31u) << (8 * (j & 3));
-                } else {
-                    T.key[j] = kv;
-                    if (PROBE) T.probe[j] = pass ? ld_nc_hint(bloom.probe + (bloom_hash((u32)kv ^ 0x80000000u, bloom.shift) >> 5), keep_policy) : 0u;
-                }
+                if (PROBE) T.probe[j] = pass ? ld_nc_hint(bloom.probe + (bloom_hash((u32)kv ^ 0x80000000u, bloom.shift) >> 5), keep_policy) : 0u;
             }
         }
-        if (!STORE) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[stage]);   // this warp holds its cells in registers: stage can be refilled
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[stage]);   // this warp holds its cells in registers: stage can be refilled
         if (MODE == 2) nsel += __popc(T.passmask);
     };
 
@@ -264,10 +236,7 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
 #pragma unroll
         for (int j = 0; j < SEL_IPT; j++) {
             if (j < ipt) {
-                if (STORE) {
-                    const u32 hb = (T.hbit[(STORE ? j : 0) >> 2] >> (8 * (j & 3))) & 31u;
-                    if (!((T.probe[j] >> hb) & 1u)) passmask &= ~(1u << j);
-                } else if (PROBE) {   // no row of the other table hashes to this key's bit: the row cannot be joined
+                if (PROBE) {   // no row of the other table hashes to this key's bit: the row cannot be joined
                     const u32 h = bloom_hash((u32)T.key[j] ^ 0x80000000u, bloom.shift);
                     if (!((T.probe[j] >> (h & 31u)) & 1u)) passmask &= ~(1u << j);
                 }
@@ -293,24 +262,7 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
             const u32 add = __shfl_sync(FULL_MASK, v0, e >> 1);
             if (e & 1u) off += add;
             if ((passmask >> j) & 1u) {
-                u32 rid = rowid_base + (u32)(tile_base + j * SEL_THREADS + tid);
-                int32_t kv;
-                if (STORE) {   // the row travels with its pair: row store entry = slot position, which becomes the row id
-                    rid = (u32)tile_base + off + rank[j];
-                    const int32_t *srow = reinterpret_cast<const int32_t *>(sel_smem + (size_t)T.stage * SEL_STAGE_BYTES) +
-                                          (u32)(j * SEL_THREADS + tid) * (u32)cols;
-                    int32_t *drow = bloom.rowstore + (size_t)rid * cols;
-                    kv = srow[key_col];
-                    if (store_vec) {
-                        for (int q = 0; q < cols / 4; q++)
-                            st_v4_hint(reinterpret_cast<int4 *>(drow) + q, reinterpret_cast<const int4 *>(srow)[q], keep_policy);
-                    } else {
-                        for (int q = 0; q < cols; q++) drow[q] = srow[q];
-                    }
-                } else {
-                    kv = T.key[STORE ? 0 : j];
-                }
-                const u64 p = make_pair(kv, rid);
+                const u64 p = make_pair(T.key[j], rowid_base + (u32)(tile_base + j * SEL_THREADS + tid));
                 dst[off + rank[j]] = p;
                 if (HIST) {
                     const u32 k = pair_key(p);
@@ -328,10 +280,6 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
                     }
                 }
             }
-        }
-        if (STORE) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[T.stage]);   // this warp has copied its surviving rows out of the stage
         }
     };
 
@@ -352,7 +300,7 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
             } else {
                 finish_tile(cur, it++);
             }
-            if (++stage == NST) { stage = 0; parity ^= 1u; }
+            if (++stage == SEL_STAGES) { stage = 0; parity ^= 1u; }
         }
         if (PROBE && have_prev) finish_tile(prev, it++);
     }
@@ -563,7 +511,6 @@ static int select_set_attrs(SmjCtx *c)   // function attributes are per device
     CUDA_TRY(cudaFuncSetAttribute(select_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SELW_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(select_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SELW_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(select_tma_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SELW_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(select_tma_kernel<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SELW_SMEM_STORE));
     c->select_attr_set = true;
     return SMJ_OK;
 }
@@ -640,27 +587,6 @@ size_t smj_bloom_bytes(int64_t n0, int64_t n1)
     return lb ? 2 * ((size_t)1 << (lb - 3)) : 0;
 }
 
-static bool semijoin_enabled(void)
-{
-    static const bool on = !(getenv("SMJ_SEMIJOIN") && atoi(getenv("SMJ_SEMIJOIN")) == 0);
-    return on;
-}
-
-// The row store only pays while it stays L2-resident next to the pair arrays and the bitmaps; the bound is on the
-// selected-second table as a whole (the store is allocated like the table, only the survivors' entries are touched).
-#ifndef SMJ_ROWSTORE_MAX_BYTES
-#define SMJ_ROWSTORE_MAX_BYTES (1ull << 30)
-#endif
-size_t smj_rowstore_bytes(const int64_t n[2], const int cols[2], int *which)
-{
-    static const bool on = getenv("SMJ_ROWSTORE") && atoi(getenv("SMJ_ROWSTORE")) != 0;
-    const int second = n[0] <= n[1] ? 1 : 0;   // the smaller table is selected first (smj_launch_select_plan2)
-    if (which) *which = second;
-    if (!on || !semijoin_enabled() || bloom_log2_bits(n[0], n[1]) == 0) return 0;
-    const size_t bytes = (size_t)n[second] * (size_t)cols[second] * 4;
-    return bytes <= SMJ_ROWSTORE_MAX_BYTES ? bytes : 0;
-}
-
 // smj_run's select stage, both tables: select (key min / max instead of histograms) per table, ONE scan launch (tile
 // offsets, survivor counts, sort plans), ONE compaction launch (dense pairs into the buffer the plan names + digit
 // histograms of key - kmin).  Returns 1 without launching anything when a table cannot take the TMA path (the caller
@@ -670,7 +596,7 @@ int smj_launch_select_plan2(SmjCtx *c, const SmjSelectJob job[2])
     for (int t = 0; t < 2; t++)
         if (job[t].n > 0 && !select_use_tma(job[t].d_in, job[t].cols)) return 1;
     static const int full_passes = (getenv("SMJ_FULL_PASSES") && atoi(getenv("SMJ_FULL_PASSES")) != 0) ? 1 : 0;
-    const bool semijoin_on = semijoin_enabled();
+    static const bool semijoin_on = !(getenv("SMJ_SEMIJOIN") && atoi(getenv("SMJ_SEMIJOIN")) == 0);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     if (!c->select_attr_set) SMJ_TRY(select_set_attrs(c));
@@ -720,11 +646,7 @@ int smj_launch_select_plan2(SmjCtx *c, const SmjSelectJob job[2])
                 B.shift = 32u - (u32)lb;
             }
             const u32 grid = tiles < (u32)(sms * SMJ_SEL_CTAS) ? tiles : (u32)(sms * SMJ_SEL_CTAS);
-            if (B.probe && J.rowstore) {
-                B.rowstore = J.rowstore;
-                smj_launch(c, select_tma_kernel<2, true, true>, grid, SELW_THREADS, SELW_SMEM_STORE, J.d_in, J.n, J.cols, ipt, J.sel_col, (int32_t)sel_val,
-                           select_all, J.key_col, 0u, J.slots, d_counts, (u32 *)nullptr, tiles, J.plan, B);
-            } else if (B.probe)
+            if (B.probe)
                 smj_launch(c, select_tma_kernel<2, true>, grid, SELW_THREADS, SELW_SMEM, J.d_in, J.n, J.cols, ipt, J.sel_col, (int32_t)sel_val, select_all,
                            J.key_col, 0u, J.slots, d_counts, (u32 *)nullptr, tiles, J.plan, B);
             else
