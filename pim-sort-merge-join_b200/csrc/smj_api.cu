@@ -517,16 +517,18 @@ extern "C" int smj_merge(const smj_table_t *a, const smj_table_t *b, int key_col
 }
 
 // ------------------------------------------------------------------ smj_join
-// Join scratch of `tiles` tiles inside a byte arena: [tile_count u32 x tiles (zeroed)] [tile_off u64 x tiles] [part u32 x 2(tiles+1)]
+// Join scratch of `tiles` tiles inside a byte arena:
+// [tile_count u32 x tiles (zeroed)] [tile_off u64 x tiles + the scan's block sums] [part u32 x 2(tiles+1)]
 struct JoinScratch { u32 *tile_count; u64 *tile_off; u32 *part; size_t zero_bytes, bytes; };
 static JoinScratch join_scratch(char *base, size_t tiles)
 {
     JoinScratch j;
+    const size_t off_bytes = align_up((tiles + smj_join_scan_blocks(tiles)) * 8, 256);
     j.zero_bytes = align_up(tiles * 4, 256);
     j.tile_count = (u32 *)base;
     j.tile_off = (u64 *)(base + j.zero_bytes);
-    j.part = (u32 *)(base + j.zero_bytes + align_up(tiles * 8, 256));
-    j.bytes = j.zero_bytes + align_up(tiles * 8, 256) + align_up((tiles + 1) * 2 * 4, 256);
+    j.part = (u32 *)(base + j.zero_bytes + off_bytes);
+    j.bytes = j.zero_bytes + off_bytes + align_up((tiles + 1) * 2 * 4, 256);
     return j;
 }
 

@@ -151,7 +151,7 @@ __device__ __forceinline__ u64 lookback_warp(u64 *status, u32 tile, u64 aggregat
 #define SCAN1_THREADS 1024
 #define SCAN1_STAGE 8192
 __device__ __forceinline__ u64 scan1_counts(const u32 *__restrict__ counts, u32 num_tiles, u64 *offsets, u32 *s_stage /*[SCAN1_STAGE]*/,
-                                            u64 *s_w /*[32]*/)
+                                            u64 *s_w /*[32]*/, u64 base = 0 /*added to every offset*/)
 {
     const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
     const bool staged = num_tiles <= SCAN1_STAGE;
@@ -180,7 +180,7 @@ __device__ __forceinline__ u64 scan1_counts(const u32 *__restrict__ counts, u32 
     }
     if (lane == 31) s_w[w] = inc;
     __syncthreads();
-    u64 run = inc - sum, total = 0;
+    u64 run = base + inc - sum, total = 0;
 #pragma unroll
     for (u32 ww = 0; ww < SCAN1_THREADS / 32; ww++) {
         const u64 x = s_w[ww];
@@ -190,6 +190,54 @@ __device__ __forceinline__ u64 scan1_counts(const u32 *__restrict__ counts, u32 
     if (staged) for (u32 i = lo; i < hi; i++) { offsets[i] = run; run += s_stage[i]; }
     else for (u32 i = lo; i < hi; i++) { offsets[i] = run; run += counts[i]; }
     return total;
+}
+
+// ---- the same scan over many CTAs, for tables with more tiles than one CTA stages at once (ncu at the 500M-row config:
+// the one-CTA scan of 488 K tile counts took 610 us, 12 % of the step, walking its chunks straight from global memory).
+// Two launches of ceil(num_tiles / chunk) CTAs, chunk <= SCAN1_STAGE: block b first sums its chunk into blocksum[b];
+// then every block adds up the sums of the blocks before it itself (a few hundred words at most, no block waits for
+// another one) and scans its chunk out of shared memory.  scan_large_apply returns the running total through the
+// block's chunk to every thread: the grand total on the last block.
+__device__ __forceinline__ void scan_large_blocksum(const u32 *__restrict__ counts, u32 num_tiles, u32 chunk, u32 b, u64 *blocksum,
+                                                    u64 *s_w /*[32]*/)
+{
+    const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+    const u64 lo64 = (u64)b * chunk;
+    const u32 lo = lo64 < (u64)num_tiles ? (u32)lo64 : num_tiles;
+    const u32 n = num_tiles - lo < chunk ? num_tiles - lo : chunk;
+    u64 sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN1_STAGE / SCAN1_THREADS; k++) {
+        const u32 i = k * SCAN1_THREADS + tid;
+        if (i < n) sum += counts[lo + i];
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) s_w[w] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        u64 t = 0;
+#pragma unroll
+        for (u32 ww = 0; ww < SCAN1_THREADS / 32; ww++) t += s_w[ww];
+        blocksum[b] = t;
+    }
+}
+__device__ __forceinline__ u64 scan_large_apply(const u32 *__restrict__ counts, u32 num_tiles, u32 chunk, u32 b, u64 *offsets,
+                                                const u64 *__restrict__ blocksum, u32 *s_stage /*[SCAN1_STAGE]*/, u64 *s_w /*[32]*/)
+{
+    const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+    u64 part = 0;
+    for (u32 i = tid; i < b; i += SCAN1_THREADS) part += blocksum[i];
+    part = warp_sum(part);
+    if (lane == 0) s_w[w] = part;
+    __syncthreads();
+    u64 base = 0;
+#pragma unroll
+    for (u32 ww = 0; ww < SCAN1_THREADS / 32; ww++) base += s_w[ww];
+    __syncthreads();                                   // scan1_counts reuses s_w
+    const u64 lo64 = (u64)b * chunk;
+    const u32 lo = lo64 < (u64)num_tiles ? (u32)lo64 : num_tiles;
+    const u32 n = num_tiles - lo < chunk ? num_tiles - lo : chunk;
+    return base + scan1_counts(counts + lo, n, offsets + lo, s_stage, s_w, base);
 }
 
 // ---- semi-join key bitmaps (smj_select.cu): bit bloom_hash(key) of a table's bitmap is set iff some surviving row of

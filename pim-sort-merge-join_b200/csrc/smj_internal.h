@@ -185,6 +185,9 @@ size_t smj_join_num_tiles(u64 total);
 // caller), d_tile_off tiles u64, d_matches tiles * smj_join_tile_size() entries (tile t's matches start at t * tile size).
 // zip mode: *d_count = number of matches (written by the scan); many mode: *d_count += total pair count (count only).
 size_t smj_join_tile_size(void);
+// d_tile_off needs smj_join_scan_blocks(tiles) more u64 words behind its `tiles` entries (block sums of the many-CTA scan)
+size_t smj_join_scan_blocks(size_t tiles);
+u32 smj_join_scan_chunk(void);
 // d_dense (zip mode, may be null): the matches compacted in result order, min(m1_max, m2_max) entries of capacity.
 int smj_launch_join_match(SmjCtx *c, const u64 *d_l, const u64 *d_r, const u64 *d_counts, u32 m1_max, u32 m2_max, int mode,
                           u32 *d_part, u32 *d_tile_count, u64 *d_tile_off, uint2 *d_matches, uint2 *d_dense, u64 *d_count);

@@ -18,6 +18,7 @@
 // columns, then right columns except key2: cpu_app.c:240-251) with coalesced stores.
 #include "smj_internal.h"
 #include "smj_dev.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -79,7 +80,14 @@ join_partition_kernel(const u64 *__restrict__ L, const u64 *__restrict__ R, cons
             u32 rs = a;
             if (a > 0 && a < m1) {
                 const u32 k = pair_key(L[a]);
-                if (pair_key(L[a - 1]) == k) rs = lower_bound_key(L, 0, a, k);
+                if (pair_key(L[a - 1]) == k) {
+                    // gallop backwards to bracket the start of the run: a plain lower bound over [0, a) costs ~28 dependent
+                    // loads whatever the run length (ncu at 200M x 200M with ~10 rows per key: 652 us for this kernel)
+                    u32 off = 2;
+                    while (off <= a && pair_key(L[a - off]) == k) off <<= 1;
+                    const u32 lo = off <= a ? a - off + 1 : 0u;    // L[lo - 1] < k (or lo == 0); L[a - off / 2] == k
+                    rs = lower_bound_key(L, lo, a - (off >> 1), k);
+                }
             }
             runstart[t] = rs;
         }
@@ -277,6 +285,35 @@ join_scan_kernel(const u32 *__restrict__ tile_count, u32 num_tiles, u64 *offsets
     if (used < num_tiles) num_tiles = used;
     const u64 t = scan1_counts(tile_count, num_tiles, offsets, s_stage, s_w);
     if (threadIdx.x == 0) *total = t;
+}
+
+// The same over many CTAs (more tiles than one CTA stages at once: scan_large_* in smj_dev.cuh); blocksum: one u64 per CTA.
+__global__ void __launch_bounds__(JS_THREADS)
+join_blocksum_kernel(const u32 *__restrict__ tile_count, u32 num_tiles, u32 chunk, u64 *blocksum, const u64 *__restrict__ counts,
+                     u32 m1_max, u32 m2_max)
+{
+    __shared__ u64 s_w[JS_THREADS / 32];
+    PDL_ENTER();
+    u32 m1, m2;
+    load_counts(counts, m1_max, m2_max, m1, m2);
+    const u32 used = (m1 == 0 || m2 == 0) ? 0u : (u32)(((u64)m1 + m2 + JN_TILE - 1) / JN_TILE);
+    if (used < num_tiles) num_tiles = used;
+    scan_large_blocksum(tile_count, num_tiles, chunk, blockIdx.x, blocksum, s_w);
+}
+
+__global__ void __launch_bounds__(JS_THREADS)
+join_apply_kernel(const u32 *__restrict__ tile_count, u32 num_tiles, u32 chunk, u64 *offsets, const u64 *__restrict__ blocksum, u64 *total,
+                  const u64 *__restrict__ counts, u32 m1_max, u32 m2_max)
+{
+    __shared__ u32 s_stage[SCAN1_STAGE];
+    __shared__ u64 s_w[JS_THREADS / 32];
+    PDL_ENTER();
+    u32 m1, m2;
+    load_counts(counts, m1_max, m2_max, m1, m2);
+    const u32 used = (m1 == 0 || m2 == 0) ? 0u : (u32)(((u64)m1 + m2 + JN_TILE - 1) / JN_TILE);
+    if (used < num_tiles) num_tiles = used;
+    const u64 t = scan_large_apply(tile_count, num_tiles, chunk, blockIdx.x, offsets, blocksum, s_stage, s_w);
+    if (blockIdx.x + 1 == gridDim.x && threadIdx.x == 0) *total = t;   // the last block's running total is the grand total
 }
 
 // dense[offsets[t] + i] = slots[t * JN_TILE + i], i < tile_count[t]: the matches in result order, contiguous.
@@ -500,6 +537,18 @@ int smj_launch_join_many_expand(SmjCtx *c, const u64 *d_l, const u64 *d_r, const
 }
 
 size_t smj_join_num_tiles(u64 total) { return (size_t)((total + JN_TILE - 1) / JN_TILE); }
+// tile counts one CTA of the many-CTA scan takes (SMJ_SCAN_CHUNK lets the tests force that path at small sizes)
+u32 smj_join_scan_chunk(void)
+{
+    static const u32 chunk = [] {
+        const char *e = getenv("SMJ_SCAN_CHUNK");
+        const long v = e ? atol(e) : 0;
+        return (u32)((v >= 32 && v <= SCAN1_STAGE) ? v : SCAN1_STAGE);
+    }();
+    return chunk;
+}
+// u64 words the scan wants behind the `tiles` tile offsets (one block sum per CTA, whatever the chunk)
+size_t smj_join_scan_blocks(size_t tiles) { return tiles / 32 + 2; }
 size_t smj_join_tile_size(void) { return JN_TILE; }
 
 static int sm_count(SmjCtx *c)
@@ -529,7 +578,15 @@ int smj_launch_join_match(SmjCtx *c, const u64 *d_l, const u64 *d_r, const u64 *
         smj_launch(c, join_match_kernel<SMJ_JOIN_ZIP>, grid, JN_THREADS, 0, d_l, d_r, d_counts, m1_max, m2_max, d_part, d_runstart,
                    d_matches, d_tile_count, d_count, (uint2 *)nullptr);
         KERNEL_CHECK(c);
-        smj_launch(c, join_scan_kernel, 1, JS_THREADS, 0, d_tile_count, tiles, d_tile_off, d_count, d_counts, m1_max, m2_max);
+        const u32 chunk = smj_join_scan_chunk();
+        if (tiles > chunk) {   // d_tile_off has smj_join_scan_blocks(tiles) spare words behind its `tiles` entries
+            const u32 nb = (tiles + chunk - 1) / chunk;
+            smj_launch(c, join_blocksum_kernel, nb, JS_THREADS, 0, d_tile_count, tiles, chunk, d_tile_off + tiles, d_counts, m1_max, m2_max);
+            KERNEL_CHECK(c);
+            smj_launch(c, join_apply_kernel, nb, JS_THREADS, 0, d_tile_count, tiles, chunk, d_tile_off, d_tile_off + tiles, d_count, d_counts,
+                       m1_max, m2_max);
+        } else
+            smj_launch(c, join_scan_kernel, 1, JS_THREADS, 0, d_tile_count, tiles, d_tile_off, d_count, d_counts, m1_max, m2_max);
         if (d_dense) {
             KERNEL_CHECK(c);
             const u32 cgrid = (tiles + 7) / 8 < (u32)(sms * 8) ? (tiles + 7) / 8 : (u32)(sms * 8);

@@ -382,6 +382,41 @@ __global__ void __launch_bounds__(TS_THREADS) plan_scan_kernel(const PlanScanArg
     }
 }
 
+// The same over many CTAs (tables with more tiles than one CTA stages at once: scan_large_* in smj_dev.cuh).  Blocks
+// [0, nb0) belong to table 1, the others to table 2; a table without tiles has no block and keeps the zeroed plan and total.
+struct PlanScanLargeArgs { PlanScanJob t[2]; u64 *blocksum[2]; u32 nb0, chunk; int full_passes; };
+
+__global__ void __launch_bounds__(TS_THREADS) plan_blocksum_kernel(const PlanScanLargeArgs A)
+{
+    __shared__ u64 s_w[TS_THREADS / 32];
+    PDL_ENTER();
+    const bool tb = blockIdx.x >= A.nb0;
+    const PlanScanJob J = tb ? A.t[1] : A.t[0];
+    scan_large_blocksum(J.counts, J.num_tiles, A.chunk, tb ? blockIdx.x - A.nb0 : blockIdx.x, tb ? A.blocksum[1] : A.blocksum[0], s_w);
+}
+
+__global__ void __launch_bounds__(TS_THREADS) plan_apply_kernel(const PlanScanLargeArgs A)
+{
+    __shared__ u32 s_stage[SCAN1_STAGE];
+    __shared__ u64 s_w[TS_THREADS / 32];
+    PDL_ENTER();
+    const bool tb = blockIdx.x >= A.nb0;
+    const PlanScanJob J = tb ? A.t[1] : A.t[0];
+    const u32 b = tb ? blockIdx.x - A.nb0 : blockIdx.x;
+    const u32 nb = (J.num_tiles + A.chunk - 1) / A.chunk;
+    const u64 total = scan_large_apply(J.counts, J.num_tiles, A.chunk, b, J.offsets, tb ? A.blocksum[1] : A.blocksum[0], s_stage, s_w);
+    if (b + 1 == nb && threadIdx.x == 0) {   // the table's last block holds the grand total: survivor count and sort plan
+        *J.total = total;
+        const u32 kmax = J.plan->kmax;
+        u32 kmin = ~J.plan->kmin_inv, npass = 0;
+        if (total >= 2 && kmax > kmin) npass = (32u - (u32)__clz(kmax - kmin) + 7u) / 8u;
+        if (total == 0) kmin = 0;
+        if (A.full_passes) { kmin = 0; npass = SMJ_KEY_PASSES; }
+        J.plan->kmin = kmin;
+        J.plan->npass = npass;
+    }
+}
+
 // The compaction copy of both tables in one launch (one warp per tile, table 1's tiles first), fused with the digit
 // histograms of (key - kmin) for the passes the plan runs.  The dense pairs land in buf[npass & 1]: pass p reads
 // buf[(npass - p) & 1] and writes the other one, so the sorted pairs always end in buf[0].
@@ -666,8 +701,32 @@ int smj_launch_select_plan2(SmjCtx *c, const SmjSelectJob job[2])
         smj_launch(c, bloom_filter_kernel, fgrid, 256, 0, FA);
         KERNEL_CHECK(c);
     }
-    smj_launch(c, plan_scan_kernel, 2, TS_THREADS, 0, SA);
-    KERNEL_CHECK(c);
+    // tile offsets, survivor counts and sort plans: one CTA per table, or many when a table has more tiles than one CTA stages
+    static const u32 scan_chunk = [] {
+        const char *e = getenv("SMJ_SCAN_CHUNK");   // tests force the many-CTA scan at small sizes with a small chunk
+        const long v = e ? atol(e) : 0;
+        return (u32)((v >= 32 && v <= SCAN1_STAGE) ? v : SCAN1_STAGE);
+    }();
+    if (tiles_of[0] > scan_chunk || tiles_of[1] > scan_chunk) {
+        PlanScanLargeArgs LA = {};
+        LA.chunk = scan_chunk;
+        LA.full_passes = full_passes;
+        u32 nb[2];
+        for (int t = 0; t < 2; t++) {
+            LA.t[t] = SA.t[t];
+            nb[t] = (tiles_of[t] + scan_chunk - 1) / scan_chunk;
+            // spare words of the table's status region, behind [offsets u64 x tiles][counts u32 x tiles] (smj_select_num_tiles)
+            LA.blocksum[t] = job[t].d_status + tiles_of[t] + (tiles_of[t] + 1) / 2;
+        }
+        LA.nb0 = nb[0];
+        smj_launch(c, plan_blocksum_kernel, nb[0] + nb[1], TS_THREADS, 0, LA);
+        KERNEL_CHECK(c);
+        smj_launch(c, plan_apply_kernel, nb[0] + nb[1], TS_THREADS, 0, LA);
+        KERNEL_CHECK(c);
+    } else {
+        smj_launch(c, plan_scan_kernel, 2, TS_THREADS, 0, SA);
+        KERNEL_CHECK(c);
+    }
     if (all_tiles) {
         const u32 cgrid = (all_tiles + 7) / 8 < (u32)(sms * 8) ? (all_tiles + 7) / 8 : (u32)(sms * 8);
         smj_launch(c, plan_compact_kernel, cgrid, 256, 0, CA);
