@@ -759,6 +759,8 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
     (void)bloom_ws;
     smj_table_t dev_out = {nullptr, 0, c_out, 1};
     SMJ_TRY(smj_alloc_out(c, &dev_out, j_max, c_out));   // upper bound; rows is set once the count is known
+    // every early return below gives the buffer back; handing it to the caller (or freeing it) disarms the guard
+    struct OutGuard { smj_table_t *t; ~OutGuard() { if (t && t->data) smj_table_free(t); } } out_guard = {&dev_out};
     CUDA_TRY(cudaEventRecord(c->ev[E_H2D], c->stream));
 
     // ---- the device pipeline: ~23 launches with no host wait in between.  A call that repeats the previous call's
@@ -842,7 +844,7 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
             c->graph_launches = c->launches - l0;
             c->launches = l0;   // counted again when the graph is launched below
         }
-        if (rc != SMJ_OK) { cudaGetLastError(); smj_table_free(&dev_out); return rc; }
+        if (rc != SMJ_OK) { cudaGetLastError(); return rc; }
     }
     if (replay || capture) {
         CUDA_TRY(cudaGraphLaunch(c->graph_exec, c->stream));
@@ -854,10 +856,7 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
     // ---- the one host wait: counts and the device-side consistency flag
     ScratchHeader *hh = (ScratchHeader *)c->h_pinned;
     CUDA_TRY(cudaMemcpyAsync(hh, h, sizeof(ScratchHeader), cudaMemcpyDeviceToHost, c->stream));
-    {
-        int r = smj_check_device_flag(c);
-        if (r != SMJ_OK) { smj_table_free(&dev_out); return r; }
-    }
+    SMJ_TRY(smj_check_device_flag(c));
     // m: pairs that were sorted and joined; m_sel: rows that passed the predicate (more, when the semi-join filter ran)
     const int64_t m[2] = {(int64_t)hh->count[0], (int64_t)hh->count[1]};
     const int64_t m_sel[2] = {c->run_planned ? (int64_t)hh->sel_count[0] : m[0], c->run_planned ? (int64_t)hh->sel_count[1] : m[1]};
@@ -868,6 +867,7 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
     // ---- GPU -> CPU (app.c timer 2)
     if (out->on_device) {
         *out = dev_out;
+        out_guard.t = nullptr;   // the caller owns the buffer now
     } else {
         SMJ_TRY(smj_alloc_out(c, out, j, c_out));
         if (j) CUDA_TRY(cudaMemcpyAsync(out->data, dev_out.data, (size_t)j * c_out * 4, cudaMemcpyDeviceToHost, c->stream));
