@@ -80,7 +80,8 @@ typedef struct {
     double  bytes_nvlink;                 /* bytes this process sent over NVLink in the exchange */
     int64_t kernel_launches;              /* kernels this call launched */
     /* average device time of the radix-sort scatter pass (the dominant kernel) and its launch count */
-    double  sort_pass_ms_avg; int32_t sort_passes; int32_t reserved;
+    double  sort_pass_ms_avg; int32_t sort_passes;
+    int32_t graph_replayed;               /* 1: the device pipeline of this call was one CUDA-graph launch (a repeat of the previous call) */
     /* algorithmic bytes (16 B per pair the launch sorts) of an average executed pass launch: the sort runs
      * ceil(bits(max key - min key) / 8) passes per table, decided on the device */
     double  sort_pass_bytes_avg;

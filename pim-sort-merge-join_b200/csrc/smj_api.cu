@@ -100,13 +100,22 @@ static int ctx_create(int device, SmjCtx **out)
     for (auto &e : c->pass_ev) CUDA_TRY(cudaEventCreate(&e));
     // The payload gathers read one 16..32-byte row per random address: ask L2 to fetch single 32-byte sectors
     // instead of 64/128-byte lines (a hint; ncu showed 3.4x DRAM read amplification on join_materialize without it).
-    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+    // It is a device-wide limit: the host application's value is put back at shutdown (SMJ_L2_FETCH=0 leaves it alone).
+    static const bool l2_fetch = !(getenv("SMJ_L2_FETCH") && atoi(getenv("SMJ_L2_FETCH")) == 0);
+    if (l2_fetch && cudaDeviceGetLimit(&c->l2_fetch_saved, cudaLimitMaxL2FetchGranularity) == cudaSuccess) {
+        c->l2_fetch_set = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32) == cudaSuccess;
+    }
     cudaGetLastError();
-    // keep freed output buffers cached in the stream-ordered pool
-    cudaMemPool_t pool;
-    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+    // output buffers come from a PRIVATE stream-ordered pool that keeps freed memory cached (the device's default pool,
+    // which the host application may share, is left as it is)
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    CUDA_TRY(cudaMemPoolCreate(&c->pool, &props));
     uint64_t thr = UINT64_MAX;
-    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    CUDA_TRY(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr));
     *out = c;
     return SMJ_OK;
 }
@@ -120,6 +129,8 @@ static void ctx_destroy(SmjCtx *c)
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->pass_ev) if (e) cudaEventDestroy(e);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    if (c->pool) cudaMemPoolDestroy(c->pool);
+    if (c->l2_fetch_set) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, c->l2_fetch_saved);
     if (c->d_out_ptr) cudaFree(c->d_out_ptr);
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -318,9 +329,14 @@ static void pinned_put(void *p)
         if (g_pinned[i].p == p) { g_pinned[i].used = false; return; }
     cudaFreeHost(p);
 }
+// frees the pooled buffers that are not handed out; an output table a caller still holds leaves the pool (its
+// smj_table_free then releases it with cudaFreeHost) instead of dangling after a shutdown or re-init
 static void pinned_clear(void)
 {
-    for (int i = 0; i < 16; i++) { if (g_pinned[i].p) cudaFreeHost(g_pinned[i].p); g_pinned[i] = {nullptr, 0, false}; }
+    for (int i = 0; i < 16; i++) {
+        if (g_pinned[i].p && !g_pinned[i].used) cudaFreeHost(g_pinned[i].p);
+        g_pinned[i] = {nullptr, 0, false};
+    }
 }
 
 // Output allocation: device memory from the stream-ordered pool, or (recycled) pinned host memory.
@@ -330,7 +346,7 @@ int smj_alloc_out(SmjCtx *c, smj_table_t *out, int64_t rows, int cols)
     out->rows = rows; out->cols = cols; out->data = nullptr;
     const size_t bytes = (size_t)rows * cols * sizeof(int32_t);
     if (bytes == 0) return SMJ_OK;
-    if (on_device) CUDA_TRY(cudaMallocAsync((void **)&out->data, bytes, c->stream));
+    if (on_device) CUDA_TRY(cudaMallocFromPoolAsync((void **)&out->data, bytes, c->pool, c->stream));
     else SMJ_TRY(pinned_get((void **)&out->data, bytes));
     return SMJ_OK;
 }
@@ -674,6 +690,8 @@ static float ev_ms(cudaEvent_t a, cudaEvent_t b)
     return ms;
 }
 
+enum { E_START, E_H2D, E_SELECT, E_SORT, E_JOIN, E_D2H };   // c->ev[] of the single-GPU pipeline
+
 // Device pipeline of one GPU, no host round trip between the stages: the survivor counts, the radix
 // histograms and the match count stay in device memory, every kernel sizes its work from them, and buffers are
 // sized by their host-known upper bounds (input rows).  The host waits once, at the end.
@@ -695,7 +713,6 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
     if (cfg->join_mode != SMJ_JOIN_ZIP && cfg->join_mode != SMJ_JOIN_MANY) return smj_set_error(SMJ_EINVAL, "smj_run: bad join_mode %d", cfg->join_mode);
     const int64_t launches0 = c->launches;
     c->pass_count = 0;
-    enum { E_START, E_H2D, E_SELECT, E_SORT, E_JOIN, E_D2H };
     if (cfg->join_mode == SMJ_JOIN_MANY) {
         // Extension (not the reference's semantics): every pair of equal keys.  The result size is data dependent and
         // unbounded by the inputs, so this path waits for the host between the stages (stage entry points underneath).
@@ -726,42 +743,105 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
         return SMJ_OK;
     }
 
+    SmjRun R;
+    SMJ_TRY(smj_run_prepare(c, cfg, t1, t2, nullptr, &R));
+    int rc = smj_run_enqueue(c, &R);
+    if (rc != SMJ_OK) { smj_run_abandon(c, &R); return rc; }
+    return smj_run_finish(c, &R, out, stats);
+}
+
+// The three phases of the device pipeline of one GPU.  Split so that a process driving several GPUs (smj_dist.cu) can do
+// every rank's allocations first, then enqueue every rank's kernels, then wait for each rank -- no allocation and no
+// host wait happens while another rank's kernels spin on this rank's flags.
+//   prepare: validation, workspace slots, the (upper-bound sized) output buffer, the H2D copies of host tables
+//   enqueue: ~23 launches with no host wait in between (or one graph launch)
+//   finish : the one host wait: counts, consistency flag, D2H, stats
+// d_rows (may be null, or hold nulls): device-resident row counts of the input tables; the descriptors' rows are then
+// upper bounds (the tables are receive buffers whose fill the host never learns: smj_dist.cu).
+
+int smj_run_prepare(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, const u64 *const *d_rows, SmjRun *R)
+{
+    CUDA_TRY(cudaSetDevice(c->device));
+    *R = SmjRun();
+    R->cfg = *cfg;
+    R->tb[0] = *t1; R->tb[1] = *t2;
+    if (d_rows) { R->d_rows[0] = d_rows[0]; R->d_rows[1] = d_rows[1]; }
+    const int sel_col[2] = {cfg->select_col1, cfg->select_col2};
+    const int key[2] = {cfg->join_key1, cfg->join_key2};
+    for (int t = 0; t < 2; t++) {
+        if (sel_col[t] < 0 || sel_col[t] >= R->tb[t].cols) return smj_set_error(SMJ_EINVAL, "SELECT_COL%d=%d out of range", t + 1, sel_col[t]);
+        if (key[t] < 0 || key[t] >= R->tb[t].cols) return smj_set_error(SMJ_EINVAL, "JOIN_KEY%d=%d out of range", t + 1, key[t]);
+        if (R->tb[t].rows > SMJ_MAX_SORT_ROWS)
+            return smj_set_error(SMJ_ETOOBIG, "table %d has %lld rows; this build handles at most 2^30 - 1 per table per GPU", t + 1,
+                                 (long long)R->tb[t].rows);
+    }
+    if (cfg->join_mode != SMJ_JOIN_ZIP) return smj_set_error(SMJ_EINVAL, "smj_run_prepare: zip mode only");
+    R->launches0 = c->launches;
+    c->pass_count = 0;
     // ---- CPU -> GPU (app.c timer 0)
     CUDA_TRY(cudaEventRecord(c->ev[E_START], c->stream));
-    const int32_t *d_t[2];
-    SMJ_TRY(smj_stage_in(c, t1, WS_T1, &d_t[0]));
-    SMJ_TRY(smj_stage_in(c, t2, WS_T2, &d_t[1]));
+    SMJ_TRY(smj_stage_in(c, t1, WS_T1, &R->d_t[0]));
+    SMJ_TRY(smj_stage_in(c, t2, WS_T2, &R->d_t[1]));
     const int64_t n[2] = {t1->rows, t2->rows};
     const int cc[2] = {t1->cols, t2->cols};
-    const int c_out = cc[0] + cc[1] - 1;
+    R->c_out = cc[0] + cc[1] - 1;
     // one zeroed arena: [header][select status x2][radix scratch x2][join header 64 B + join status]; then join partitions
-    const size_t stiles[2] = {smj_select_num_tiles(n[0]), smj_select_num_tiles(n[1])};
-    const size_t rb[2] = {align_up(smj_radix_scratch_bytes((u32)n[0]), 256), align_up(smj_radix_scratch_bytes((u32)n[1]), 256)};
-    const size_t jt = (n[0] == 0 || n[1] == 0) ? 0 : smj_join_num_tiles((u64)n[0] + n[1]);
-    const size_t off_sel = align_up(sizeof(ScratchHeader), 256);
-    const size_t off_radix = align_up(off_sel + (stiles[0] + stiles[1]) * 8, 256);
-    const size_t off_join = off_radix + rb[0] + rb[1];
-    const JoinScratch jsz = join_scratch(nullptr, jt);
-    const size_t zero_bytes = off_join + jsz.zero_bytes;
-    const size_t sbytes = off_join + jsz.bytes;
+    R->stiles[0] = smj_select_num_tiles(n[0]); R->stiles[1] = smj_select_num_tiles(n[1]);
+    R->rb[0] = align_up(smj_radix_scratch_bytes((u32)n[0]), 256); R->rb[1] = align_up(smj_radix_scratch_bytes((u32)n[1]), 256);
+    R->jt = (n[0] == 0 || n[1] == 0) ? 0 : smj_join_num_tiles((u64)n[0] + n[1]);
+    R->off_sel = align_up(sizeof(ScratchHeader), 256);
+    R->off_radix = align_up(R->off_sel + (R->stiles[0] + R->stiles[1]) * 8, 256);
+    R->off_join = R->off_radix + R->rb[0] + R->rb[1];
+    const JoinScratch jsz = join_scratch(nullptr, R->jt);
+    R->zero_bytes = R->off_join + jsz.zero_bytes;
+    const size_t sbytes = R->off_join + jsz.bytes;
     WS_TRY(scr, char *, c, WS_SCRATCH, sbytes);
     WS_TRY(ping0, u64 *, c, WS_PAIRS_A1, (size_t)n[0] * 8);
     WS_TRY(ping1, u64 *, c, WS_PAIRS_A2, (size_t)n[1] * 8);
     WS_TRY(pong0, u64 *, c, WS_PAIRS_B1, (size_t)n[0] * 8);
     WS_TRY(pong1, u64 *, c, WS_PAIRS_B2, (size_t)n[1] * 8);
-    u64 *ping[2] = {ping0, ping1}, *pong[2] = {pong0, pong1};
-    const int64_t j_max = n[0] < n[1] ? n[0] : n[1];
+    R->scr = scr;
+    R->ping[0] = ping0; R->ping[1] = ping1; R->pong[0] = pong0; R->pong[1] = pong1;
+    R->j_max = n[0] < n[1] ? n[0] : n[1];
     // the join's per-tile match slots; before the sort the same bytes hold the select kernels' per-tile pair slots
-    const size_t mm_bytes = jt * smj_join_tile_size() * 8 > (size_t)(n[0] + n[1]) * 8 ? jt * smj_join_tile_size() * 8 : (size_t)(n[0] + n[1]) * 8;
+    const size_t mm_bytes = R->jt * smj_join_tile_size() * 8 > (size_t)(n[0] + n[1]) * 8 ? R->jt * smj_join_tile_size() * 8 : (size_t)(n[0] + n[1]) * 8;
     WS_TRY(mm, uint2 *, c, WS_MATCH, mm_bytes);
-    WS_TRY(md, uint2 *, c, WS_MATCH_DENSE, (size_t)j_max * 8);
+    WS_TRY(md, uint2 *, c, WS_MATCH_DENSE, (size_t)R->j_max * 8);
+    R->mm = mm; R->md = md;
     WS_TRY(bloom_ws, char *, c, WS_BLOOM, smj_bloom_bytes(n[0], n[1]));   // sized here: no allocation inside a graph capture
     (void)bloom_ws;
-    smj_table_t dev_out = {nullptr, 0, c_out, 1};
-    SMJ_TRY(smj_alloc_out(c, &dev_out, j_max, c_out));   // upper bound; rows is set once the count is known
-    // every early return below gives the buffer back; handing it to the caller (or freeing it) disarms the guard
-    struct OutGuard { smj_table_t *t; ~OutGuard() { if (t && t->data) smj_table_free(t); } } out_guard = {&dev_out};
+    R->dev_out = {nullptr, 0, R->c_out, 1};
+    SMJ_TRY(smj_alloc_out(c, &R->dev_out, R->j_max, R->c_out));   // upper bound; rows is set once the count is known
     CUDA_TRY(cudaEventRecord(c->ev[E_H2D], c->stream));
+    R->prepared = true;
+    return SMJ_OK;
+}
+
+// gives back what prepare took when the run cannot go on
+void smj_run_abandon(SmjCtx *c, SmjRun *R)
+{
+    (void)c;
+    if (R->prepared && R->dev_out.data) smj_table_free(&R->dev_out);
+    R->prepared = false;
+}
+
+int smj_run_enqueue(SmjCtx *c, SmjRun *R)
+{
+    CUDA_TRY(cudaSetDevice(c->device));
+    const smj_config_t *cfg = &R->cfg;
+    const int sel_col[2] = {cfg->select_col1, cfg->select_col2};
+    const int64_t sel_val[2] = {cfg->select_val1, cfg->select_val2};
+    const int key[2] = {cfg->join_key1, cfg->join_key2};
+    const int64_t n[2] = {R->tb[0].rows, R->tb[1].rows};
+    const int cc[2] = {R->tb[0].cols, R->tb[1].cols};
+    const int32_t *const *d_t = R->d_t;
+    u64 *const *ping = R->ping, *const *pong = R->pong;
+    char *scr = R->scr;
+    const size_t off_sel = R->off_sel, off_radix = R->off_radix, off_join = R->off_join, zero_bytes = R->zero_bytes;
+    const size_t *stiles = R->stiles, *rb = R->rb;
+    const size_t jt = R->jt;
+    uint2 *mm = R->mm, *md = R->md;
+    const int64_t j_max = R->j_max;
 
     // ---- the device pipeline: ~23 launches with no host wait in between.  A call that repeats the previous call's
     // tables, shapes and knobs replays it as ONE CUDA graph (the launch gaps are ~8 % of a 0.6 ms step); the output
@@ -769,7 +849,7 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
     ScratchHeader *h = (ScratchHeader *)scr;
     u64 key_now[16] = {(u64)(uintptr_t)d_t[0], (u64)(uintptr_t)d_t[1], (u64)n[0], (u64)n[1], (u64)cc[0], (u64)cc[1],
                        (u64)sel_col[0], (u64)sel_col[1], (u64)sel_val[0], (u64)sel_val[1], (u64)key[0], (u64)key[1], c->ws_gen,
-                       (u64)(uintptr_t)scr, 0, 0};
+                       (u64)(uintptr_t)scr, (u64)(uintptr_t)R->d_rows[0], (u64)(uintptr_t)R->d_rows[1]};
     static const bool graphs_on = !(getenv("SMJ_NO_GRAPH") && atoi(getenv("SMJ_NO_GRAPH")) != 0);
     if (memcmp(key_now, c->graph_key, sizeof key_now) != 0) {
         memcpy(c->graph_key, key_now, sizeof key_now);
@@ -779,8 +859,9 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
     c->graph_seen++;
     const bool replay = graphs_on && c->graph_exec != nullptr;
     const bool capture = graphs_on && !replay && c->graph_seen >= 2;   // the first call warms attributes and slots eagerly
+    R->replayed = replay || capture;
     int32_t **h_ptr = (int32_t **)((char *)c->h_pinned + c->h_pinned_bytes - 128);
-    *h_ptr = dev_out.data;
+    *h_ptr = R->dev_out.data;
     CUDA_TRY(cudaMemcpyAsync(c->d_out_ptr, h_ptr, sizeof(int32_t *), cudaMemcpyHostToDevice, c->stream));
     if (!replay) {
         const int64_t l0 = c->launches;
@@ -797,10 +878,13 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
                 SmjSelectJob job[2];
                 for (int t = 0; t < 2; t++)
                     job[t] = {d_t[t], n[t], cc[t], sel_col[t], sel_val[t], 0, key[t], {ping[t], pong[t]}, (u64 *)mm + (t ? n[0] : 0),
-                              (u64 *)(scr + off_sel + (t ? stiles[0] * 8 : 0)), h->hist[t], &h->count[t], &h->plan[t], &h->sel_count[t], &h->kept_count[t]};
+                              (u64 *)(scr + off_sel + (t ? stiles[0] * 8 : 0)), h->hist[t], &h->count[t], &h->plan[t], &h->sel_count[t], &h->kept_count[t],
+                              R->d_rows[t]};
                 rc = smj_launch_select_plan2(c, job);
                 if (rc == 1) { planned = false; rc = SMJ_OK; }   // a table the TMA path cannot take: histograms in the select kernel, four passes
             }
+            if (rc == SMJ_OK && !planned && (R->d_rows[0] || R->d_rows[1]))
+                rc = smj_set_error(SMJ_EINVAL, "device-resident row counts need the TMA select path (16-byte aligned tables of <= 32 columns)");
             for (int t = 0; t < 2 && rc == SMJ_OK && !planned; t++)
                 rc = smj_launch_select_pairs(c, d_t[t], n[t], cc[t], sel_col[t], sel_val[t], 0, key[t], 0, ping[t], pong[t],
                                              (u64 *)(scr + off_sel + (t ? stiles[0] * 8 : 0)), &h->counter[t], h->hist[t], &h->count[t]);
@@ -852,10 +936,26 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
         c->pass_count = c->stage_from_pass ? 1 : 0;   // the timed sort group (both tables, four launches) is a pair of event-record nodes of the graph
     }
     CUDA_TRY(cudaEventRecord(c->ev[E_JOIN], c->stream));
+    // counts and sort plans for the host, read after the one wait in smj_run_finish
+    ScratchHeader *hh = (ScratchHeader *)c->h_pinned;
+    CUDA_TRY(cudaMemcpyAsync(hh, h, sizeof(ScratchHeader), cudaMemcpyDeviceToHost, c->stream));
+    return SMJ_OK;
+}
+
+int smj_run_finish(SmjCtx *c, SmjRun *R, smj_table_t *out, smj_stats_t *stats)
+{
+    CUDA_TRY(cudaSetDevice(c->device));
+    // every early return below gives the buffer back; handing it to the caller (or freeing it) disarms the guard
+    struct OutGuard { smj_table_t *t; ~OutGuard() { if (t && t->data) smj_table_free(t); } } out_guard = {&R->dev_out};
+    R->prepared = false;
+    const smj_config_t *cfg = &R->cfg;
+    const int64_t n[2] = {R->tb[0].rows, R->tb[1].rows};
+    const int cc[2] = {R->tb[0].cols, R->tb[1].cols};
+    const int c_out = R->c_out;
+    smj_table_t &dev_out = R->dev_out;
 
     // ---- the one host wait: counts and the device-side consistency flag
     ScratchHeader *hh = (ScratchHeader *)c->h_pinned;
-    CUDA_TRY(cudaMemcpyAsync(hh, h, sizeof(ScratchHeader), cudaMemcpyDeviceToHost, c->stream));
     SMJ_TRY(smj_check_device_flag(c));
     // m: pairs that were sorted and joined; m_sel: rows that passed the predicate (more, when the semi-join filter ran)
     const int64_t m[2] = {(int64_t)hh->count[0], (int64_t)hh->count[1]};
@@ -899,7 +999,8 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
         for (int t = 0; t < 2; t++) { stats->rows_in[t] = n[t]; stats->rows_selected[t] = m_sel[t]; }
         stats->rows_joined = j;
         stats->bytes_model = bytes_model(n, cc, m_sel, j);
-        stats->kernel_launches = c->launches - launches0;
+        stats->kernel_launches = c->launches - R->launches0;
+        stats->graph_replayed = R->replayed ? 1 : 0;
         double sum = 0;
         if (!smj_stage_events()) c->pass_count = 0;
         for (int p = 0; p < c->pass_count; p++) sum += ev_ms(c->pass_ev[2 * p], c->pass_ev[2 * p + 1]);
@@ -919,6 +1020,7 @@ int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, co
 }
 
 int smj_run_multi(const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, smj_table_t *out, smj_stats_t *stats);
+int smj_run_multi_local(const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, smj_table_t *out, smj_stats_t *stats);
 bool smj_dist_active(void);
 
 extern "C" int smj_run(const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, smj_table_t *out,
@@ -930,6 +1032,7 @@ extern "C" int smj_run(const smj_config_t *cfg, const smj_table_t *t1, const smj
     SMJ_TRY(check_table(t1, "smj_run(t1)"));
     SMJ_TRY(check_table(t2, "smj_run(t2)"));
     if (!out) return smj_set_error(SMJ_EINVAL, "smj_run: null out");
-    if (smj_dist_active() || cfg->nr_gpus > 1) return smj_run_multi(cfg, t1, t2, out, stats);
+    if (smj_dist_active()) return smj_run_multi(cfg, t1, t2, out, stats);         // one process per GPU (smj_init_dist)
+    if (cfg->nr_gpus > 1) return smj_run_multi_local(cfg, t1, t2, out, stats);     // this process drives nr_gpus devices
     return smj_run_single(g_ctx[0], cfg, t1, t2, out, stats);
 }

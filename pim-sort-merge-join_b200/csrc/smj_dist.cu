@@ -1,27 +1,29 @@
-// smj_dist.cu -- key-range partitioned sort-merge-join across the GPUs of one box, one process per GPU.
+// smj_dist.cu -- key-range partitioned sort-merge-join across the GPUs of one box.
 //
 // Replaces the reference's host-mediated data movement between stages -- the per-DPU dpu_push_xfer gathers and
 // scatters (sort-merge-join/app.c:222-288), the log-depth merge tournament that round-trips whole tables through
 // host memory (app.c:413-547) and the host-side key-range split for the join (app.c:585-633) -- with ONE exchange.
 //
-// Default path, smj_run_multi (partition first):
-//   1. splitters: every rank contributes regular row samples of both tables with the predicate applied
-//      (ncclAllGather); every rank sorts the same gathered samples on the device and so derives the same G-1 key
-//      splitters (splitters_kernel, the device twin of smj_plan_splitters) -- no host round trip;
+// Default path (the "fabric" path; one process per GPU under torchrun, or all GPUs from one process for the C driver):
+//   1. splitters: every rank stores regular row samples of both tables (predicate applied) into every peer's mailbox
+//      and sorts the same G x 2S samples itself -- ONE kernel, no collective call, identical splitters everywhere;
 //   2. select fused with key-range partitioning of the ROWS (smj_partition.cu): survivors grouped by destination rank
-//      inside their tile's slot, original order kept inside each bucket;
-//   3. the per-bucket totals (and every rank's receive capacity) are all-gathered: the G x G row-count matrix, the one
-//      host wait of this path (buffer sizing, smj_plan_exchange);
-//   4. exchange fused into the compaction kernel: each (tile, bucket) segment is stored straight into the destination
-//      rank's receive buffer through a CUDA-IPC mapping (NVLink stores from the SMs); SMJ_DIST_EXCHANGE=nccl uses a
-//      send buffer and one grouped ncclSend/ncclRecv all-to-all instead;
-//   5. the single-GPU pipeline (smj_run_single, select disabled) sorts and joins what arrived: runs sit in source-rank
-//      order with original order inside each, so the stable sort reproduces the reference's order;
+//      inside their tile's slot, original order kept inside each bucket; a many-CTA scan gives every segment its offset;
+//   3. counts: every rank stores its G bucket totals into every peer's count matrix and derives, from the same matrix,
+//      where its buckets start in the owners' receive buffers -- on the device, never waited for on the host;
+//   4. exchange fused into the compaction kernel: every tile's survivors are stored straight into the destination
+//      ranks' receive buffers (peer mappings: NVLink stores from the SMs), then an arrival flag;
+//   5. the single-GPU pipeline (smj_run_*, select disabled) sorts and joins what arrived, sized from the device-resident
+//      row count: runs sit in source-rank order with original order inside each, so the stable sort reproduces the
+//      reference's order;
 //   6. the result shards, concatenated in rank order, are the single-GPU result (splitters are key values, so all
 //      rows of one key meet on one rank and the zip pairing of equal keys is local).
+// Receive buffers are sized once for an upper bound; a step whose shares do not fit stores nothing, says so in a verdict
+// that every rank computes from the same matrix, and is re-run after a collective re-sizing.
 //
-// SMJ_DIST_MODE=merge, smj_run_multi_sorted (sort first; also the fallback for tables the partition kernel cannot
-// take): local select + sort + payload gather, splitters from samples of the sorted keys (host), bucket bounds by
+// SMJ_DIST_EXCHANGE=nccl: the same partitioning with NCCL collectives, a host wait for the counts and one grouped
+// ncclSend/ncclRecv all-to-all.  SMJ_DIST_MODE=merge, smj_run_multi_sorted (sort first; also what tables of more than 32
+// columns take): local select + sort + payload gather, splitters from samples of the sorted keys (host), bucket bounds by
 // binary search, one grouped ncclSend/ncclRecv of the contiguous sorted slices, a merge-path merge tree over the G
 // received runs per table (ties: lower source rank first = original row order), local join.
 //
@@ -87,12 +89,6 @@ int nccl_fail(ncclResult_t r, const char *what)
 }
 #define NCCL_TRY(x) do { ncclResult_t r_ = (x); if (r_ != 0) return nccl_fail(r_, #x); } while (0)
 
-struct DistState {
-    bool active = false;
-    int rank = 0, world = 1;
-    ncclComm_t comm = nullptr;
-} g_dist;
-
 constexpr int DIST_SAMPLES = 256;   // regular samples per table per rank
 
 // samples[i] = key of the pair at position floor((2i+1) * m / (2S)) of the sorted pairs (0xffffffff when m == 0)
@@ -156,14 +152,583 @@ extern "C" int smj_plan_exchange(const int64_t *counts, int world, int me, int64
     return SMJ_OK;
 }
 
+// ------------------------------------------------------------------ the peer fabric
+// Every rank owns a WINDOW in device memory that every other rank maps (CUDA IPC between processes, peer access inside
+// one process): flag mailboxes, the sample mailbox and the G x G count matrices.  A rank "all-gathers" by storing its
+// piece into every peer's window and then its step sequence number into its flag there (st.release.sys); it waits by
+// polling its OWN window's flags (ld.acquire.sys).  Sequence numbers only grow, so nothing is ever reset and a flag left
+// over from an earlier step can never satisfy a later wait.  The waits are bounded (DIST_WAIT_NS): a rank that never
+// arrives surfaces as SMJ_EINTERNAL on its peers, not as a hung GPU.
+extern SmjCtx *g_ctx[8];
+extern int g_nctx;
+int smj_stage_in(SmjCtx *c, const smj_table_t *t, int slot, const int32_t **d);
+int smj_alloc_out(SmjCtx *c, smj_table_t *out, int64_t rows, int cols);
+int smj_check_device_flag(SmjCtx *c);
+int smj_join_pairs_to_table(SmjCtx *c, const u64 *pl, u32 m1, const u64 *pr, u32 m2, const int32_t *d_t1, int c1, const int32_t *d_t2,
+                            int c2, int key2, smj_table_t *out, int64_t *rows_out);
+int smj_sorted_pairs_of_table(SmjCtx *c, const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val, int select_all,
+                              int key_col, int table_idx, u64 **d_sorted, int64_t *m_out);
+int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, smj_table_t *out, smj_stats_t *stats);
+int smj_ensure_init(void);
+
+namespace {
+
+constexpr int DIST_S_MAX = 512;                      // samples per table per rank
+constexpr unsigned long long DIST_WAIT_NS = 30ull * 1000 * 1000 * 1000;
+enum { PH_SAMPLES = 0, PH_COUNTS0, PH_COUNTS1, PH_XCHG0, PH_XCHG1, PH_N = 8 };
+#define SMJ_ERR_DIST_WAIT 4u
+
+struct DistWindow {                                   // mapped by every peer
+    u64 flag[PH_N][SMJ_MAX_G];                        // [phase][source rank]: the last step the source signalled
+    u64 counts[2][SMJ_MAX_G][SMJ_MAX_G];              // [table][src][dst]: rows src sends to dst (row src written by src)
+    u32 samples[SMJ_MAX_G][2 * DIST_S_MAX];           // [src][table * S + i]
+};
+
+struct DistLocal {                                    // private to the rank; copied to the host at the end of a step
+    u32 split[SMJ_MAX_G];                             // G - 1 key splitters
+    u64 rows[2];                                      // rows of table t this rank holds after the exchange (0 after an overflow verdict)
+    u64 row0[2][SMJ_MAX_G];                           // first row of this rank's bucket b inside rank b's receive buffer
+    u64 matrix[2][SMJ_MAX_G][SMJ_MAX_G];              // the gathered count matrices
+    u32 verdict[2];                                   // non-zero: some rank's receive buffer cannot take its share of table t
+    u32 pad[2];
+};
+
+struct DistPeers { DistWindow *win[SMJ_MAX_G]; };     // every rank's window as seen from this rank's device
+
+__device__ __forceinline__ u64 ld_acquire_sys(const u64 *p)
+{
+    u64 v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(u64 *p, u64 v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// spins until *p >= seq; false (and the error flag set) after DIST_WAIT_NS
+__device__ __forceinline__ bool wait_flag(const u64 *p, u64 seq, u32 *err)
+{
+    if (ld_acquire_sys(p) >= seq) return true;
+    const unsigned long long t0 = global_ns();
+    for (;;) {
+        for (int i = 0; i < 64; i++)
+            if (ld_acquire_sys(p) >= seq) return true;
+        if (global_ns() - t0 > DIST_WAIT_NS) { atomicExch(err, SMJ_ERR_DIST_WAIT); return false; }
+    }
+}
+
+// "I have arrived at `phase` of step `seq`" to every rank, then wait until every rank has.  Everything this rank's
+// earlier kernels on the stream stored -- into its own or into peer memory -- happens-before the flag store (stream order,
+// then a system-scope release), so a peer that sees the flag sees the data.
+__device__ __forceinline__ void signal_and_wait(const DistPeers &P, int me, int G, int phase, u64 seq, u32 *err)
+{
+    const int tid = threadIdx.x;
+    __threadfence_system();
+    __syncthreads();
+    if (tid < G) st_release_sys(&P.win[tid]->flag[phase][me], seq);
+    if (tid < G) wait_flag(&P.win[me]->flag[phase][tid], seq, err);
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(32) dist_arrive_kernel(const DistPeers P, int me, int G, int phase, u64 seq, u32 *err)
+{
+    signal_and_wait(P, me, G, phase, seq, err);
+}
+
+// ---- step 1, ONE kernel, one CTA: regular row samples of both tables (predicate applied) -> every peer's sample mailbox
+// -> wait for everybody's -> sort all G x 2S samples in shared memory (bitonic) -> G - 1 splitters.  Every rank sorts the
+// same samples, so every rank derives the same splitters; no collective library call, no host round trip.
+struct SampleJob { const int32_t *in; int64_t n; int cols, sel_col; int32_t sel_val; int select_all, key_col; };
+constexpr int SPL2_THREADS = 1024;
+
+__global__ void __launch_bounds__(SPL2_THREADS)
+dist_splitters_kernel(const DistPeers P, DistLocal *loc, int me, int G, u64 seq, int S, const SampleJob j0, const SampleJob j1,
+                      int n_pow2, u32 *err)
+{
+    extern __shared__ u32 s_s[];
+    __shared__ int s_valid;
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_valid = 0; loc->verdict[0] = 0; loc->verdict[1] = 0; loc->rows[0] = 0; loc->rows[1] = 0; }
+    if (tid < 2 * S) {
+        const SampleJob &J = tid < S ? j0 : j1;
+        const int i = tid < S ? tid : tid - S;
+        u32 v = 0xffffffffu;
+        if (J.n > 0) {
+            int64_t pos = (int64_t)(((unsigned long long)(2 * i + 1) * (unsigned long long)J.n) / (unsigned long long)(2 * S));
+            if (pos >= J.n) pos = J.n - 1;
+            const int32_t *r = J.in + pos * J.cols;
+            if (J.select_all || r[J.sel_col] > J.sel_val) v = (u32)r[J.key_col] ^ 0x80000000u;
+        }
+        for (int r = 0; r < G; r++) P.win[r]->samples[me][tid] = v;
+    }
+    signal_and_wait(P, me, G, PH_SAMPLES, seq, err);
+    const DistWindow *mine = P.win[me];
+    const int n_samples = G * 2 * S;
+    for (int i = tid; i < n_pow2; i += SPL2_THREADS)
+        s_s[i] = i < n_samples ? __ldcg(&mine->samples[i / (2 * S)][i % (2 * S)]) : 0xffffffffu;
+    __syncthreads();
+    for (int k = 2; k <= n_pow2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n_pow2; i += SPL2_THREADS) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const u32 a = s_s[i], b = s_s[p];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { s_s[i] = b; s_s[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    int local = 0;
+    for (int i = tid; i < n_pow2; i += SPL2_THREADS) local += s_s[i] != 0xffffffffu;
+    atomicAdd(&s_valid, local);
+    __syncthreads();
+    const int nv = s_valid;
+    if (tid >= 1 && tid < G) {   // the device twin of smj_plan_splitters: the "none" marks sort last, splitter b = quantile b / G
+        u32 v = 0xffffffffu;
+        if (nv > 0) {
+            long long pos = (long long)tid * nv / G;
+            if (pos >= nv) pos = nv - 1;
+            v = s_s[pos];
+        }
+        loc->split[tid - 1] = v;
+    }
+}
+
+// ---- step 3, one CTA per table: this rank's G bucket totals into every peer's count matrix, wait for everybody's, then
+// everything the exchange needs, computed identically on every rank from the same matrix: where my bucket b starts inside
+// rank b's receive buffer (rows the lower ranks send there), how many rows I will hold, and the VERDICT -- does any rank's
+// share exceed its receive capacity?  If so every rank skips the stores of this table and the host re-sizes the buffers
+// collectively after the step (the counts are never waited for on the host in a step that fits).
+__global__ void __launch_bounds__(64)
+dist_counts_kernel(const DistPeers P, DistLocal *loc, int me, int G, u64 seq, int t, const u64 *__restrict__ bucket_total, u64 cap_rows, u32 *err)
+{
+    __shared__ u64 s_m[SMJ_MAX_G][SMJ_MAX_G];
+    __shared__ u32 s_over;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_over = 0;
+    if (tid < G * G) P.win[tid / G]->counts[t][me][tid % G] = bucket_total[tid % G];
+    signal_and_wait(P, me, G, PH_COUNTS0 + t, seq, err);
+    if (tid < G * G) {
+        const u64 v = __ldcg(&P.win[me]->counts[t][tid / G][tid % G]);
+        s_m[tid / G][tid % G] = v;
+        loc->matrix[t][tid / G][tid % G] = v;
+    }
+    __syncthreads();
+    if (tid < G) {
+        u64 tot = 0, before = 0;
+        for (int src = 0; src < G; src++) { tot += s_m[src][tid]; if (src < me) before += s_m[src][tid]; }
+        loc->row0[t][tid] = before;
+        if (tot > cap_rows) atomicOr(&s_over, 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        u64 mine = 0;
+        for (int src = 0; src < G; src++) mine += s_m[src][me];
+        loc->verdict[t] = s_over;
+        loc->rows[t] = s_over ? 0ull : mine;
+    }
+}
+
+// ------------------------------------------------------------------ host side of the fabric
+struct DistRank {
+    SmjCtx *c = nullptr;
+    int me = 0;
+    DistWindow *win = nullptr;
+    DistLocal *loc = nullptr, *h_loc = nullptr;
+    DistPeers peers = {};
+    void *ipc_win[SMJ_MAX_G] = {};                    // IPC mappings this process opened (closed at shutdown / re-setup)
+    void *ipc_recv[2][SMJ_MAX_G] = {};
+    int32_t *recv[2] = {nullptr, nullptr};            // my receive buffers
+    int32_t *peer_recv[2][SMJ_MAX_G] = {};            // everybody's, as seen from my device
+    int64_t cap_rows[2] = {0, 0};
+    int cap_cols[2] = {0, 0};
+    cudaStream_t aux = nullptr;                       // table 2's partition / exchange chain
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev[8] = {};
+    // one step in flight
+    SmjRun run;
+    smj_table_t blk[2];
+    int64_t launches0 = 0;
+    int32_t *slots[2] = {};
+    char *pscr[2] = {};
+    int none[2] = {};
+};
+enum { DE_START, DE_H2D, DE_SPLIT, DE_PART, DE_XCHG };
+
+struct DistState {
+    bool active = false;          // smj_init_dist: one process per GPU
+    bool local = false;           // one process drives all ranks (smj_run with nr_gpus > 1 after smj_init)
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;    // multi-process: bootstrap collectives + the NCCL exchange paths
+    u64 seq = 0;                  // step sequence number, the same on every rank
+    int nlocal = 0;
+    DistRank rk[SMJ_MAX_G];
+} g_dist;
+
+int dist_rank_create(DistRank &K, SmjCtx *c, int me)
+{
+    K = DistRank();
+    K.c = c; K.me = me;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMalloc((void **)&K.win, sizeof(DistWindow)));
+    CUDA_TRY(cudaMemset(K.win, 0, sizeof(DistWindow)));
+    CUDA_TRY(cudaMalloc((void **)&K.loc, sizeof(DistLocal)));
+    CUDA_TRY(cudaMemset(K.loc, 0, sizeof(DistLocal)));
+    CUDA_TRY(cudaMallocHost((void **)&K.h_loc, sizeof(DistLocal)));
+    CUDA_TRY(cudaStreamCreateWithFlags(&K.aux, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&K.ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&K.ev_join, cudaEventDisableTiming));
+    for (auto &e : K.ev) CUDA_TRY(cudaEventCreate(&e));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return SMJ_OK;
+}
+
+void dist_rank_unmap_recv(DistRank &K)
+{
+    for (int t = 0; t < 2; t++)
+        for (int r = 0; r < SMJ_MAX_G; r++) {
+            if (K.ipc_recv[t][r]) cudaIpcCloseMemHandle(K.ipc_recv[t][r]);
+            K.ipc_recv[t][r] = nullptr;
+            K.peer_recv[t][r] = nullptr;
+        }
+    cudaGetLastError();
+}
+
+void dist_rank_destroy(DistRank &K)
+{
+    if (!K.c) return;
+    cudaSetDevice(K.c->device);
+    cudaDeviceSynchronize();
+    dist_rank_unmap_recv(K);
+    for (int r = 0; r < SMJ_MAX_G; r++) if (K.ipc_win[r]) cudaIpcCloseMemHandle(K.ipc_win[r]);
+    if (K.win) cudaFree(K.win);
+    if (K.loc) cudaFree(K.loc);
+    if (K.h_loc) cudaFreeHost(K.h_loc);
+    if (K.aux) cudaStreamDestroy(K.aux);
+    if (K.ev_fork) cudaEventDestroy(K.ev_fork);
+    if (K.ev_join) cudaEventDestroy(K.ev_join);
+    for (auto &e : K.ev) if (e) cudaEventDestroy(e);
+    cudaGetLastError();
+    K = DistRank();
+}
+
+// host-side all-gather of `bytes` per rank over the bootstrap communicator (multi-process mode; setup paths only)
+int boot_allgather(SmjCtx *c, const void *mine, void *all, size_t bytes)
+{
+    const int G = g_dist.world;
+    char *d = (char *)smj_ws(c, WS_SAMPLES, bytes * (size_t)(G + 1) + 256);
+    if (!d) return SMJ_ENOMEM;
+    CUDA_TRY(cudaMemcpyAsync(d, mine, bytes, cudaMemcpyHostToDevice, c->stream));
+    NCCL_TRY(g_nccl.AllGather(d, d + bytes, bytes, /*ncclUint8*/ 1, g_dist.comm, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(all, d + bytes, bytes * (size_t)G, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SMJ_OK;
+}
+
+// maps every rank's window into this process (multi-process mode, once, at smj_init_dist)
+int dist_map_windows_ipc(DistRank &K)
+{
+    const int G = g_dist.world;
+    cudaIpcMemHandle_t mine;
+    CUDA_TRY(cudaIpcGetMemHandle(&mine, K.win));
+    std::vector<cudaIpcMemHandle_t> all((size_t)G);
+    SMJ_TRY(boot_allgather(K.c, &mine, all.data(), sizeof mine));
+    for (int r = 0; r < G; r++) {
+        if (r == K.me) { K.peers.win[r] = K.win; continue; }
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return smj_cuda_fail(e, "cudaIpcOpenMemHandle(window): peer access between the GPUs is required", __FILE__, __LINE__);
+        K.ipc_win[r] = p;
+        K.peers.win[r] = (DistWindow *)p;
+    }
+    return SMJ_OK;
+}
+
+// ---- receive buffers.  Sized ONCE per shape for an upper bound of what a rank can receive (cap_pct % of the largest
+// input block plus slack), so that a step needs no host round trip for the counts; (re)sized collectively: at the first
+// step, when the column counts change, or after a step whose verdict said some rank's share did not fit (need_rows = what
+// the matrix asked for).  All ranks take the same decision from the same facts, so nobody waits in a collective alone.
+int dist_cap_pct(void)
+{
+    static const int pct = [] {
+        const char *e = getenv("SMJ_DIST_CAP_PCT");
+        const long v = e ? atol(e) : 0;
+        return (int)((v >= 1 && v <= 100000) ? v : 150);
+    }();
+    return pct;
+}
+
+int64_t dist_cap_from(const int64_t *n_local, const int64_t *need, int G)
+{
+    int64_t cap = 0;
+    for (int r = 0; r < G; r++) {
+        const int64_t a = n_local[r] / 100 * dist_cap_pct() + (n_local[r] % 100) * dist_cap_pct() / 100 + 4096;
+        const int64_t b = need[r] + need[r] / 4 + 4096;
+        if (a > cap) cap = a;
+        if (need[r] > 0 && b > cap) cap = b;
+    }
+    if (cap > SMJ_MAX_SORT_ROWS) cap = SMJ_MAX_SORT_ROWS;   // the local sort's limit; a share beyond it is refused in the verdict check
+    return cap;
+}
+
+// multi-process: K = the one local rank; n_local / need: this rank's rows per table / rows it must be able to receive (0: unknown)
+int dist_setup_recv_ipc(DistRank &K, const int64_t n_local[2], const int cols[2], const int64_t need[2])
+{
+    const int G = g_dist.world;
+    SmjCtx *c = K.c;
+    int64_t mine[4] = {n_local[0], n_local[1], need[0], need[1]};
+    std::vector<int64_t> all((size_t)4 * G);
+    SMJ_TRY(boot_allgather(c, mine, all.data(), sizeof mine));
+    // everybody closes its mappings of the old buffers BEFORE any owner frees one (the gather above and below are the barriers)
+    dist_rank_unmap_recv(K);
+    int64_t dummy = 0;
+    std::vector<int64_t> dummies((size_t)G);
+    SMJ_TRY(boot_allgather(c, &dummy, dummies.data(), sizeof dummy));
+    cudaIpcMemHandle_t hnd[2];
+    for (int t = 0; t < 2; t++) {
+        std::vector<int64_t> nl((size_t)G), nd((size_t)G);
+        for (int r = 0; r < G; r++) { nl[(size_t)r] = all[(size_t)4 * r + t]; nd[(size_t)r] = all[(size_t)4 * r + 2 + t]; }
+        const int64_t cap = dist_cap_from(nl.data(), nd.data(), G);
+        K.recv[t] = (int32_t *)smj_ws(c, t ? WS_DIST_RECV2 : WS_DIST_RECV1, (size_t)cap * cols[t] * 4);
+        if (!K.recv[t]) return SMJ_ENOMEM;
+        K.cap_rows[t] = cap;
+        K.cap_cols[t] = cols[t];
+        CUDA_TRY(cudaIpcGetMemHandle(&hnd[t], K.recv[t]));
+    }
+    std::vector<cudaIpcMemHandle_t> hall((size_t)2 * G);
+    SMJ_TRY(boot_allgather(c, hnd, hall.data(), sizeof hnd));
+    for (int r = 0; r < G; r++)
+        for (int t = 0; t < 2; t++) {
+            if (r == K.me) { K.peer_recv[t][r] = K.recv[t]; continue; }
+            void *p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, hall[(size_t)2 * r + t], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return smj_cuda_fail(e, "cudaIpcOpenMemHandle(receive buffer)", __FILE__, __LINE__);
+            K.ipc_recv[t][r] = p;
+            K.peer_recv[t][r] = (int32_t *)p;
+        }
+    return SMJ_OK;
+}
+
+// one process, G ranks: the same decision, no collectives; peers address each other's memory directly (peer access)
+int dist_setup_recv_local(const int64_t n_local[][2], const int cols[2], const int64_t need[][2])
+{
+    const int G = g_dist.world;
+    for (int t = 0; t < 2; t++) {
+        int64_t nl[SMJ_MAX_G], nd[SMJ_MAX_G];
+        for (int r = 0; r < G; r++) { nl[r] = n_local[r][t]; nd[r] = need[r][t]; }
+        const int64_t cap = dist_cap_from(nl, nd, G);
+        for (int r = 0; r < G; r++) {
+            DistRank &K = g_dist.rk[r];
+            CUDA_TRY(cudaSetDevice(K.c->device));
+            K.recv[t] = (int32_t *)smj_ws(K.c, t ? WS_DIST_RECV2 : WS_DIST_RECV1, (size_t)cap * cols[t] * 4);
+            if (!K.recv[t]) return SMJ_ENOMEM;
+            K.cap_rows[t] = cap;
+            K.cap_cols[t] = cols[t];
+        }
+        for (int r = 0; r < G; r++)
+            for (int q = 0; q < G; q++) g_dist.rk[r].peer_recv[t][q] = g_dist.rk[q].recv[t];
+    }
+    return SMJ_OK;
+}
+
+float dist_ev_ms(cudaEvent_t a, cudaEvent_t b)
+{
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return ms;
+}
+
+bool dist_two_streams(void)
+{
+    static const bool two = !(getenv("SMJ_DIST_STREAMS") && atoi(getenv("SMJ_DIST_STREAMS")) == 1);
+    return two;
+}
+
+// ---- one step of the partition-first pipeline on one rank, in three phases (see smj_run_prepare in smj_api.cu for why)
+// prepare: stage the rank's row blocks, size every buffer (the receive buffers were sized by dist_setup_recv_*)
+int dist_step_prepare(DistRank &K, const smj_config_t *cfg, const smj_table_t *b1, const smj_table_t *b2)
+{
+    SmjCtx *c = K.c;
+    CUDA_TRY(cudaSetDevice(c->device));
+    K.blk[0] = *b1; K.blk[1] = *b2;
+    K.launches0 = c->launches;
+    const int64_t sel_val[2] = {cfg->select_val1, cfg->select_val2};
+    CUDA_TRY(cudaEventRecord(K.ev[DE_START], c->stream));
+    for (int t = 0; t < 2; t++) {
+        const int32_t *d = nullptr;
+        smj_table_t tt = K.blk[t];
+        if (tt.on_device && tt.rows > 0 && ((uintptr_t)tt.data & 15)) {
+            // a caller's device view that is not 16-byte aligned: a local copy, so that every rank takes the same path
+            int32_t *p = (int32_t *)smj_ws(c, t ? WS_T2 : WS_T1, (size_t)tt.rows * tt.cols * 4);
+            if (!p) return SMJ_ENOMEM;
+            CUDA_TRY(cudaMemcpyAsync(p, tt.data, (size_t)tt.rows * tt.cols * 4, cudaMemcpyDeviceToDevice, c->stream));
+            d = p;
+        } else {
+            SMJ_TRY(smj_stage_in(c, &tt, t ? WS_T2 : WS_T1, &d));
+        }
+        K.blk[t].data = const_cast<int32_t *>(d);
+        K.blk[t].on_device = 1;
+        const size_t cells = (size_t)tt.rows * tt.cols;
+        K.slots[t] = (int32_t *)smj_ws(c, t ? WS_TMP_ROWS2 : WS_TMP_ROWS, cells * 4);
+        K.pscr[t] = (char *)smj_ws(c, t ? WS_MERGE_B : WS_MERGE_A, smj_partition_scratch_bytes(tt.rows, tt.cols));
+        if (!K.slots[t] || !K.pscr[t]) return SMJ_ENOMEM;
+        K.none[t] = (sel_val[t] >= (int64_t)INT32_MAX) ? 1 : 0;
+    }
+    CUDA_TRY(cudaEventRecord(K.ev[DE_H2D], c->stream));
+    // the local pipeline on what will arrive: select disabled, row counts device-resident (loc->rows)
+    smj_config_t local = *cfg;
+    local.nr_gpus = 1;
+    local.select_col1 = 0; local.select_col2 = 0;
+    local.select_val1 = INT64_MIN; local.select_val2 = INT64_MIN;
+    const smj_table_t r1 = {K.recv[0], K.cap_rows[0], K.blk[0].cols, 1}, r2 = {K.recv[1], K.cap_rows[1], K.blk[1].cols, 1};
+    const u64 *d_rows[2] = {&K.loc->rows[0], &K.loc->rows[1]};
+    SMJ_TRY(smj_run_prepare(c, &local, &r1, &r2, d_rows, &K.run));
+    return SMJ_OK;
+}
+
+// enqueue: splitters -> per table: select + partition, offsets, counts, exchange, arrival -> the local pipeline.
+// Table 2's chain runs on a second stream and starts when table 1's partition kernel is done, so that its HBM-bound
+// partition pass overlaps table 1's NVLink-bound exchange.
+int dist_step_enqueue(DistRank &K, const smj_config_t *cfg, u64 seq)
+{
+    SmjCtx *c = K.c;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int G = g_dist.world, me = K.me;
+    const int sel_col[2] = {cfg->select_col1, cfg->select_col2};
+    const int64_t sel_val[2] = {cfg->select_val1, cfg->select_val2};
+    const int key[2] = {cfg->join_key1, cfg->join_key2};
+    const int S = G <= 4 ? DIST_S_MAX : DIST_S_MAX / 2;
+    int n_pow2 = 1;
+    while (n_pow2 < G * 2 * S) n_pow2 <<= 1;
+    SampleJob sj[2];
+    for (int t = 0; t < 2; t++) {
+        int select_all = sel_val[t] < (int64_t)INT32_MIN;
+        int64_t n = K.blk[t].rows;
+        if (!select_all && sel_val[t] >= (int64_t)INT32_MAX) n = 0;
+        sj[t] = {K.blk[t].data, n, K.blk[t].cols, sel_col[t], (int32_t)sel_val[t], select_all, key[t]};
+    }
+    dist_splitters_kernel<<<1, SPL2_THREADS, (size_t)n_pow2 * 4, c->stream>>>(K.peers, K.loc, me, G, seq, S, sj[0], sj[1], n_pow2, c->d_err);
+    KERNEL_CHECK(c);
+    CUDA_TRY(cudaEventRecord(K.ev[DE_SPLIT], c->stream));
+    const bool two = dist_two_streams();
+    for (int t = 0; t < 2; t++) {
+        cudaStream_t st = (t == 1 && two) ? K.aux : c->stream;
+        SMJ_TRY(smj_launch_select_partition(c, st, K.blk[t].data, K.blk[t].rows, K.blk[t].cols, sel_col[t], sel_val[t], key[t], K.loc->split, G,
+                                            K.slots[t], K.pscr[t]));
+        if (t == 0) {
+            CUDA_TRY(cudaEventRecord(K.ev[DE_PART], c->stream));
+            if (two) {   // table 2's chain starts here
+                CUDA_TRY(cudaEventRecord(K.ev_fork, c->stream));
+                CUDA_TRY(cudaStreamWaitEvent(K.aux, K.ev_fork, 0));
+            }
+        }
+        const SmjPartScratch PS = smj_partition_scratch(K.pscr[t], K.none[t] ? 0 : K.blk[t].rows, K.blk[t].cols);
+        dist_counts_kernel<<<1, 64, 0, st>>>(K.peers, K.loc, me, G, seq, t, PS.bucket_total, (u64)K.cap_rows[t], c->d_err);
+        KERNEL_CHECK(c);
+        SmjPartitionDst D = {};
+        for (int b = 0; b < G; b++) D.base[b] = K.peer_recv[t][b];
+        D.row0 = K.loc->row0[t];
+        D.skip = &K.loc->verdict[t];
+        SMJ_TRY(smj_launch_partition_exchange(c, st, K.blk[t].rows, K.blk[t].cols, K.none[t], G, K.slots[t], K.pscr[t], D));
+        // every rank's stores must have landed before anybody reads its receive buffer
+        dist_arrive_kernel<<<1, 32, 0, st>>>(K.peers, me, G, PH_XCHG0 + t, seq, c->d_err);
+        KERNEL_CHECK(c);
+    }
+    if (two) {
+        CUDA_TRY(cudaEventRecord(K.ev_join, K.aux));
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, K.ev_join, 0));
+    }
+    CUDA_TRY(cudaEventRecord(K.ev[DE_XCHG], c->stream));
+    CUDA_TRY(cudaMemcpyAsync(K.h_loc, K.loc, sizeof(DistLocal), cudaMemcpyDeviceToHost, c->stream));
+    return smj_run_enqueue(c, &K.run);
+}
+
+// finish: the one host wait.  *retry = the verdict (the same on every rank): the step stored nothing, `need` says what
+// every rank must be able to receive, the caller re-sizes collectively and runs the step again.
+int dist_step_finish(DistRank &K, const smj_config_t *cfg, smj_table_t *out, smj_stats_t *stats, bool *retry, int64_t need[2])
+{
+    SmjCtx *c = K.c;
+    const int G = g_dist.world, me = K.me;
+    smj_stats_t ls;
+    SMJ_TRY(smj_run_finish(c, &K.run, out, &ls));
+    const DistLocal *h = K.h_loc;
+    *retry = h->verdict[0] || h->verdict[1];
+    int64_t sel[2] = {0, 0}, own[2] = {0, 0};
+    double sent = 0;
+    for (int t = 0; t < 2; t++) {
+        int64_t worst = 0;
+        for (int dst = 0; dst < G; dst++) {
+            int64_t tot = 0;
+            for (int src = 0; src < G; src++) tot += (int64_t)h->matrix[t][src][dst];
+            if (tot > worst) worst = tot;
+            sel[t] += (int64_t)h->matrix[t][me][dst];
+            if (dst != me) sent += (double)h->matrix[t][me][dst] * K.blk[t].cols * 4;
+        }
+        for (int src = 0; src < G; src++) own[t] += (int64_t)h->matrix[t][src][me];
+        need[t] = worst;
+        if (worst > SMJ_MAX_SORT_ROWS) {
+            if (out->data) smj_table_free(out);
+            return smj_set_error(SMJ_ETOOBIG, "a rank would receive %lld rows of table %d (limit 2^30 - 1 per GPU)", (long long)worst, t + 1);
+        }
+    }
+    if (*retry) {
+        if (out->data) smj_table_free(out);
+        return SMJ_OK;
+    }
+    static const bool trace = getenv("SMJ_DIST_TRACE") != nullptr;
+    if (trace && me == 0)
+        fprintf(stderr, "[dist] fabric step %llu; dev ms: samples+splitters %.3f | select/partition t1 %.3f | both chains to exchange done %.3f | local %.3f\n",
+                (unsigned long long)g_dist.seq, dist_ev_ms(K.ev[DE_H2D], K.ev[DE_SPLIT]), dist_ev_ms(K.ev[DE_SPLIT], K.ev[DE_PART]),
+                dist_ev_ms(K.ev[DE_PART], K.ev[DE_XCHG]), dist_ev_ms(K.ev[DE_XCHG], c->ev[4]));
+    if (cfg->debug) {
+        printf("==================\n#   exchange.cu  #\n==================\n");
+        for (int t = 0; t < 2; t++)
+            printf("Table %d - GPU %d selected %lld rows, owns %lld rows after the key-range exchange\n", t, me, (long long)sel[t], (long long)own[t]);
+        printf("####################\n\n");
+    }
+    if (stats) {
+        *stats = ls;
+        stats->h2d_ms = dist_ev_ms(K.ev[DE_START], K.ev[DE_H2D]);
+        stats->select_ms = dist_ev_ms(K.ev[DE_H2D], K.ev[DE_PART]);      // samples + splitters + select/partition of table 1
+        stats->exchange_ms = dist_ev_ms(K.ev[DE_PART], K.ev[DE_XCHG]);   // table 2's partition overlapped with both exchanges
+        // pairs of the received rows + the radix passes: from the end of the exchange to the start of the join stage
+        stats->sort_ms = dist_ev_ms(K.ev[DE_XCHG], c->ev[4]) - ls.join_ms;
+        stats->merge_ms = 0;
+        stats->total_device_ms = dist_ev_ms(K.ev[DE_H2D], c->ev[4]);     // through the local pipeline's end-of-join event
+        for (int t = 0; t < 2; t++) { stats->rows_in[t] = K.blk[t].rows; stats->rows_selected[t] = sel[t]; }
+        stats->bytes_nvlink = sent;
+        stats->kernel_launches = c->launches - K.launches0;
+    }
+    return SMJ_OK;
+}
+
+}  // namespace
+
 // ------------------------------------------------------------------ init / shutdown
 bool smj_dist_active(void) { return g_dist.active; }
 
-static void peer_unmap_all();
-
 int smj_dist_shutdown(void)
 {
-    peer_unmap_all();
+    if (g_dist.active && g_dist.comm && g_dist.rk[0].c) {
+        // close this process's mappings of the peers' memory, then meet the peers, and only then free what they had mapped
+        DistRank &K = g_dist.rk[0];
+        cudaSetDevice(K.c->device);
+        cudaDeviceSynchronize();
+        dist_rank_unmap_recv(K);
+        for (int r = 0; r < SMJ_MAX_G; r++) { if (K.ipc_win[r]) cudaIpcCloseMemHandle(K.ipc_win[r]); K.ipc_win[r] = nullptr; }
+        int64_t dummy = 0;
+        std::vector<int64_t> all((size_t)g_dist.world);
+        boot_allgather(K.c, &dummy, all.data(), sizeof dummy);
+        cudaGetLastError();
+    }
+    for (int r = 0; r < SMJ_MAX_G; r++) dist_rank_destroy(g_dist.rk[r]);
     if (g_dist.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(g_dist.comm);
     g_dist = DistState();
     return SMJ_OK;
@@ -183,79 +748,218 @@ int smj_init_on_device(const smj_config_t *cfg, int device);   // smj_api.cu
 
 extern "C" int smj_init_dist(const smj_config_t *cfg, int rank, int world, int local_device, const void *nccl_id_128)
 {
-    if (world < 1 || rank < 0 || rank >= world || !nccl_id_128) return smj_set_error(SMJ_EINVAL, "smj_init_dist: bad rank/world/id");
+    if (world < 1 || world > SMJ_MAX_G || rank < 0 || rank >= world || !nccl_id_128)
+        return smj_set_error(SMJ_EINVAL, "smj_init_dist: bad rank/world/id (world <= %d)", SMJ_MAX_G);
     SMJ_TRY(nccl_load());
-    SMJ_TRY(smj_init_on_device(cfg, local_device));
-    smj_dist_shutdown();
+    SMJ_TRY(smj_init_on_device(cfg, local_device));   // (shuts a previous mode down first)
     ncclUniqueId id;
     memcpy(&id, nccl_id_128, sizeof id);
     NCCL_TRY(g_nccl.CommInitRank(&g_dist.comm, world, id, rank));
     g_dist.rank = rank;
     g_dist.world = world;
     g_dist.active = true;
+    g_dist.nlocal = 1;
+    SMJ_TRY(dist_rank_create(g_dist.rk[0], g_ctx[0], rank));
+    SMJ_TRY(dist_map_windows_ipc(g_dist.rk[0]));
     return SMJ_OK;
 }
 
-// ------------------------------------------------------------------ the distributed pipeline
-extern SmjCtx *g_ctx[8];
-int smj_stage_in(SmjCtx *c, const smj_table_t *t, int slot, const int32_t **d);
-int smj_alloc_out(SmjCtx *c, smj_table_t *out, int64_t rows, int cols);
-int smj_check_device_flag(SmjCtx *c);
-int smj_join_pairs_to_table(SmjCtx *c, const u64 *pl, u32 m1, const u64 *pr, u32 m2, const int32_t *d_t1, int c1, const int32_t *d_t2,
-                            int c2, int key2, smj_table_t *out, int64_t *rows_out);
-int smj_sorted_pairs_of_table(SmjCtx *c, const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val, int select_all,
-                              int key_col, int table_idx, u64 **d_sorted, int64_t *m_out);
-
-static float dist_ev_ms(cudaEvent_t a, cudaEvent_t b)
+// One process, G GPUs (smj_init with nr_gpus = G, then smj_run): rank r = device r.
+static int dist_init_local(int G)
 {
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return 0; }
-    return ms;
-}
-
-// ------------------------------------------------------------------ partition-first pipeline (default)
-bool smj_partition_supported(const int32_t *d_in, int cols);
-size_t smj_partition_scratch_bytes(int64_t n, int cols);
-int smj_launch_sample_rows(SmjCtx *c, const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val, int key_col, int S,
-                           u32 *d_samples);
-int smj_launch_select_partition(SmjCtx *c, const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val, int key_col,
-                                const u32 *d_splitters, int G, int32_t *d_slots, char *d_scratch, u64 **d_bucket_start);
-int smj_launch_partition_compact(SmjCtx *c, int64_t n, int cols, int sel_val_none, int G, const int32_t *d_slots, char *d_scratch,
-                                 int32_t *d_send, int32_t *const *d_dst_by_bucket);
-int smj_launch_splitters(SmjCtx *c, const u32 *d_samples, int n_samples, int G, u32 *d_splitters);
-int smj_run_single(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, smj_table_t *out, smj_stats_t *stats);
-static int smj_run_multi_sorted(const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, smj_table_t *out, smj_stats_t *stats);
-
-// Peer receive buffers mapped through CUDA IPC (one process per GPU on one box): g_peer[t][r] is rank r's receive buffer
-// of table t as seen from this process.  Re-mapped whenever the owner reallocated (its handle changed).
-struct PeerMap { void *base = nullptr; cudaIpcMemHandle_t handle; bool have = false; };
-static PeerMap g_peer[2][8];
-
-static void peer_unmap_all()
-{
-    for (int t = 0; t < 2; t++)
-        for (int r = 0; r < 8; r++) {
-            if (g_peer[t][r].base) cudaIpcCloseMemHandle(g_peer[t][r].base);
-            g_peer[t][r] = PeerMap();
+    if (g_dist.local && g_dist.world == G) return SMJ_OK;
+    if (g_dist.active) return smj_set_error(SMJ_EINVAL, "smj_init_dist mode is active: it drives one GPU per process");
+    if (G > g_nctx || G > SMJ_MAX_G) return smj_set_error(SMJ_EINVAL, "nr_gpus=%d but %d contexts", G, g_nctx);
+    smj_dist_shutdown();
+    for (int r = 0; r < G; r++)
+        for (int q = 0; q < G; q++) {
+            if (r == q) continue;
+            int can = 0;
+            CUDA_TRY(cudaDeviceCanAccessPeer(&can, g_ctx[r]->device, g_ctx[q]->device));
+            if (!can) return smj_set_error(SMJ_EINVAL, "GPU %d cannot access GPU %d's memory: the key-range exchange needs peer access", r, q);
+            CUDA_TRY(cudaSetDevice(g_ctx[r]->device));
+            cudaError_t e = cudaDeviceEnablePeerAccess(g_ctx[q]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return smj_cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+            cudaGetLastError();
         }
-    cudaGetLastError();
+    g_dist.world = G;
+    g_dist.nlocal = G;
+    for (int r = 0; r < G; r++) SMJ_TRY(dist_rank_create(g_dist.rk[r], g_ctx[r], r));
+    for (int r = 0; r < G; r++)
+        for (int q = 0; q < G; q++) g_dist.rk[r].peers.win[q] = g_dist.rk[q].win;
+    g_dist.local = true;
+    return SMJ_OK;
 }
 
-// select + key-range partition of the ROWS (one streaming pass, smj_partition.cu) -> exchange -> the single-GPU pipeline
-// (sort + join, select disabled) on what arrived.  Compared with sorting first and merging the received runs
-// (smj_run_multi_sorted below, SMJ_DIST_MODE=merge) no row is gathered at random before it travels and there are no merge
-// rounds (0.51 ms per step at 8 GPUs).  The exchange itself is FUSED into the compaction kernel: each (tile, bucket)
-// segment is stored straight into the destination rank's receive buffer through a CUDA-IPC mapping, i.e. over NVLink
-// from the SMs (SMJ_DIST_EXCHANGE=nccl falls back to a send buffer + grouped ncclSend/ncclRecv, which reached 240 GB/s
-// per GPU here against ~770 GB/s for peer copies).
+// ------------------------------------------------------------------ the distributed pipeline (default path)
+static int smj_run_multi_sorted(const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, smj_table_t *out, smj_stats_t *stats);
+static int smj_run_multi_nccl(const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, smj_table_t *out, smj_stats_t *stats);
+
+static int dist_check_knobs(const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2)
+{
+    const smj_table_t *tb[2] = {t1, t2};
+    const int sel_col[2] = {cfg->select_col1, cfg->select_col2};
+    const int key[2] = {cfg->join_key1, cfg->join_key2};
+    if (cfg->join_mode != SMJ_JOIN_ZIP) return smj_set_error(SMJ_EINVAL, "smj_run on several GPUs materialises SMJ_JOIN_ZIP only (the reference semantics)");
+    for (int t = 0; t < 2; t++) {
+        if (sel_col[t] < 0 || sel_col[t] >= tb[t]->cols) return smj_set_error(SMJ_EINVAL, "SELECT_COL%d=%d out of range", t + 1, sel_col[t]);
+        if (key[t] < 0 || key[t] >= tb[t]->cols) return smj_set_error(SMJ_EINVAL, "JOIN_KEY%d=%d out of range", t + 1, key[t]);
+    }
+    return SMJ_OK;
+}
+
+// One process per GPU.  select + key-range partition of the ROWS (one streaming pass, smj_partition.cu) -> exchange fused into
+// the compaction kernel (stores into the owners' receive buffers over NVLink) -> the single-GPU pipeline (sort + join, select
+// disabled) on what arrived.  All synchronisation between the ranks is flag mailboxes in peer memory; the host waits once.
+// Which path a step takes depends only on facts every rank shares (environment, column counts), never on one rank's data.
 int smj_run_multi(const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, smj_table_t *out, smj_stats_t *stats)
 {
-    if (!g_dist.active) return smj_set_error(SMJ_EINVAL, "nr_gpus > 1 needs one process per GPU: call smj_init_dist first (see INTEGRATION.md)");
-    if (cfg->join_mode != SMJ_JOIN_ZIP) return smj_set_error(SMJ_EINVAL, "smj_run materialises SMJ_JOIN_ZIP only (the reference semantics)");
+    if (!g_dist.active) return smj_set_error(SMJ_EINVAL, "smj_run_multi: call smj_init_dist first (one process per GPU)");
+    SMJ_TRY(dist_check_knobs(cfg, t1, t2));
     const char *mode = getenv("SMJ_DIST_MODE");
-    if (mode && strcmp(mode, "merge") == 0) return smj_run_multi_sorted(cfg, t1, t2, out, stats);
+    if ((mode && strcmp(mode, "merge") == 0) || t1->cols > 32 || t2->cols > 32) return smj_run_multi_sorted(cfg, t1, t2, out, stats);
     const char *xmode = getenv("SMJ_DIST_EXCHANGE");
-    const bool use_peer = !(xmode && strcmp(xmode, "nccl") == 0);
+    if (xmode && strcmp(xmode, "nccl") == 0) return smj_run_multi_nccl(cfg, t1, t2, out, stats);
+    DistRank &K = g_dist.rk[0];
+    const int cols[2] = {t1->cols, t2->cols};
+    const int64_t n_local[2] = {t1->rows, t2->rows};
+    int64_t need[2] = {0, 0};
+    for (int attempt = 0; attempt < 4; attempt++) {
+        if (attempt > 0 || K.cap_rows[0] == 0 || K.cap_cols[0] != cols[0] || K.cap_cols[1] != cols[1])
+            SMJ_TRY(dist_setup_recv_ipc(K, n_local, cols, need));
+        const u64 seq = ++g_dist.seq;
+        SMJ_TRY(dist_step_prepare(K, cfg, t1, t2));
+        int rc = dist_step_enqueue(K, cfg, seq);
+        if (rc != SMJ_OK) { smj_run_abandon(K.c, &K.run); cudaStreamSynchronize(K.c->stream); cudaStreamSynchronize(K.aux); return rc; }
+        bool retry = false;
+        SMJ_TRY(dist_step_finish(K, cfg, out, stats, &retry, need));
+        if (!retry) return SMJ_OK;
+    }
+    return smj_set_error(SMJ_EINTERNAL, "the key-range exchange did not fit its receive buffers after three re-sizings");
+}
+
+// One process, G GPUs (the C driver: NR_GPUS / SMJ_NR_GPUS = G): the host tables are cut into G contiguous row blocks
+// (rank order = row order, as app.c:155-218 deals rows to DPUs), every rank runs the step above on its own device and
+// stream, and the shards are copied back in rank order = key order into ONE result table (app.c:739-753).
+int smj_run_multi_local(const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, smj_table_t *out, smj_stats_t *stats)
+{
+    const int G = cfg->nr_gpus;
+    SMJ_TRY(dist_check_knobs(cfg, t1, t2));
+    if (t1->cols > 32 || t2->cols > 32) return smj_set_error(SMJ_EINVAL, "several GPUs in one process: tables of at most 32 columns");
+    SMJ_TRY(dist_init_local(G));
+    const smj_table_t *tb[2] = {t1, t2};
+    const int cols[2] = {t1->cols, t2->cols};
+    smj_table_t blk[SMJ_MAX_G][2];
+    int64_t n_local[SMJ_MAX_G][2], need[SMJ_MAX_G][2] = {};
+    for (int t = 0; t < 2; t++) {
+        int owner = -1;   // a device table (the GPU CSV parser's output) lives on one GPU: the other ranks' blocks travel over NVLink
+        if (tb[t]->on_device && tb[t]->rows > 0) {
+            cudaPointerAttributes at;
+            CUDA_TRY(cudaPointerGetAttributes(&at, tb[t]->data));
+            owner = at.device;
+        }
+        for (int r = 0; r < G; r++) {
+            const int64_t lo = tb[t]->rows * r / G, hi = tb[t]->rows * (r + 1) / G;
+            int32_t *src = tb[t]->data ? tb[t]->data + (size_t)lo * cols[t] : nullptr;
+            blk[r][t] = {src, hi - lo, cols[t], tb[t]->on_device};
+            n_local[r][t] = hi - lo;
+            SmjCtx *c = g_ctx[r];
+            if (owner >= 0 && owner != c->device && hi > lo) {
+                const size_t bytes = (size_t)(hi - lo) * cols[t] * 4;
+                CUDA_TRY(cudaSetDevice(c->device));
+                int32_t *p = (int32_t *)smj_ws(c, t ? WS_T2 : WS_T1, bytes);
+                if (!p) return SMJ_ENOMEM;
+                CUDA_TRY(cudaMemcpyPeerAsync(p, c->device, src, owner, bytes, c->stream));
+                blk[r][t].data = p;
+            }
+        }
+    }
+    smj_table_t shard[SMJ_MAX_G];
+    smj_stats_t st[SMJ_MAX_G];
+    bool done = false;
+    for (int attempt = 0; attempt < 4 && !done; attempt++) {
+        DistRank &K0 = g_dist.rk[0];
+        if (attempt > 0 || K0.cap_rows[0] == 0 || K0.cap_cols[0] != cols[0] || K0.cap_cols[1] != cols[1])
+            SMJ_TRY(dist_setup_recv_local(n_local, cols, need));
+        const u64 seq = ++g_dist.seq;
+        int rc = SMJ_OK;
+        int prepared = 0;
+        for (int r = 0; r < G && rc == SMJ_OK; r++) { rc = dist_step_prepare(g_dist.rk[r], cfg, &blk[r][0], &blk[r][1]); if (rc == SMJ_OK) prepared = r + 1; }
+        for (int r = 0; r < G && rc == SMJ_OK; r++) rc = dist_step_enqueue(g_dist.rk[r], cfg, seq);
+        if (rc != SMJ_OK) {
+            for (int r = 0; r < prepared; r++) {
+                DistRank &K = g_dist.rk[r];
+                cudaSetDevice(K.c->device);
+                cudaStreamSynchronize(K.c->stream); cudaStreamSynchronize(K.aux);
+                smj_run_abandon(K.c, &K.run);
+            }
+            cudaSetDevice(g_ctx[0]->device);
+            return rc;
+        }
+        bool retry = false;
+        for (int r = 0; r < G; r++) {
+            shard[r] = {nullptr, 0, 0, 1};   // shards stay on their devices until the total is known
+            bool rr = false;
+            int frc = dist_step_finish(g_dist.rk[r], cfg, &shard[r], &st[r], &rr, need[r]);
+            if (frc != SMJ_OK && rc == SMJ_OK) rc = frc;
+            retry = retry || rr;
+        }
+        if (rc != SMJ_OK || retry) {
+            for (int r = 0; r < G; r++) if (shard[r].data) smj_table_free(&shard[r]);
+            if (rc != SMJ_OK) { cudaSetDevice(g_ctx[0]->device); return rc; }
+            continue;
+        }
+        done = true;
+    }
+    if (!done) return smj_set_error(SMJ_EINTERNAL, "the key-range exchange did not fit its receive buffers after three re-sizings");
+    // ---- GPU -> CPU: the shards in rank order = key order (app.c:739-753 writes the DPUs' results in order)
+    int64_t total = 0;
+    for (int r = 0; r < G; r++) total += shard[r].rows;
+    const int c_out = cols[0] + cols[1] - 1;
+    out->on_device = 0;
+    SMJ_TRY(smj_alloc_out(g_ctx[0], out, total, c_out));
+    int64_t at = 0;
+    for (int r = 0; r < G; r++) {
+        DistRank &K = g_dist.rk[r];
+        CUDA_TRY(cudaSetDevice(K.c->device));
+        CUDA_TRY(cudaEventRecord(K.ev[5], K.c->stream));
+        if (shard[r].rows)
+            CUDA_TRY(cudaMemcpyAsync(out->data + (size_t)at * c_out, shard[r].data, (size_t)shard[r].rows * c_out * 4, cudaMemcpyDeviceToHost, K.c->stream));
+        CUDA_TRY(cudaEventRecord(K.ev[6], K.c->stream));
+        at += shard[r].rows;
+    }
+    double d2h = 0;
+    for (int r = 0; r < G; r++) {
+        DistRank &K = g_dist.rk[r];
+        CUDA_TRY(cudaSetDevice(K.c->device));
+        CUDA_TRY(cudaStreamSynchronize(K.c->stream));
+        const double ms = dist_ev_ms(K.ev[5], K.ev[6]);
+        if (ms > d2h) d2h = ms;
+        if (shard[r].data) smj_table_free(&shard[r]);
+    }
+    CUDA_TRY(cudaSetDevice(g_ctx[0]->device));
+    if (stats) {   // times: the slowest rank; counts and bytes: summed
+        *stats = st[0];
+        for (int r = 1; r < G; r++) {
+            const smj_stats_t &x = st[r];
+#define MAXF(f) if (x.f > stats->f) stats->f = x.f
+            MAXF(h2d_ms); MAXF(select_ms); MAXF(sort_ms); MAXF(exchange_ms); MAXF(join_ms); MAXF(total_device_ms); MAXF(sort_pass_ms_avg);
+#undef MAXF
+            for (int t = 0; t < 2; t++) { stats->rows_in[t] += x.rows_in[t]; stats->rows_selected[t] += x.rows_selected[t]; }
+            stats->rows_joined += x.rows_joined;
+            stats->bytes_model += x.bytes_model; stats->bytes_planned += x.bytes_planned; stats->bytes_nvlink += x.bytes_nvlink;
+            stats->kernel_launches += x.kernel_launches;
+        }
+        stats->d2h_ms = d2h;
+    }
+    return SMJ_OK;
+}
+
+// ------------------------------------------------------------------ the same partitioning through NCCL (SMJ_DIST_EXCHANGE=nccl)
+// The A/B partner of the fabric path: splitters from an ncclAllGather of the samples, the count matrix all-gathered and
+// WAITED FOR on the host (exact receive buffers), a send buffer and one grouped ncclSend/ncclRecv all-to-all.
+static int smj_run_multi_nccl(const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, smj_table_t *out, smj_stats_t *stats)
+{
     SmjCtx *c = g_ctx[0];
     CUDA_TRY(cudaSetDevice(c->device));
     const int G = g_dist.world, me = g_dist.rank;
@@ -263,46 +967,39 @@ int smj_run_multi(const smj_config_t *cfg, const smj_table_t *t1, const smj_tabl
     const int sel_col[2] = {cfg->select_col1, cfg->select_col2};
     const int64_t sel_val[2] = {cfg->select_val1, cfg->select_val2};
     const int key[2] = {cfg->join_key1, cfg->join_key2};
-    for (int t = 0; t < 2; t++) {
-        if (sel_col[t] < 0 || sel_col[t] >= tb[t]->cols) return smj_set_error(SMJ_EINVAL, "SELECT_COL%d=%d out of range", t + 1, sel_col[t]);
-        if (key[t] < 0 || key[t] >= tb[t]->cols) return smj_set_error(SMJ_EINVAL, "JOIN_KEY%d=%d out of range", t + 1, key[t]);
-    }
     const int64_t launches0 = c->launches;
-    enum { E_START, E_H2D, E_PART, E_XCHG, E_SAMP, E_SPLIT, E_CNT };
+    enum { E_START, E_H2D, E_PART, E_XCHG };
     cudaEvent_t *ev = c->ev + 8;   // smj_run_single below uses c->ev[0..5]
-    static const bool trace = getenv("SMJ_DIST_TRACE") != nullptr;
     CUDA_TRY(cudaEventRecord(ev[E_START], c->stream));
     const int32_t *d_t[2];
-    SMJ_TRY(smj_stage_in(c, t1, WS_T1, &d_t[0]));
-    SMJ_TRY(smj_stage_in(c, t2, WS_T2, &d_t[1]));
     const int cc[2] = {t1->cols, t2->cols};
-    if ((tb[0]->rows && !smj_partition_supported(d_t[0], cc[0])) || (tb[1]->rows && !smj_partition_supported(d_t[1], cc[1])))
-        return smj_run_multi_sorted(cfg, t1, t2, out, stats);   // > 32 columns or a table that is not 16-byte aligned
+    for (int t = 0; t < 2; t++) {
+        if (tb[t]->on_device && tb[t]->rows > 0 && ((uintptr_t)tb[t]->data & 15)) {   // unaligned device view: local copy, same path on every rank
+            int32_t *p = (int32_t *)smj_ws(c, t ? WS_T2 : WS_T1, (size_t)tb[t]->rows * cc[t] * 4);
+            if (!p) return SMJ_ENOMEM;
+            CUDA_TRY(cudaMemcpyAsync(p, tb[t]->data, (size_t)tb[t]->rows * cc[t] * 4, cudaMemcpyDeviceToDevice, c->stream));
+            d_t[t] = p;
+        } else SMJ_TRY(smj_stage_in(c, tb[t], t ? WS_T2 : WS_T1, &d_t[t]));
+    }
     CUDA_TRY(cudaEventRecord(ev[E_H2D], c->stream));
 
     // ---- 1. splitters: regular row samples of both tables on every rank (predicate applied), all-gathered
     const int S = G <= 4 ? 1024 : 4096 / G;          // <= 8192 samples in all: one CTA sorts them in shared memory
-    const int MSG = 2 * (G + 1) + 2;                   // per-rank count message: bucket starts of both tables + receive capacities
+    const int MSG = 2 * (G + 1);                       // per-rank count message: bucket starts of both tables
     u32 *d_samp = (u32 *)smj_ws(c, WS_SAMPLES, (size_t)(2 * S) * 4 * (G + 1) + 4096 + (size_t)MSG * 8 * (G + 1) + 1024);
     if (!d_samp) return SMJ_ENOMEM;
     u32 *d_samp_all = d_samp + 2 * S;
     u32 *d_split = d_samp_all + (size_t)G * 2 * S;
     u64 *d_msg = (u64 *)(d_split + 16);                // [MSG]
     u64 *d_msg_all = d_msg + MSG;                      // [G][MSG]
-    int32_t **d_dst = (int32_t **)(d_msg_all + (size_t)G * MSG);   // [2][8] destination pointers per bucket
-    unsigned char *d_hnd = (unsigned char *)(d_dst + 16);          // [G+1][2][64] IPC handles
     for (int t = 0; t < 2; t++)
         SMJ_TRY(smj_launch_sample_rows(c, d_t[t], tb[t]->rows, cc[t], sel_col[t], sel_val[t], key[t], S, d_samp + t * S));
     NCCL_TRY(g_nccl.AllGather(d_samp, d_samp_all, (size_t)2 * S, ncclUint32, g_dist.comm, c->stream));
-    CUDA_TRY(cudaEventRecord(ev[E_SAMP], c->stream));
-    char *hp = (char *)c->h_pinned;                    // small pinned mailbox for the host legs below
     SMJ_TRY(smj_launch_splitters(c, d_samp_all, G * 2 * S, G, d_split));   // same samples, same kernel, same splitters on every rank
-    CUDA_TRY(cudaEventRecord(ev[E_SPLIT], c->stream));
 
     // ---- 2. select + partition of the rows by destination rank (rows grouped by bucket inside every tile's slot)
     int32_t *slots[2];
     char *pscr[2];
-    u64 *d_bs[2];
     int none[2];
     for (int t = 0; t < 2; t++) {
         const size_t cells = (size_t)tb[t]->rows * cc[t];
@@ -310,24 +1007,20 @@ int smj_run_multi(const smj_config_t *cfg, const smj_table_t *t1, const smj_tabl
         pscr[t] = (char *)smj_ws(c, t ? WS_MERGE_B : WS_MERGE_A, smj_partition_scratch_bytes(tb[t]->rows, cc[t]));
         if (!slots[t] || !pscr[t]) return SMJ_ENOMEM;
         none[t] = (sel_val[t] >= (int64_t)INT32_MAX) ? 1 : 0;
-        SMJ_TRY(smj_launch_select_partition(c, d_t[t], tb[t]->rows, cc[t], sel_col[t], sel_val[t], key[t], d_split, G, slots[t], pscr[t], &d_bs[t]));
-        CUDA_TRY(cudaMemcpyAsync(d_msg + t * (G + 1), d_bs[t], (size_t)(G + 1) * 8, cudaMemcpyDeviceToDevice, c->stream));
+        SMJ_TRY(smj_launch_select_partition(c, c->stream, d_t[t], tb[t]->rows, cc[t], sel_col[t], sel_val[t], key[t], d_split, G, slots[t], pscr[t]));
+        const SmjPartScratch PS = smj_partition_scratch(pscr[t], none[t] ? 0 : tb[t]->rows, cc[t]);
+        CUDA_TRY(cudaMemcpyAsync(d_msg + t * (G + 1), PS.bucket_start, (size_t)(G + 1) * 8, cudaMemcpyDeviceToDevice, c->stream));
     }
-    // receive capacities (rows) ride along so that every rank knows who must grow its buffer this step
-    uint64_t *hp_cap = (uint64_t *)(hp + 2048);
-    for (int t = 0; t < 2; t++) hp_cap[t] = (uint64_t)(c->slot_bytes[t ? WS_XCHG_RECV2 : WS_XCHG_RECV1] / ((size_t)cc[t] * 4));
-    CUDA_TRY(cudaMemcpyAsync(d_msg + 2 * (G + 1), hp_cap, 16, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(cudaEventRecord(ev[E_PART], c->stream));
 
-    // ---- 3. the G x G row-count matrix
+    // ---- 3. the G x G row-count matrix, waited for on the host
     NCCL_TRY(g_nccl.AllGather(d_msg, d_msg_all, (size_t)MSG, ncclUint64, g_dist.comm, c->stream));
-    CUDA_TRY(cudaEventRecord(ev[E_CNT], c->stream));
-    uint64_t *h_msg = (uint64_t *)(hp + 4096);         // [G][MSG] <= 8 * 20 * 8 bytes
+    uint64_t *h_msg = (uint64_t *)((char *)c->h_pinned + 4096);         // [G][MSG] <= 8 * 18 * 8 bytes
     CUDA_TRY(cudaMemcpyAsync(h_msg, d_msg_all, (size_t)G * MSG * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     std::vector<int64_t> counts[2], recv_off[2];
     int64_t recv_total[2], m[2];
-    bool someone_grows = false;
+    int too_big = 0;
     for (int t = 0; t < 2; t++) {
         counts[t].assign((size_t)G * G, 0);
         recv_off[t].assign((size_t)G, 0);
@@ -338,107 +1031,46 @@ int smj_run_multi(const smj_config_t *cfg, const smj_table_t *t1, const smj_tabl
             }
         SMJ_TRY(smj_plan_exchange(counts[t].data(), G, me, recv_off[t].data(), &recv_total[t]));
         m[t] = (int64_t)h_msg[(size_t)me * MSG + (size_t)t * (G + 1) + G];
-        if (recv_total[t] > SMJ_MAX_SORT_ROWS)
-            return smj_set_error(SMJ_ETOOBIG, "rank %d would receive %lld rows of table %d (limit 2^30 - 1 per GPU)", me, (long long)recv_total[t], t + 1);
-        for (int r = 0; r < G; r++) {                  // the same verdict on every rank: does rank r have to grow table t?
+        for (int r = 0; r < G; r++) {   // every rank checks every rank's share: the refusal is collective
             int64_t tot = 0;
             for (int src = 0; src < G; src++) tot += counts[t][(size_t)src * G + r];
-            const uint64_t cap = h_msg[(size_t)r * MSG + 2 * (G + 1) + t];
-            if ((uint64_t)tot > cap || !g_peer[t][r].have) someone_grows = true;
+            if (tot > SMJ_MAX_SORT_ROWS) too_big = t + 1;
         }
     }
-    int32_t *recv[2];
+    if (too_big) return smj_set_error(SMJ_ETOOBIG, "a rank would receive more than 2^30 - 1 rows of table %d", too_big);
+    int32_t *recv[2], *send[2];
     for (int t = 0; t < 2; t++) {
-        // 25 % head room so that a slightly different split next step does not force a re-map on every rank
-        const size_t want = (size_t)recv_total[t] * cc[t] * 4;
-        const int slot = t ? WS_XCHG_RECV2 : WS_XCHG_RECV1;
-        recv[t] = (int32_t *)smj_ws(c, slot, c->slot_bytes[slot] >= want ? want : want + want / 4);
-        if (!recv[t]) return SMJ_ENOMEM;
+        recv[t] = (int32_t *)smj_ws(c, t ? WS_XCHG_RECV2 : WS_XCHG_RECV1, (size_t)recv_total[t] * cc[t] * 4);
+        send[t] = (int32_t *)smj_ws(c, t ? WS_XCHG_SEND2 : WS_XCHG_SEND1, (size_t)tb[t]->rows * cc[t] * 4);
+        if (!recv[t] || !send[t]) return SMJ_ENOMEM;
     }
 
+    // ---- 4. send buffer (buckets contiguous) + one grouped ncclSend/ncclRecv all-to-all
     double sent_bytes = 0;
-    bool peer_ok = use_peer;
-    if (use_peer && someone_grows) {
-        // every rank publishes the IPC handles of its two receive buffers; peers map what changed
-        unsigned char *hp_h = (unsigned char *)(hp + 8192);        // [2][64] mine, then [G][2][64]
-        for (int t = 0; t < 2; t++) {
-            cudaIpcMemHandle_t hnd;
-            if (cudaIpcGetMemHandle(&hnd, recv[t]) != cudaSuccess) { cudaGetLastError(); memset(&hnd, 0, sizeof hnd); }
-            memcpy(hp_h + t * 64, &hnd, 64);
-        }
-        CUDA_TRY(cudaMemcpyAsync(d_hnd, hp_h, 128, cudaMemcpyHostToDevice, c->stream));
-        NCCL_TRY(g_nccl.AllGather(d_hnd, d_hnd + 128, 128, /*ncclUint8*/ 1, g_dist.comm, c->stream));
-        CUDA_TRY(cudaMemcpyAsync(hp_h + 128, d_hnd + 128, (size_t)G * 128, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
-        for (int r = 0; r < G; r++)
-            for (int t = 0; t < 2; t++) {
-                PeerMap &pm = g_peer[t][r];
-                const unsigned char *hb = hp_h + 128 + (size_t)r * 128 + t * 64;
-                if (r == me) { pm.have = true; pm.base = nullptr; continue; }
-                if (pm.have && memcmp(&pm.handle, hb, 64) == 0) continue;
-                if (pm.base) { cudaIpcCloseMemHandle(pm.base); pm.base = nullptr; }
-                memcpy(&pm.handle, hb, 64);
-                cudaError_t e = cudaIpcOpenMemHandle(&pm.base, pm.handle, cudaIpcMemLazyEnablePeerAccess);
-                pm.have = (e == cudaSuccess);
-                if (e != cudaSuccess) { cudaGetLastError(); pm.base = nullptr; peer_ok = false; }
-            }
-        // all ranks must agree on the path: one failed mapping anywhere sends everybody to NCCL for this step
-        uint64_t *hp_ok = (uint64_t *)(hp + 3072);
-        *hp_ok = peer_ok ? 1 : 0;
-        CUDA_TRY(cudaMemcpyAsync(d_msg, hp_ok, 8, cudaMemcpyHostToDevice, c->stream));
-        NCCL_TRY(g_nccl.AllGather(d_msg, d_msg_all, 1, ncclUint64, g_dist.comm, c->stream));
-        CUDA_TRY(cudaMemcpyAsync(h_msg, d_msg_all, (size_t)G * 8, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
-        for (int r = 0; r < G; r++) if (!h_msg[r]) peer_ok = false;
-        if (!peer_ok) for (int t = 0; t < 2; t++) for (int r = 0; r < G; r++) g_peer[t][r].have = false;   // try again next step
+    for (int t = 0; t < 2; t++) {
+        const SmjPartScratch PS = smj_partition_scratch(pscr[t], none[t] ? 0 : tb[t]->rows, cc[t]);
+        SmjPartitionDst D = {};
+        for (int b = 0; b < G; b++) D.base[b] = send[t];
+        D.row0 = PS.bucket_start;
+        SMJ_TRY(smj_launch_partition_exchange(c, c->stream, tb[t]->rows, cc[t], none[t], G, slots[t], pscr[t], D));
     }
-
-    if (peer_ok) {
-        // ---- 4a. fused compaction + exchange: segments are stored straight into the owners' receive buffers (NVLink)
-        int32_t **hp_dst = (int32_t **)(hp + 3200);
-        for (int t = 0; t < 2; t++)
-            for (int b = 0; b < 8; b++) {
-                int32_t *p = nullptr;
-                if (b < G) {
-                    int64_t before = 0;                              // rows the lower ranks put in front of mine at rank b
-                    for (int src = 0; src < me; src++) before += counts[t][(size_t)src * G + b];
-                    int32_t *base = (b == me) ? recv[t] : (int32_t *)g_peer[t][b].base;
-                    p = base + (size_t)before * cc[t];
-                    if (b != me) sent_bytes += (double)counts[t][(size_t)me * G + b] * cc[t] * 4;
-                }
-                hp_dst[t * 8 + b] = p;
+    NCCL_TRY(g_nccl.GroupStart());
+    for (int t = 0; t < 2; t++) {
+        const uint64_t *mine = h_msg + (size_t)me * MSG + (size_t)t * (G + 1);
+        for (int peer = 0; peer < G; peer++) {
+            const int64_t scount = counts[t][(size_t)me * G + peer] * cc[t];
+            const int64_t rcount = counts[t][(size_t)peer * G + me] * cc[t];
+            const int32_t *sbuf = send[t] + (size_t)mine[peer] * cc[t];
+            int32_t *rbuf = recv[t] + (size_t)recv_off[t][peer] * cc[t];
+            if (peer == me) {
+                if (scount) CUDA_TRY(cudaMemcpyAsync(rbuf, sbuf, (size_t)scount * 4, cudaMemcpyDeviceToDevice, c->stream));
+                continue;
             }
-        CUDA_TRY(cudaMemcpyAsync(d_dst, hp_dst, 16 * sizeof(int32_t *), cudaMemcpyHostToDevice, c->stream));
-        for (int t = 0; t < 2; t++)
-            SMJ_TRY(smj_launch_partition_compact(c, tb[t]->rows, cc[t], none[t], G, slots[t], pscr[t], nullptr, d_dst + t * 8));
-        // every rank's stores must have landed before anybody sorts: a collective after the kernels is that barrier
-        NCCL_TRY(g_nccl.AllGather(d_msg, d_msg_all, 1, ncclUint64, g_dist.comm, c->stream));
-    } else {
-        // ---- 4b. send buffer + one grouped ncclSend/ncclRecv all-to-all
-        int32_t *send[2];
-        for (int t = 0; t < 2; t++) {
-            send[t] = (int32_t *)smj_ws(c, t ? WS_XCHG_SEND2 : WS_XCHG_SEND1, (size_t)tb[t]->rows * cc[t] * 4);
-            if (!send[t]) return SMJ_ENOMEM;
-            SMJ_TRY(smj_launch_partition_compact(c, tb[t]->rows, cc[t], none[t], G, slots[t], pscr[t], send[t], nullptr));
+            if (scount) { NCCL_TRY(g_nccl.Send(sbuf, (size_t)scount, ncclInt32, peer, g_dist.comm, c->stream)); sent_bytes += (double)scount * 4; }
+            if (rcount) NCCL_TRY(g_nccl.Recv(rbuf, (size_t)rcount, ncclInt32, peer, g_dist.comm, c->stream));
         }
-        NCCL_TRY(g_nccl.GroupStart());
-        for (int t = 0; t < 2; t++) {
-            const uint64_t *mine = h_msg + (size_t)me * MSG + (size_t)t * (G + 1);
-            for (int peer = 0; peer < G; peer++) {
-                const int64_t scount = counts[t][(size_t)me * G + peer] * cc[t];
-                const int64_t rcount = counts[t][(size_t)peer * G + me] * cc[t];
-                const int32_t *sbuf = send[t] + (size_t)mine[peer] * cc[t];
-                int32_t *rbuf = recv[t] + (size_t)recv_off[t][peer] * cc[t];
-                if (peer == me) {
-                    if (scount) CUDA_TRY(cudaMemcpyAsync(rbuf, sbuf, (size_t)scount * 4, cudaMemcpyDeviceToDevice, c->stream));
-                    continue;
-                }
-                if (scount) { NCCL_TRY(g_nccl.Send(sbuf, (size_t)scount, ncclInt32, peer, g_dist.comm, c->stream)); sent_bytes += (double)scount * 4; }
-                if (rcount) NCCL_TRY(g_nccl.Recv(rbuf, (size_t)rcount, ncclInt32, peer, g_dist.comm, c->stream));
-            }
-        }
-        NCCL_TRY(g_nccl.GroupEnd());
     }
+    NCCL_TRY(g_nccl.GroupEnd());
     CUDA_TRY(cudaEventRecord(ev[E_XCHG], c->stream));
 
     // ---- 5. this rank's key range: the single-GPU pipeline on the received rows, select disabled.  Runs arrived in
@@ -450,10 +1082,6 @@ int smj_run_multi(const smj_config_t *cfg, const smj_table_t *t1, const smj_tabl
     const smj_table_t r1 = {recv[0], recv_total[0], cc[0], 1}, r2 = {recv[1], recv_total[1], cc[1], 1};
     smj_stats_t ls;
     SMJ_TRY(smj_run_single(c, &local, &r1, &r2, out, &ls));
-    if (trace && me == 0)
-        fprintf(stderr, "[dist] %s exchange; dev ms: samples+allgather %.3f | splitters %.3f | select/partition %.3f | counts %.3f | compaction+exchange %.3f | local %.3f\n",
-                peer_ok ? "peer-store" : "nccl", dist_ev_ms(ev[E_H2D], ev[E_SAMP]), dist_ev_ms(ev[E_SAMP], ev[E_SPLIT]),
-                dist_ev_ms(ev[E_SPLIT], ev[E_PART]), dist_ev_ms(ev[E_PART], ev[E_CNT]), dist_ev_ms(ev[E_CNT], ev[E_XCHG]), ls.total_device_ms);
     if (cfg->debug) {
         printf("==================\n#   exchange.cu  #\n==================\n");
         for (int t = 0; t < 2; t++)
@@ -464,8 +1092,8 @@ int smj_run_multi(const smj_config_t *cfg, const smj_table_t *t1, const smj_tabl
         *stats = ls;
         stats->h2d_ms = dist_ev_ms(ev[E_START], ev[E_H2D]);
         stats->select_ms = dist_ev_ms(ev[E_H2D], ev[E_PART]);          // samples + splitters + select/partition of both tables
-        stats->exchange_ms = dist_ev_ms(ev[E_PART], ev[E_XCHG]);       // count all-gather + compaction/exchange
-        stats->sort_ms = ls.select_ms + ls.sort_ms;                     // pairs of the received rows + the four passes
+        stats->exchange_ms = dist_ev_ms(ev[E_PART], ev[E_XCHG]);       // count all-gather + compaction + all-to-all
+        stats->sort_ms = ls.select_ms + ls.sort_ms;                     // pairs of the received rows + the radix passes
         stats->merge_ms = 0;
         stats->total_device_ms = dist_ev_ms(ev[E_H2D], c->ev[4]);      // through smj_run_single's end-of-join event
         for (int t = 0; t < 2; t++) { stats->rows_in[t] = tb[t]->rows; stats->rows_selected[t] = m[t]; }

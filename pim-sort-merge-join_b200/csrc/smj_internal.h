@@ -19,12 +19,15 @@ struct SmjCtx {
     int device = -1;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
+    cudaMemPool_t pool = nullptr;    // private stream-ordered pool of the output buffers
+    size_t l2_fetch_saved = 0;       // the device's cudaLimitMaxL2FetchGranularity before this library changed it
+    bool l2_fetch_set = false;
     u32 *d_err = nullptr;            // device-side consistency flag (bounded spins, bad partitions)
     void *h_pinned = nullptr;        // small pinned mailbox for counts / histograms
     size_t h_pinned_bytes = 0;
     int64_t launches = 0;
     // grow-only workspace slots (no cudaMalloc in steady state)
-    static const int kSlots = 24;
+    static const int kSlots = 32;
     void *slot[kSlots] = {};
     size_t slot_bytes[kSlots] = {};
     cudaEvent_t ev[16] = {};
@@ -57,7 +60,29 @@ enum SmjSlot {
     WS_TMP_ROWS, WS_TMP_ROWS2,       // staging for in-place sort / host outputs
     WS_XCHG_SEND1, WS_XCHG_SEND2, WS_XCHG_RECV1, WS_XCHG_RECV2, WS_SAMPLES,
     WS_MERGE_A, WS_MERGE_B, WS_RADIX, WS_MATCH_DENSE, WS_BLOOM,
+    WS_DIST_RECV1, WS_DIST_RECV2,    // peer-mapped receive buffers of the key-range exchange (smj_dist.cu)
+    WS_ROWSTORE1, WS_ROWSTORE2,
 };
+
+// One smj_run device pipeline in flight on a context: prepare -> enqueue -> finish (smj_api.cu).
+struct SmjRun {
+    smj_config_t cfg;
+    smj_table_t tb[2];
+    const u64 *d_rows[2] = {nullptr, nullptr};   // device-resident row counts (tb[t].rows is then an upper bound)
+    const int32_t *d_t[2] = {nullptr, nullptr};
+    int c_out = 0;
+    int64_t j_max = 0, launches0 = 0;
+    size_t stiles[2] = {}, rb[2] = {}, jt = 0, off_sel = 0, off_radix = 0, off_join = 0, zero_bytes = 0;
+    char *scr = nullptr;
+    u64 *ping[2] = {}, *pong[2] = {};
+    uint2 *mm = nullptr, *md = nullptr;
+    smj_table_t dev_out = {nullptr, 0, 0, 1};
+    bool prepared = false, replayed = false;
+};
+int  smj_run_prepare(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, const u64 *const *d_rows, SmjRun *R);
+int  smj_run_enqueue(SmjCtx *c, SmjRun *R);
+int  smj_run_finish(SmjCtx *c, SmjRun *R, smj_table_t *out, smj_stats_t *stats);
+void smj_run_abandon(SmjCtx *c, SmjRun *R);
 
 int   smj_set_error(int code, const char *fmt, ...);
 int   smj_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
@@ -139,6 +164,7 @@ struct SmjSelectJob {
     SmjSortPlan *plan;    // zeroed
     u64 *d_sel_count;     // zeroed; out: rows that passed the predicate (smj_stats_t.rows_selected)
     u64 *d_kept_count;    // zeroed; out: of those, the rows whose key bit was set in the other table's bitmap
+    const u64 *n_dev;     // device-resident row count (may be null); n is then the upper bound the buffers were sized for
 };
 // returns 1 (nothing launched) when a table cannot take the TMA path
 int smj_launch_select_plan2(SmjCtx *c, const SmjSelectJob job[2]);
@@ -200,6 +226,28 @@ int smj_launch_join_many_expand(SmjCtx *c, const u64 *d_l, const u64 *d_r, const
 // d_out_indirect (may be null): device cell holding the output pointer, read instead of d_out (graph replay)
 int smj_launch_join_materialize(SmjCtx *c, const uint2 *d_dense, const u64 *d_nj, int64_t nj_max, const int32_t *d_t1, int c1,
                                 const int32_t *d_t2, int c2, int key2, int32_t *d_out, int32_t *const *d_out_indirect = nullptr);
+
+// ------------------------------------------------------------------ key-range partitioning of rows (smj_partition.cu)
+#define SMJ_MAX_G 8
+struct SmjPartScratch { u32 *counts, *off32; u64 *blocksum, *bucket_total, *bucket_start; size_t tiles, ctas, bytes; };
+// where the exchange kernel puts this rank's bucket b: behind base[b], row0[b] (+ the segment's offset inside the bucket) rows in
+struct SmjPartitionDst {
+    int32_t *base[SMJ_MAX_G];
+    const u64 *row0;             // device [SMJ_MAX_G] (null: 0)
+    const u32 *skip;             // device flag (may be null): non-zero = store nothing (receive overflow, see smj_dist.cu)
+};
+bool smj_partition_supported(const int32_t *d_in, int cols);
+size_t smj_partition_tiles(int64_t n, int cols);
+u32 smj_partition_tile_rows(int cols);
+SmjPartScratch smj_partition_scratch(char *base, int64_t n, int cols);
+size_t smj_partition_scratch_bytes(int64_t n, int cols);
+int smj_launch_sample_rows(SmjCtx *c, const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val, int key_col, int S,
+                           u32 *d_samples);
+int smj_launch_select_partition(SmjCtx *c, cudaStream_t st, const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val,
+                                int key_col, const u32 *d_splitters, int G, int32_t *d_slots, char *d_scratch);
+int smj_launch_partition_exchange(SmjCtx *c, cudaStream_t st, int64_t n, int cols, int sel_val_none, int G, const int32_t *d_slots,
+                                  char *d_scratch, const SmjPartitionDst &D);
+int smj_launch_splitters(SmjCtx *c, const u32 *d_samples, int n_samples, int G, u32 *d_splitters);
 
 // ------------------------------------------------------------------ synth (smj_synth.cu)
 int smj_launch_synth(SmjCtx *c, int32_t *d_out, int64_t row0, int64_t rows, int64_t total_rows, int cols,

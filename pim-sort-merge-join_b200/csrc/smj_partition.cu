@@ -11,8 +11,8 @@
 //   select_partition_kernel : TMA-fed like select_tma_kernel (1 producer warp, 8 compute warps).  Per tile: predicate,
 //                             bucket id (<= 7 compares), per-(bucket,row group,warp) ballot counts, one 512-entry
 //                             scan, rows written to the tile's own slot ordered by bucket, G counts per tile.
-//   partition_scan_kernel   : offsets of every (bucket, tile) segment in the send buffer + bucket starts.
-//   partition_compact_kernel: one warp per segment copies it to its place.
+//   partition_blocksum / partition_offsets_kernel: offsets of every (bucket, tile) segment + bucket totals, many CTAs.
+//   partition_exchange_kernel: one warp per tile routes the tile's survivors to their buckets' destinations.
 //   sample_rows_kernel      : regular row samples (predicate applied) from which the splitters are derived.
 #include "smj_internal.h"
 #include "smj_dev.cuh"
@@ -24,7 +24,7 @@ constexpr int PT_WARPS = PT_THREADS / 32;
 constexpr int PT_IPT = 8;
 constexpr int PT_STAGES = 2;
 constexpr int PT_STAGE_BYTES = 32768;
-constexpr int PT_MAX_G = 8;
+constexpr int PT_MAX_G = SMJ_MAX_G;
 constexpr int PTW_THREADS = PT_THREADS + 32;
 constexpr int PT_ENTRIES = PT_MAX_G * PT_IPT * PT_WARPS;   // 512 = 2 per compute thread
 constexpr size_t PTW_SMEM = (size_t)PT_STAGES * PT_STAGE_BYTES;
@@ -168,67 +168,185 @@ select_partition_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int
     }
 }
 
-// off[t][b] = destination row of segment (tile t, bucket b) in the send buffer, segments ordered bucket-major then by
-// tile (= original row order inside a bucket); bucket_start[b] = first row of bucket b, bucket_start[G] = total.
-constexpr int PS_THREADS = 1024;
-__global__ void __launch_bounds__(PS_THREADS)
-partition_scan_kernel(const u32 *__restrict__ tile_counts, u32 num_tiles, int G, u64 *__restrict__ off, u64 *__restrict__ bucket_start)
+// ---- offsets of every (tile, bucket) segment, over many CTAs.
+// off32[t][b] = rows of bucket b in this rank's tiles before tile t (segments of one bucket in tile order = original row
+// order); bucket_total[b] = rows of bucket b on this rank; bucket_start[b] = first row of bucket b in a bucket-major send
+// buffer, bucket_start[G] = all survivors.  Two launches of ceil(tiles / PS_CHUNK) CTAs: CTA c first sums the eight bucket
+// counts of its PS_CHUNK tiles; then every CTA adds up the sums of the CTAs before it itself (a few hundred words at the
+// 2 B-row config, no CTA waits for another one) and scans its own chunk.  The first version was one CTA walking
+// tiles x G counts from global memory (11 us at 10 M rows; the same pattern cost 610 us per 488 K counts in the select scan).
+constexpr int PS_THREADS = 256;
+constexpr int PS_TPT = 8;                          // consecutive tiles per thread
+constexpr int PS_CHUNK = PS_THREADS * PS_TPT;      // 2048 tiles per CTA
+
+__device__ __forceinline__ void ps_load_tiles(const u32 *__restrict__ tile_counts, u32 num_tiles, u32 t0, u32 (&v)[PS_TPT][PT_MAX_G])
 {
-    __shared__ u64 s_w[PS_THREADS / 32];
-    const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
-    const u64 total_items = (u64)num_tiles * (u64)G;
-    const u64 chunk = (total_items + PS_THREADS - 1) / PS_THREADS;
-    const u64 lo = (u64)tid * chunk < total_items ? (u64)tid * chunk : total_items;
-    const u64 hi = lo + chunk < total_items ? lo + chunk : total_items;
-    u64 sum = 0;
-    for (u64 i = lo; i < hi; i++) { const u32 b = (u32)(i / num_tiles), t = (u32)(i % num_tiles); sum += tile_counts[(size_t)t * PT_MAX_G + b]; }
-    u64 inc = sum;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const u64 t = __shfl_up_sync(FULL_MASK, inc, o);
-        if (lane >= (u32)o) inc += t;
-    }
-    if (lane == 31) s_w[w] = inc;
-    __syncthreads();
-    u64 run = inc - sum;
-    for (u32 ww = 0; ww < w; ww++) run += s_w[ww];
-    if (tid == PS_THREADS - 1) bucket_start[G] = run + sum;
-    for (u64 i = lo; i < hi; i++) {
-        const u32 b = (u32)(i / num_tiles), t = (u32)(i % num_tiles);
-        if (t == 0) bucket_start[b] = run;
-        off[(size_t)t * PT_MAX_G + b] = run;
-        run += tile_counts[(size_t)t * PT_MAX_G + b];
+    for (int k = 0; k < PS_TPT; k++) {
+        uint4 a = make_uint4(0, 0, 0, 0), b = a;
+        if (t0 + k < num_tiles) {
+            a = __ldg(reinterpret_cast<const uint4 *>(tile_counts + (size_t)(t0 + k) * PT_MAX_G));
+            b = __ldg(reinterpret_cast<const uint4 *>(tile_counts + (size_t)(t0 + k) * PT_MAX_G) + 1);
+        }
+        v[k][0] = a.x; v[k][1] = a.y; v[k][2] = a.z; v[k][3] = a.w;
+        v[k][4] = b.x; v[k][5] = b.y; v[k][6] = b.z; v[k][7] = b.w;
     }
 }
 
-__global__ void __launch_bounds__(256)
-partition_compact_kernel(const int32_t *__restrict__ slots, const u32 *__restrict__ tile_counts, const u64 *__restrict__ off,
-                         const u64 *__restrict__ bucket_start, u32 num_tiles, int G, u32 tile_rows, int cols,
-                         int32_t *__restrict__ send, int32_t *const *__restrict__ dst_by_bucket)
+__global__ void __launch_bounds__(PS_THREADS)
+partition_blocksum_kernel(const u32 *__restrict__ tile_counts, u32 num_tiles, u64 *__restrict__ blocksum /*[ctas][8]*/)
 {
-    // dst_by_bucket (may be null): where the first row of this rank's bucket b goes -- the local receive buffer for the
-    // rank's own bucket, a PEER GPU's receive buffer (CUDA-IPC mapping, stores travel over NVLink) for the others.
-    // With it the compaction IS the exchange: no send buffer, no separate copy.
+    __shared__ u32 s_w[PS_THREADS / 32][PT_MAX_G];
+    PDL_ENTER();
+    const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+    u32 v[PS_TPT][PT_MAX_G];
+    ps_load_tiles(tile_counts, num_tiles, blockIdx.x * PS_CHUNK + tid * PS_TPT, v);
+#pragma unroll
+    for (int b = 0; b < PT_MAX_G; b++) {
+        u32 s = 0;
+#pragma unroll
+        for (int k = 0; k < PS_TPT; k++) s += v[k][b];
+        s = __reduce_add_sync(FULL_MASK, s);
+        if (lane == 0) s_w[w][b] = s;
+    }
+    __syncthreads();
+    if (tid < (u32)PT_MAX_G) {
+        u64 t = 0;
+#pragma unroll
+        for (int ww = 0; ww < PS_THREADS / 32; ww++) t += s_w[ww][tid];
+        blocksum[(size_t)blockIdx.x * PT_MAX_G + tid] = t;
+    }
+}
+
+__global__ void __launch_bounds__(PS_THREADS)
+partition_offsets_kernel(const u32 *__restrict__ tile_counts, u32 num_tiles, int G, const u64 *__restrict__ blocksum, u32 *__restrict__ off32,
+                         u64 *__restrict__ bucket_total /*[8]*/, u64 *__restrict__ bucket_start /*[G+1]*/)
+{
+    __shared__ u64 s_red[PS_THREADS / 32][2][PT_MAX_G];
+    __shared__ u32 s_w[PS_THREADS / 32][PT_MAX_G];
+    __shared__ u64 s_base[PT_MAX_G];
+    PDL_ENTER();
+    const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+    // sums of the CTAs before this one (base) and of all CTAs (total), per bucket
+    u64 before[PT_MAX_G] = {}, total[PT_MAX_G] = {};
+    for (u32 cta = tid; cta < gridDim.x; cta += PS_THREADS) {
+#pragma unroll
+        for (int b = 0; b < PT_MAX_G; b++) {
+            const u64 x = blocksum[(size_t)cta * PT_MAX_G + b];
+            total[b] += x;
+            if (cta < blockIdx.x) before[b] += x;
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < PT_MAX_G; b++) {
+        const u64 x = warp_sum(before[b]), y = warp_sum(total[b]);
+        if (lane == 0) { s_red[w][0][b] = x; s_red[w][1][b] = y; }
+    }
+    u32 v[PS_TPT][PT_MAX_G];
+    const u32 t0 = blockIdx.x * PS_CHUNK + tid * PS_TPT;
+    ps_load_tiles(tile_counts, num_tiles, t0, v);
+    u32 mine[PT_MAX_G], incl[PT_MAX_G];
+#pragma unroll
+    for (int b = 0; b < PT_MAX_G; b++) {
+        u32 s = 0;
+#pragma unroll
+        for (int k = 0; k < PS_TPT; k++) s += v[k][b];
+        mine[b] = s;
+        incl[b] = warp_incl_scan(s);
+        if (lane == 31) s_w[w][b] = incl[b];
+    }
+    __syncthreads();
+    if (tid < (u32)PT_MAX_G) {
+        u64 x = 0, y = 0;
+#pragma unroll
+        for (int ww = 0; ww < PS_THREADS / 32; ww++) { x += s_red[ww][0][tid]; y += s_red[ww][1][tid]; }
+        s_base[tid] = x;
+        if (blockIdx.x == 0) bucket_total[tid] = y;
+        s_red[0][1][tid] = y;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && tid == 0) {
+        u64 run = 0;
+        for (int b = 0; b < G; b++) { bucket_start[b] = run; run += s_red[0][1][b]; }
+        bucket_start[G] = run;
+    }
+#pragma unroll
+    for (int b = 0; b < PT_MAX_G; b++) {
+        u32 run = (u32)s_base[b] + incl[b] - mine[b];
+        for (u32 ww = 0; ww < w; ww++) run += s_w[ww][b];
+#pragma unroll
+        for (int k = 0; k < PS_TPT; k++) { const u32 c = v[k][b]; v[k][b] = run; run += c; }
+    }
+#pragma unroll
+    for (int k = 0; k < PS_TPT; k++)
+        if (t0 + k < num_tiles) {
+            uint4 *o = reinterpret_cast<uint4 *>(off32 + (size_t)(t0 + k) * PT_MAX_G);
+            o[0] = make_uint4(v[k][0], v[k][1], v[k][2], v[k][3]);
+            o[1] = make_uint4(v[k][4], v[k][5], v[k][6], v[k][7]);
+        }
+}
+
+// The exchange.  A tile's survivors sit bucket-ordered and contiguous at the start of the tile's slot; segment (t, b) goes to
+// dst.base[b] + (row0[b] + off32[t][b]) rows -- dst.base[b] is the local send buffer (grouped ncclSend path), the rank's own
+// receive buffer (its own bucket) or a PEER GPU's receive buffer (peer mapping: the stores travel over NVLink from the SMs,
+// so the compaction IS the exchange).  One warp per tile: the tile's 8 counts and offsets arrive with two 32-byte loads,
+// then the warp walks the slot as a flat array of cells (16-byte words when rows are whole 16-byte multiples), PX_UNROLL
+// independent loads in flight per lane before the first store, each word routed to its bucket by comparing its index with
+// the bucket boundaries held in registers.  (The first version took one warp per SEGMENT: a dependent chain of count ->
+// offset -> data loads for every ~2 KB piece, 0.30 ms for 122 MB at 8 GPUs.)
+constexpr int PX_UNROLL = 4;
+
+template <typename W>   // W = int4 (rows are multiples of 16 bytes and every pointer is 16-byte aligned) or int32_t
+__global__ void __launch_bounds__(256)
+partition_exchange_kernel(const int32_t *__restrict__ slots, const u32 *__restrict__ tile_counts, const u32 *__restrict__ off32,
+                          u32 num_tiles, int G, u32 tile_rows, int cols, const SmjPartitionDst D)
+{
+    PDL_ENTER();
+    if (D.skip && *D.skip) return;
+    constexpr u32 CPW = sizeof(W) / 4;               // cells per word
+    const u32 wpr = (u32)cols / CPW;                 // words per row
     const u32 lane = threadIdx.x & 31u;
-    const u64 warps = (u64)gridDim.x * (blockDim.x >> 5);
-    const u64 segs = (u64)num_tiles * (u64)G;
-    for (u64 s = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s < segs; s += warps) {
-        const u32 t = (u32)(s / (u64)G), b = (u32)(s % (u64)G);
-        const u32 *tc = tile_counts + (size_t)t * PT_MAX_G;
-        const u32 cnt = tc[b];
-        if (cnt == 0) continue;
-        u32 before = 0;
-        for (u32 q = 0; q < b; q++) before += tc[q];
-        const int32_t *src = slots + ((size_t)t * tile_rows + before) * cols;
-        int32_t *dst = dst_by_bucket ? dst_by_bucket[b] + (off[(size_t)t * PT_MAX_G + b] - bucket_start[b]) * (u64)cols
-                                     : send + off[(size_t)t * PT_MAX_G + b] * (u64)cols;
-        const u32 cells = cnt * (u32)cols;
-        if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
-            const u32 v = cells >> 2;
-            for (u32 i = lane; i < v; i += 32) reinterpret_cast<int4 *>(dst)[i] = reinterpret_cast<const int4 *>(src)[i];
-            for (u32 i = (v << 2) + lane; i < cells; i += 32) dst[i] = src[i];
-        } else {
-            for (u32 i = lane; i < cells; i += 32) dst[i] = src[i];
+    const u32 warps = gridDim.x * (blockDim.x >> 5);
+    for (u32 t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < num_tiles; t += warps) {
+        u32 cnt = 0, off = 0;
+        u64 r0 = 0;
+        if (lane < (u32)G) {
+            cnt = tile_counts[(size_t)t * PT_MAX_G + lane];
+            off = off32[(size_t)t * PT_MAX_G + lane];
+            r0 = D.row0 ? D.row0[lane] : 0ull;
+        }
+        const u32 incl = warp_incl_scan(cnt);
+        const u32 total_w = __shfl_sync(FULL_MASK, incl, PT_MAX_G - 1) * wpr;
+        if (total_w == 0) continue;
+        // per bucket: first word of its segment inside the slot, and where that word goes
+        u32 start_w[PT_MAX_G];
+        W *dstp[PT_MAX_G];
+#pragma unroll
+        for (int b = 0; b < PT_MAX_G; b++) {
+            start_w[b] = (__shfl_sync(FULL_MASK, incl, b) - __shfl_sync(FULL_MASK, cnt, b)) * wpr;
+            const u64 row = __shfl_sync(FULL_MASK, r0, b) + (u64)__shfl_sync(FULL_MASK, off, b);
+            dstp[b] = reinterpret_cast<W *>(D.base[b]) + row * wpr;
+        }
+        const W *src = reinterpret_cast<const W *>(slots + (size_t)t * tile_rows * cols);
+        for (u32 i0 = 0; i0 < total_w; i0 += 32 * PX_UNROLL) {
+            W v[PX_UNROLL];
+#pragma unroll
+            for (int k = 0; k < PX_UNROLL; k++) {
+                const u32 i = i0 + k * 32 + lane;
+                if (i < total_w) v[k] = __ldcs(src + i);   // read once
+            }
+#pragma unroll
+            for (int k = 0; k < PX_UNROLL; k++) {
+                const u32 i = i0 + k * 32 + lane;
+                if (i < total_w) {
+                    W *d = dstp[0];
+                    u32 s = 0;
+#pragma unroll
+                    for (int b = 1; b < PT_MAX_G; b++)
+                        if (b < G && i >= start_w[b]) { d = dstp[b]; s = start_w[b]; }
+                    d[i - s] = v[k];
+                }
+            }
         }
     }
 }
@@ -300,8 +418,24 @@ int pt_ipt(int cols)
 
 bool smj_partition_supported(const int32_t *d_in, int cols) { return cols <= PT_MAX_COLS && ((uintptr_t)d_in & 15) == 0; }
 size_t smj_partition_tiles(int64_t n, int cols) { const int64_t tr = (int64_t)pt_ipt(cols) * PT_THREADS; return (size_t)((n + tr - 1) / tr); }
-// scratch: [tile_counts u32 tiles*8][off u64 tiles*8][bucket_start u64 16]
-size_t smj_partition_scratch_bytes(int64_t n, int cols) { return smj_partition_tiles(n, cols) * PT_MAX_G * 12 + 256; }
+u32 smj_partition_tile_rows(int cols) { return (u32)(pt_ipt(cols) * PT_THREADS); }
+
+// scratch of one table: [tile_counts u32 tiles*8][off32 u32 tiles*8][blocksum u64 ctas*8][bucket_total u64 8][bucket_start u64 9]
+SmjPartScratch smj_partition_scratch(char *base, int64_t n, int cols)
+{
+    SmjPartScratch s;
+    s.tiles = smj_partition_tiles(n, cols);
+    s.ctas = (s.tiles + PS_CHUNK - 1) / PS_CHUNK;
+    const size_t tb = align_up(s.tiles * PT_MAX_G * 4, 256);
+    s.counts = (u32 *)base;
+    s.off32 = (u32 *)(base + tb);
+    s.blocksum = (u64 *)(base + 2 * tb);
+    s.bucket_total = s.blocksum + (s.ctas ? s.ctas : 1) * PT_MAX_G;
+    s.bucket_start = s.bucket_total + PT_MAX_G;
+    s.bytes = 2 * tb + ((s.ctas ? s.ctas : 1) * PT_MAX_G + PT_MAX_G + PT_MAX_G + 1) * 8 + 256;
+    return s;
+}
+size_t smj_partition_scratch_bytes(int64_t n, int cols) { return smj_partition_scratch(nullptr, n, cols).bytes; }
 
 int smj_launch_sample_rows(SmjCtx *c, const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val, int key_col, int S,
                            u32 *d_samples)
@@ -314,21 +448,17 @@ int smj_launch_sample_rows(SmjCtx *c, const int32_t *d_in, int64_t n, int cols, 
     return SMJ_OK;
 }
 
-// Stage 1: rows of d_in that pass the predicate, grouped by destination bucket inside each tile's slot (d_slots:
-// n*cols cells of scratch), with the per-tile counts, every segment's offset and the bucket starts (G+1 u64 row
-// offsets, returned in *d_bucket_start, inside d_scratch of smj_partition_scratch_bytes).
-int smj_launch_select_partition(SmjCtx *c, const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val, int key_col,
-                                const u32 *d_splitters, int G, int32_t *d_slots, char *d_scratch, u64 **d_bucket_start)
+// Stage 1 (on stream st): rows of d_in that pass the predicate, grouped by destination bucket inside each tile's slot (d_slots:
+// n*cols cells of scratch), then the per-tile counts, every segment's offset inside its bucket, the bucket totals and
+// the bucket starts (d_scratch: smj_partition_scratch).
+int smj_launch_select_partition(SmjCtx *c, cudaStream_t st, const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val,
+                                int key_col, const u32 *d_splitters, int G, int32_t *d_slots, char *d_scratch)
 {
-    const size_t tiles = smj_partition_tiles(n, cols);
-    u32 *d_counts = (u32 *)d_scratch;
-    u64 *d_off = (u64 *)(d_scratch + align_up(tiles * PT_MAX_G * 4, 8));
-    u64 *d_bs = d_off + tiles * PT_MAX_G;
-    *d_bucket_start = d_bs;
     if (G < 1 || G > PT_MAX_G) return smj_set_error(SMJ_EINVAL, "select_partition: %d buckets (max %d)", G, PT_MAX_G);
     int select_all = sel_val < (int64_t)INT32_MIN;
     if (!select_all && sel_val >= (int64_t)INT32_MAX) n = 0;
-    if (n <= 0) { CUDA_TRY(cudaMemsetAsync(d_bs, 0, (size_t)(G + 1) * 8, c->stream)); return SMJ_OK; }
+    const SmjPartScratch S = smj_partition_scratch(d_scratch, n > 0 ? n : 0, cols);
+    if (n <= 0) { CUDA_TRY(cudaMemsetAsync(S.bucket_total, 0, (size_t)(2 * PT_MAX_G + 1) * 8, st)); return SMJ_OK; }
     static bool attr_set[16] = {};
     if (!attr_set[c->device & 15]) {
         CUDA_TRY(cudaFuncSetAttribute(select_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PTW_SMEM));
@@ -337,31 +467,32 @@ int smj_launch_select_partition(SmjCtx *c, const int32_t *d_in, int64_t n, int c
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     const int ipt = pt_ipt(cols);
-    const u32 grid = tiles < (size_t)(sms * 3) ? (u32)tiles : (u32)(sms * 3);
-    select_partition_kernel<<<grid, PTW_THREADS, PTW_SMEM, c->stream>>>(d_in, n, cols, ipt, sel_col, (int32_t)sel_val, select_all, key_col,
-                                                                       d_splitters, G, d_slots, d_counts, (u32)tiles);
+    const u32 grid = S.tiles < (size_t)(sms * 3) ? (u32)S.tiles : (u32)(sms * 3);
+    select_partition_kernel<<<grid, PTW_THREADS, PTW_SMEM, st>>>(d_in, n, cols, ipt, sel_col, (int32_t)sel_val, select_all, key_col,
+                                                                d_splitters, G, d_slots, S.counts, (u32)S.tiles);
     KERNEL_CHECK(c);
-    partition_scan_kernel<<<1, PS_THREADS, 0, c->stream>>>(d_counts, (u32)tiles, G, d_off, d_bs);
+    partition_blocksum_kernel<<<(u32)S.ctas, PS_THREADS, 0, st>>>(S.counts, (u32)S.tiles, S.blocksum);
+    KERNEL_CHECK(c);
+    partition_offsets_kernel<<<(u32)S.ctas, PS_THREADS, 0, st>>>(S.counts, (u32)S.tiles, G, S.blocksum, S.off32, S.bucket_total, S.bucket_start);
     KERNEL_CHECK(c);
     return SMJ_OK;
 }
 
-// Stage 2: every (tile, bucket) segment to its place: in d_send (buckets contiguous, for ncclSend) when d_dst_by_bucket is
-// null, else straight into the destination ranks' receive buffers (device array of G pointers).
-int smj_launch_partition_compact(SmjCtx *c, int64_t n, int cols, int sel_val_none, int G, const int32_t *d_slots, char *d_scratch,
-                                 int32_t *d_send, int32_t *const *d_dst_by_bucket)
+// Stage 2 (on stream st): every (tile, bucket) segment to its place behind D.base[bucket] (see partition_exchange_kernel).
+int smj_launch_partition_exchange(SmjCtx *c, cudaStream_t st, int64_t n, int cols, int sel_val_none, int G, const int32_t *d_slots,
+                                  char *d_scratch, const SmjPartitionDst &D)
 {
     if (n <= 0 || sel_val_none) return SMJ_OK;
-    const size_t tiles = smj_partition_tiles(n, cols);
-    const u32 *d_counts = (const u32 *)d_scratch;
-    const u64 *d_off = (const u64 *)(d_scratch + align_up(tiles * PT_MAX_G * 4, 8));
-    const u64 *d_bs = d_off + tiles * PT_MAX_G;
+    const SmjPartScratch S = smj_partition_scratch(d_scratch, n, cols);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    const u64 segs = (u64)tiles * G;
-    const u32 cgrid = (u32)((segs + 7) / 8 < (u64)sms * 8 ? (segs + 7) / 8 : (u64)sms * 8);
-    partition_compact_kernel<<<cgrid, 256, 0, c->stream>>>(d_slots, d_counts, d_off, d_bs, (u32)tiles, G, (u32)(pt_ipt(cols) * PT_THREADS), cols,
-                                                           d_send, d_dst_by_bucket);
+    const u32 cgrid = (u32)((S.tiles + 7) / 8 < (size_t)sms * 8 ? (S.tiles + 7) / 8 : (size_t)sms * 8);
+    uintptr_t al = (uintptr_t)d_slots;
+    for (int b = 0; b < G; b++) al |= (uintptr_t)D.base[b];
+    if (cols % 4 == 0 && (al & 15) == 0)
+        partition_exchange_kernel<int4><<<cgrid, 256, 0, st>>>(d_slots, S.counts, S.off32, (u32)S.tiles, G, smj_partition_tile_rows(cols), cols, D);
+    else
+        partition_exchange_kernel<int32_t><<<cgrid, 256, 0, st>>>(d_slots, S.counts, S.off32, (u32)S.tiles, G, smj_partition_tile_rows(cols), cols, D);
     KERNEL_CHECK(c);
     return SMJ_OK;
 }

@@ -37,7 +37,7 @@ class Stats(C.Structure):
                 ("d2h_ms", C.c_double), ("total_device_ms", C.c_double),
                 ("rows_in", C.c_int64 * 2), ("rows_selected", C.c_int64 * 2), ("rows_joined", C.c_int64),
                 ("bytes_model", C.c_double), ("bytes_nvlink", C.c_double), ("kernel_launches", C.c_int64),
-                ("sort_pass_ms_avg", C.c_double), ("sort_passes", C.c_int32), ("reserved", C.c_int32),
+                ("sort_pass_ms_avg", C.c_double), ("sort_passes", C.c_int32), ("graph_replayed", C.c_int32),
                 ("sort_pass_bytes_avg", C.c_double), ("bytes_planned", C.c_double)]
 
     def as_dict(self):

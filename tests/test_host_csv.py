@@ -113,13 +113,22 @@ def test_csv_roundtrip_large(csvlib, tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("nr_gpus", [1, 2, 4])
 @pytest.mark.parametrize("case", ["g1", "g2", "kat2", "kat4"])
-def test_c_driver_end_to_end(case, golden, golden_csv, tmp_path):
-    """./app data1.csv data2.csv -> data/result.csv, byte-identical to the reference's result (default user.h knobs)."""
+def test_c_driver_end_to_end(case, nr_gpus, golden, golden_csv, tmp_path):
+    """./app data1.csv data2.csv -> data/result.csv, byte-identical to the reference's result (default user.h knobs).
+    SMJ_NR_GPUS = G > 1 (the NR_DPUS knob's successor): ONE process deals the rows to G devices (app.c:155-218), the
+    key-range exchange runs over peer memory, and the shards come back in key order as one result.csv (app.c:739-753)."""
+    import smj_b200
+    if smj_b200.lib().smj_device_count() < nr_gpus:
+        pytest.skip(f"needs {nr_gpus} GPUs")
     subprocess.run(["make", "-s", "-C", HOST], check=True)
     (tmp_path / "data").mkdir()
+    env = dict(os.environ, SMJ_NR_GPUS=str(nr_gpus))
+    if nr_gpus == 4 and case == "g2":
+        env["SMJ_CSV"] = "host"   # host tables dealt to the devices (the GPU CSV parser's device tables travel over NVLink otherwise)
     r = subprocess.run([os.path.join(HOST, "app"), golden_csv(f"{case}_data1.csv"), golden_csv(f"{case}_data2.csv")],
-                       cwd=tmp_path, capture_output=True, text=True, timeout=300)
+                       cwd=tmp_path, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     g = golden["cases"][case]
     assert hashlib.sha256(open(tmp_path / "data" / "result.csv", "rb").read()).hexdigest() == g["sha256"]
