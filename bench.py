@@ -24,9 +24,11 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: rows1, rows2, cols, selectivity, key_domain (0 = 3n as data/generate_data.py:9)
     "c2": dict(n1=10_000_000, n2=10_000_000, cols=4, sel=0.5, desc="synthetic 10M x 10M rows, 4 int32 cols, uniform unique int32 keys, select selectivity 50%"),
-    "c3": dict(n1=200_000_000, n2=200_000_000, cols=4, sel=1.0, kind=1, key_domain=20_000_000,
-               desc="synthetic 200M x 200M rows, 4 int32 cols, heavy duplicates (uniform over 20M keys, ~10 rows per key per side; "
-                    "the Zipf(1.1) generator of BASELINE config 3 exists at test size only), zip semantics"),
+    "c3": dict(n1=200_000_000, n2=200_000_000, cols=4, sel=1.0, kind=2, key_domain=1 << 20,
+               desc="synthetic 200M x 200M rows, 4 int32 cols, Zipf(1.1) keys over a 2^20-key domain (key 1 holds ~12 % of the rows: "
+                    "one ~25 M-row run per side; smj_synth_table kind 2, inverse CDF), every row selected, zip semantics"),
+    "c3u": dict(n1=200_000_000, n2=200_000_000, cols=4, sel=1.0, kind=1, key_domain=20_000_000,
+                desc="synthetic 200M x 200M rows, 4 int32 cols, heavy duplicates (uniform over 20M keys, ~10 rows per key per side), zip semantics"),
     "c4": dict(n1=500_000_000, n2=100_000_000, cols=8, sel=0.1, desc="synthetic 500M x 100M rows, 8 int32 cols, 10% select selectivity"),
     "c5": dict(n1=2_000_000_000, n2=2_000_000_000, cols=5, sel=1.0, desc="synthetic 2B x 2B rows, 5 int32 cols, key-range partitioned"),
 }
@@ -137,7 +139,8 @@ def run_reference(args, w, name):
         # O(n^2) insertion sort (cpu_app.c:172-202): ~1e-9 * m^2 s per table at -O2; 65,536 rows/table keeps a step near 2-3 s.
         rows = min(w["n1"], w["n2"], 65_536)
         workers = max(1, min(ncores, w["n1"] // rows, w["n2"] // rows))
-        jobs = [(i, rows, w["cols"], w["n1"], w["n2"], v1, v2, args.steps, min(args.warmup, 1)) for i in range(workers)]
+        ref_warmup = args.warmup           # the warm-up the driver asked for, as echoed in the line
+        jobs = [(i, rows, w["cols"], w["n1"], w["n2"], v1, v2, args.steps, ref_warmup) for i in range(workers)]
         with mp.get_context("fork").Pool(workers) as pool:
             times = pool.map(_ref_worker, jobs)
         dt = max(times) / args.steps
@@ -149,9 +152,12 @@ def run_reference(args, w, name):
     else:
         import numpy as np
         port, kind, cores = oracle.Port(), "port", 1
+        ref_warmup = args.warmup
         rows = min(w["n1"], w["n2"], 4_000_000)
         t1 = smj_b200.datagen.table(rows, w["cols"], 1, total_rows=w["n1"])
         t2 = smj_b200.datagen.table(rows, w["cols"], 2, total_rows=w["n2"])
+        for _ in range(ref_warmup):
+            port.run(t1, t2, 0, v1, 0, v2, 0, 0)
         t0 = time.perf_counter()
         for _ in range(args.steps):
             port.run(t1, t2, 0, v1, 0, v2, 0, 0)
@@ -168,7 +174,7 @@ def run_reference(args, w, name):
     pdt = time.perf_counter() - tp
     line = {
         "impl": "reference", "metric": "select+sort+merge-join throughput", "value": val, "unit": "Mrows/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": ref_warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": w["desc"], "name": name, "join_mode": "zip (cpu_app.c semantics)"},
         "cpu_baseline": {"value": val, "unit": "Mrows/s", "cores": cores, "host_cores": ncores, "kind": kind, "sample": sample},
@@ -246,6 +252,26 @@ def main():
     clk = clocks.stop()
     ms = dev_ms / args.steps
     value = nrows / ms / 1e3
+    replayed = bool(st.get("graph_replayed", 0))
+
+    # the same step on tables the library has not seen in the previous call: the pipeline is enqueued kernel by kernel
+    # (programmatic dependent launch) instead of replayed as one CUDA graph -- what a caller with fresh inputs gets
+    eager_ms = None
+    if name == "c2" and not os.environ.get("SMJ_BENCH_NO_EAGER"):
+        e1 = smj_b200.synth_device_table(w["n1"], w["cols"], 3, kind=w.get("kind", 0), key_domain=w.get("key_domain", 0), total_rows=tot)
+        e2 = smj_b200.synth_device_table(w["n2"], w["cols"], 4, kind=w.get("kind", 0), key_domain=w.get("key_domain", 0), total_rows=tot)
+        pairs, acc, nrep = [(d1, d2), (e1, e2)], 0.0, 0
+        for i in range(4 + 2 * args.steps):
+            a, b = pairs[i & 1]
+            out, ste = smj_b200.run(a, b, cfg=cfg, on_device=True, keep_output=True)
+            L.smj_table_free(C.byref(out))
+            if i >= 4:
+                acc += ste["total_device_ms"]; nrep += ste.get("graph_replayed", 0)
+        eager_ms = acc / (2 * args.steps)
+        assert nrep == 0, "alternating inputs must not replay a graph"
+        smj_b200.free(e1); smj_b200.free(e2)
+        for _ in range(2):
+            step_device()          # back to the repeated pair (the e2e leg below stages its own copies)
 
     # roofline of the dominant kernel: one radix scatter pass reads 8 B and writes 8 B per selected row
     peak, peak_src = peaks()
@@ -262,6 +288,13 @@ def main():
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             pass
+    dram = None   # DRAM bytes of one whole step, summed over its kernels from the committed ncu pass of this command
+    dp = os.path.join(ROOT, "profiles", f"r02_{name}_dram_bytes.json")
+    if os.path.exists(dp):
+        try:
+            dram = json.load(open(dp))
+        except Exception:
+            dram = None
     roofline = {"bound": "hbm", "kernel": f"radix_pass_kernel (onesweep scatter pass; {st['sort_passes']} launches with work per step, each over both tables' pairs)", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": pass_bytes, "avg_launch_ms": pass_avg_ms,
@@ -273,6 +306,11 @@ def main():
                 "pipeline_frac_of_peak": st["bytes_model"] / (ms * 1e-3) / 1e9 / peak,
                 "pipeline_planned_bytes": st.get("bytes_planned", 0.0),
                 "pipeline_planned_frac_of_peak": st.get("bytes_planned", 0.0) / (ms * 1e-3) / 1e9 / peak,
+                # what the step really moved: ncu dram__bytes_read + dram__bytes_write summed over one step's kernels
+                # (profiles/r02_<workload>_dram_bytes.json, taken with tools/gpu_profile.sh on this command) / this run's time
+                "pipeline_dram_bytes": dram.get("dram_bytes_per_step") if dram else None,
+                "pipeline_dram_frac_of_peak": (dram["dram_bytes_per_step"] / (ms * 1e-3) / 1e9 / peak) if dram else None,
+                "pipeline_dram_source": dram.get("source") if dram else None,
                 "note": (f"pair arrays of this workload ({8e-6 * m_avg:.0f} MB each) " +
                          ("fit the 126 MB L2: the pass is not HBM-bound here (ncu: DRAM 11 %), the fraction is of the HBM roofline the model names"
                           if 16 * m_avg < 100e6 else "exceed the 126 MB L2: the pass streams from and to HBM"))}
@@ -324,6 +362,9 @@ def main():
                    "rows_selected": st["rows_selected"], "rows_joined": st["rows_joined"],
                    "l2": f"inputs ({w['n1'] * w['cols'] * 4 / 1e6:.0f} + {w['n2'] * w['cols'] * 4 / 1e6:.0f} MB) larger than the 126 MB L2; no explicit flush"},
         "stage_ms": {k: v / args.steps for k, v in stages.items()}, "wall_ms_per_step": wall_ms,
+        "graph_replayed": replayed, "eager_ms_per_step": eager_ms,
+        "timing_note": "value = repeated call on the same device tables (the pipeline replays as one CUDA graph when graph_replayed); "
+                       "eager_ms_per_step = alternating between two table pairs, every call enqueued kernel by kernel",
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk,
     }
     print(json.dumps(line))

@@ -160,10 +160,15 @@ int  smj_csv_format(const smj_table_t *t, char **text, size_t *bytes);
  * kind 0: column key_col = a seeded bijection of the row index into [1, 3*total_rows] (unique keys, as
  *         generate_data.py:9 draws them), other columns uniform in [1, 3*total_rows).
  * kind 1: key column uniform in [1, key_domain] (duplicates), other columns as kind 0.
+ * kind 2: key column Zipf(1.1) over [1, key_domain] (key_domain 0: 2^20; at most 2^26): key k with probability
+ *         proportional to k^-1.1, i.e. key 1 holds ~12 % of the rows of a 2^20-key domain (BASELINE config 3's "heavy
+ *         duplicates"); drawn by inverse CDF from the 64-bit threshold table smj_synth_zipf_cdf() builds.
  * Rows [row0, row0+rows) of the virtual table of total_rows rows are written to dev_out (device pointer).
  * pim-sort-merge-join_b200/datagen.py computes the same cells with numpy (tests check they agree). */
 int  smj_synth_table(int32_t *dev_out, int64_t row0, int64_t rows, int64_t total_rows, int cols,
                      int key_col, uint64_t seed, int kind, int64_t key_domain);
+/* host-only: cdf_out[k-1] = floor(2^64 * P(Zipf(s) rank <= k)) for k = 1..key_domain (the table kind 2 searches) */
+int  smj_synth_zipf_cdf(int64_t key_domain, double s, uint64_t *cdf_out);
 
 /* number of CUDA kernels launched by this library since smj_init (claim for bench.py "gpu_launches") */
 int64_t smj_kernel_launches(void);

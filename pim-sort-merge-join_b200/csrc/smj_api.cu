@@ -857,8 +857,8 @@ int smj_run_enqueue(SmjCtx *c, SmjRun *R)
         if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
     }
     c->graph_seen++;
-    const bool replay = graphs_on && c->graph_exec != nullptr;
-    const bool capture = graphs_on && !replay && c->graph_seen >= 2;   // the first call warms attributes and slots eagerly
+    const bool replay = graphs_on && !R->no_graph && c->graph_exec != nullptr;
+    const bool capture = graphs_on && !R->no_graph && !replay && c->graph_seen >= 2;   // the first call warms attributes and slots eagerly
     R->replayed = replay || capture;
     int32_t **h_ptr = (int32_t **)((char *)c->h_pinned + c->h_pinned_bytes - 128);
     *h_ptr = R->dev_out.data;

@@ -382,6 +382,14 @@ int dist_rank_create(DistRank &K, SmjCtx *c, int me)
     CUDA_TRY(cudaMalloc((void **)&K.loc, sizeof(DistLocal)));
     CUDA_TRY(cudaMemset(K.loc, 0, sizeof(DistLocal)));
     CUDA_TRY(cudaMallocHost((void **)&K.h_loc, sizeof(DistLocal)));
+    {   // every kernel a step launches is loaded now: a lazy load must not happen while a peer spins on this rank (smj_preload_*)
+        cudaFuncAttributes a;
+        cudaFuncGetAttributes(&a, dist_arrive_kernel);
+        cudaFuncGetAttributes(&a, dist_splitters_kernel);
+        cudaFuncGetAttributes(&a, dist_counts_kernel);
+        cudaGetLastError();
+        smj_preload_partition(); smj_preload_select(); smj_preload_radix(); smj_preload_join();
+    }
     CUDA_TRY(cudaStreamCreateWithFlags(&K.aux, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&K.ev_fork, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&K.ev_join, cudaEventDisableTiming));
@@ -590,6 +598,8 @@ int dist_step_prepare(DistRank &K, const smj_config_t *cfg, const smj_table_t *b
     const smj_table_t r1 = {K.recv[0], K.cap_rows[0], K.blk[0].cols, 1}, r2 = {K.recv[1], K.cap_rows[1], K.blk[1].cols, 1};
     const u64 *d_rows[2] = {&K.loc->rows[0], &K.loc->rows[1]};
     SMJ_TRY(smj_run_prepare(c, &local, &r1, &r2, d_rows, &K.run));
+    // one process, several ranks: no graph capture / instantiation (an allocation) between one rank's spinning kernels and the next rank's launches
+    K.run.no_graph = g_dist.local;
     return SMJ_OK;
 }
 

@@ -61,7 +61,7 @@ enum SmjSlot {
     WS_XCHG_SEND1, WS_XCHG_SEND2, WS_XCHG_RECV1, WS_XCHG_RECV2, WS_SAMPLES,
     WS_MERGE_A, WS_MERGE_B, WS_RADIX, WS_MATCH_DENSE, WS_BLOOM,
     WS_DIST_RECV1, WS_DIST_RECV2,    // peer-mapped receive buffers of the key-range exchange (smj_dist.cu)
-    WS_ROWSTORE1, WS_ROWSTORE2,
+    WS_ROWSTORE1, WS_ROWSTORE2, WS_ZIPF,
 };
 
 // One smj_run device pipeline in flight on a context: prepare -> enqueue -> finish (smj_api.cu).
@@ -78,11 +78,17 @@ struct SmjRun {
     uint2 *mm = nullptr, *md = nullptr;
     smj_table_t dev_out = {nullptr, 0, 0, 1};
     bool prepared = false, replayed = false;
+    bool no_graph = false;                       // run the pipeline eagerly (a process driving several GPUs: smj_dist.cu)
 };
 int  smj_run_prepare(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, const smj_table_t *t2, const u64 *const *d_rows, SmjRun *R);
 int  smj_run_enqueue(SmjCtx *c, SmjRun *R);
 int  smj_run_finish(SmjCtx *c, SmjRun *R, smj_table_t *out, smj_stats_t *stats);
 void smj_run_abandon(SmjCtx *c, SmjRun *R);
+
+void smj_preload_select(void);
+void smj_preload_radix(void);
+void smj_preload_join(void);
+void smj_preload_partition(void);
 
 int   smj_set_error(int code, const char *fmt, ...);
 int   smj_cuda_fail(cudaError_t e, const char *what, const char *file, int line);

@@ -621,3 +621,21 @@ int smj_launch_join_materialize(SmjCtx *c, const uint2 *d_dense, const u64 *d_nj
     KERNEL_CHECK(c);
     return SMJ_OK;
 }
+
+// Loads this file's pipeline kernels on the current device.  CUDA loads a kernel lazily at its first launch, and that load can
+// wait for other GPUs' running kernels when peer access is enabled; a process that drives several GPUs (smj_dist.cu) must
+// not meet such a load while another rank's kernel spins on this rank's flags, so it loads everything up front.
+void smj_preload_join(void)
+{
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, join_partition_kernel);
+    cudaFuncGetAttributes(&a, join_match_kernel<SMJ_JOIN_ZIP>);
+    cudaFuncGetAttributes(&a, join_match_kernel<SMJ_JOIN_MANY>);
+    cudaFuncGetAttributes(&a, join_scan_kernel);
+    cudaFuncGetAttributes(&a, join_blocksum_kernel);
+    cudaFuncGetAttributes(&a, join_apply_kernel);
+    cudaFuncGetAttributes(&a, join_compact_kernel);
+    cudaFuncGetAttributes(&a, join_materialize_kernel<true>);
+    cudaFuncGetAttributes(&a, join_materialize_kernel<false>);
+    cudaGetLastError();
+}

@@ -513,3 +513,19 @@ int smj_launch_splitters(SmjCtx *c, const u32 *d_samples, int n_samples, int G, 
     KERNEL_CHECK(c);
     return SMJ_OK;
 }
+
+// Loads this file's pipeline kernels on the current device.  CUDA loads a kernel lazily at its first launch, and that load can
+// wait for other GPUs' running kernels when peer access is enabled; a process that drives several GPUs (smj_dist.cu) must
+// not meet such a load while another rank's kernel spins on this rank's flags, so it loads everything up front.
+void smj_preload_partition(void)
+{
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, select_partition_kernel);
+    cudaFuncGetAttributes(&a, partition_blocksum_kernel);
+    cudaFuncGetAttributes(&a, partition_offsets_kernel);
+    cudaFuncGetAttributes(&a, partition_exchange_kernel<int4>);
+    cudaFuncGetAttributes(&a, partition_exchange_kernel<int32_t>);
+    cudaFuncGetAttributes(&a, sample_rows_kernel);
+    cudaFuncGetAttributes(&a, splitters_kernel);
+    cudaGetLastError();
+}

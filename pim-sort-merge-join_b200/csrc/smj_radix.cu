@@ -12,6 +12,7 @@
 // Digit histograms for all passes come from the compaction copy (smj_select.cu) or radix_hist_kernel up front.
 #include "smj_internal.h"
 #include "smj_dev.cuh"
+#include <stdlib.h>
 
 // Optional per-phase cycle accounting for tools/radix_lab.cu (compiled out of libsmj.so).
 #ifdef SMJ_PHASE_TIMING
@@ -50,21 +51,22 @@ __device__ __forceinline__ u32 pair_digit(u64 p, u32 sel, u32 kmin) { return __b
 // the tile's 256 counts EARLY -> rank and reorder into shared memory -> batched look-back -> coalesced copy-out while
 // the next tile's loads are already in flight.
 template <bool FULL>
-__device__ __forceinline__ void radix_count_tile(const u64 (&item)[RS_IPT], u32 sel, u32 kmin, u32 *my_cnt, u32 rel0, u32 valid)
+__device__ __forceinline__ void radix_count_tile(const u64 (&item)[RS_IPT], u32 sel, u32 kmin, u32 *my_cnt, u32 rel0, u32 valid, u32 ipt)
 {
 #pragma unroll
     for (int j = 0; j < RS_IPT; j++) {
         const u32 d = pair_digit(item[j], sel, kmin);
-        if (FULL || rel0 + j * 32 < valid) atomicAdd(&my_cnt[d], 1u);
+        if (FULL || ((u32)j < ipt && rel0 + j * 32 < valid)) atomicAdd(&my_cnt[d], 1u);
     }
 }
 
 template <bool FULL>
 __device__ __forceinline__ void radix_rank_tile(const u64 (&item)[RS_IPT], u32 sel, u32 kmin, u32 *my_cnt, u32 *my_mask, u64 *s_items,
-                                                u32 rel0, u32 valid, u32 lane, u32 lt)
+                                                u32 rel0, u32 valid, u32 lane, u32 lt, u32 ipt)
 {
 #pragma unroll
     for (int j = 0; j < RS_IPT; j++) {
+        if (!FULL && (u32)j >= ipt) break;   // warp-uniform: this launch's tiles hold ipt items per thread
         const u32 d = pair_digit(item[j], sel, kmin);
         const bool ok = FULL || rel0 + j * 32 < valid;
         u32 *mk = my_mask + d;
@@ -96,11 +98,12 @@ struct RadixProblem {
     const u32 *bin_base;   // [256] first output slot of each digit
     u32 *status, *status_next;
     const SmjSortPlan *plan;   // device, or null
+    u32 cap_tiles;             // tiles the status arrays hold
 };
 struct RadixLaunch { RadixProblem p[2]; int nprob; };
 
 __global__ void __launch_bounds__(RS_THREADS, 2)
-radix_pass_kernel(const RadixLaunch L, int pass, u32 *tile_counter, u32 *err)
+radix_pass_kernel(const RadixLaunch L, int pass, u32 *tile_counter, u32 *err, int dyn_tiles)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *s_items = reinterpret_cast<u64 *>(smem_raw);              // RS_TILE, tile in digit order
@@ -119,15 +122,18 @@ radix_pass_kernel(const RadixLaunch L, int pass, u32 *tile_counter, u32 *err)
     const u32 sel = 0x4440u | (u32)pass;
     // sizes of both problems (device-resident counts), and the shared ticket space [0, tiles0) [tiles0, tiles0 + tiles1)
     u32 n0, n1 = 0;
+    u32 raw0 = 0, raw1 = 0;   // pairs of each problem whatever its pass count: the tile size must be the same in every pass
     {
         u32 np0 = SMJ_KEY_PASSES, np1 = SMJ_KEY_PASSES, km0 = 0, km1 = 0;
         const u64 v = L.p[0].n_dev ? *L.p[0].n_dev : (u64)L.p[0].n_max;
         n0 = v < (u64)L.p[0].n_max ? (u32)v : L.p[0].n_max;
+        raw0 = n0;
         if (L.p[0].plan) { np0 = L.p[0].plan->npass; km0 = L.p[0].plan->kmin; }
         if ((u32)pass >= np0) n0 = 0;
         if (L.nprob > 1) {
             const u64 v1 = L.p[1].n_dev ? *L.p[1].n_dev : (u64)L.p[1].n_max;
             n1 = v1 < (u64)L.p[1].n_max ? (u32)v1 : L.p[1].n_max;
+            raw1 = n1;
             if (L.p[1].plan) { np1 = L.p[1].plan->npass; km1 = L.p[1].plan->kmin; }
             if ((u32)pass >= np1) n1 = 0;
         }
@@ -141,8 +147,29 @@ radix_pass_kernel(const RadixLaunch L, int pass, u32 *tile_counter, u32 *err)
             s_kmin[1] = km1;
         }
     }
-    const u32 tiles0 = (n0 + RS_TILE - 1) / RS_TILE;
-    const u32 all_tiles = tiles0 + (n1 + RS_TILE - 1) / RS_TILE;
+    // Tile size of THIS launch: ipt items per thread (1..16), tile = 512 * ipt pairs.  A fixed 8192-pair tile leaves the
+    // last wave mostly idle when the pairs are few (3.3 M pairs = 407 tiles on 296 resident CTAs = two tile times for 1.4
+    // waves of work, profiles/r01_ncu_full_final.txt); here the pairs of both problems are cut into k whole waves of
+    // equal tiles, k = the waves 8192-pair tiles would need.  The status arrays hold cap tiles per problem, so the tile
+    // only shrinks as far as every problem's tile count still fits.
+    u32 ipt = RS_IPT;
+    {
+        const u64 total = (u64)raw0 + raw1;   // (a pass re-zeroes the other status array only for the tiles it has itself)
+        const u64 slots = gridDim.x;
+        const u64 k = (total + slots * RS_TILE - 1) / (slots * RS_TILE);
+        if (k > 0 && dyn_tiles) {
+            ipt = (u32)((total + k * slots * RS_THREADS - 1) / (k * slots * RS_THREADS));
+            if (ipt < 1) ipt = 1;
+            if (ipt > (u32)RS_IPT) ipt = RS_IPT;
+            while (ipt < (u32)RS_IPT &&
+                   (((u64)raw0 + RS_THREADS * ipt - 1) / (RS_THREADS * ipt) > (u64)L.p[0].cap_tiles ||
+                    (L.nprob > 1 && ((u64)raw1 + RS_THREADS * ipt - 1) / (RS_THREADS * ipt) > (u64)L.p[1].cap_tiles)))
+                ipt++;
+        }
+    }
+    const u32 tile_items = ipt * RS_THREADS;
+    const u32 tiles0 = (n0 + tile_items - 1) / tile_items;
+    const u32 all_tiles = tiles0 + (n1 + tile_items - 1) / tile_items;
 
     if (tid == 0) s_tile[0] = atomicAdd(tile_counter, 1u);
     for (u32 i = tid; i < RS_WARPS * SMJ_RADIX; i += RS_THREADS) s_mask[i] = 0;
@@ -151,15 +178,15 @@ radix_pass_kernel(const RadixLaunch L, int pass, u32 *tile_counter, u32 *err)
     int par = 0;
 
     // warp-striped layout: element order inside the tile is (warp, j, lane) == ascending index
-    const u32 rel0 = w * 32 * RS_IPT + lane;   // tile-relative index of item[0]
+    const u32 rel0 = w * 32 * ipt + lane;   // tile-relative index of item[0]
     u64 item[RS_IPT];
     if (ticket < all_tiles) {
         const bool second = ticket >= tiles0;
         const u64 *src_in = s_in[second];
         const u32 nn = second ? n1 : n0;
-        const u32 g0 = (second ? ticket - tiles0 : ticket) * RS_TILE + rel0;
+        const u32 g0 = (second ? ticket - tiles0 : ticket) * tile_items + rel0;
 #pragma unroll
-        for (int j = 0; j < RS_IPT; j++) item[j] = (g0 + j * 32 < nn) ? src_in[g0 + j * 32] : 0ull;
+        for (int j = 0; j < RS_IPT; j++) item[j] = ((u32)j < ipt && g0 + j * 32 < nn) ? src_in[g0 + j * 32] : 0ull;
     }
 
     u32 *my_cnt = s_wcnt + w * SMJ_RADIX;
@@ -174,9 +201,9 @@ radix_pass_kernel(const RadixLaunch L, int pass, u32 *tile_counter, u32 *err)
         const u32 kmin = s_kmin[second];
         const u32 *__restrict__ bin_base = P.bin_base;
         u32 *status = P.status, *status_next = P.status_next;
-        const u32 base = tile * RS_TILE;
-        const u32 valid = (n - base < (u32)RS_TILE) ? (n - base) : (u32)RS_TILE;
-        const bool full = valid == (u32)RS_TILE;
+        const u32 base = tile * tile_items;
+        const u32 valid = (n - base < tile_items) ? (n - base) : tile_items;
+        const bool full = valid == (u32)RS_TILE;   // (only 8192-pair tiles take the unpredicated path)
 
 #pragma unroll
         for (int i = 0; i < RS_WARPS * SMJ_RADIX / RS_THREADS; i++) s_wcnt[i * RS_THREADS + tid] = 0;
@@ -184,8 +211,8 @@ radix_pass_kernel(const RadixLaunch L, int pass, u32 *tile_counter, u32 *err)
         PHASE(0);   // zero counters (+ wait for this tile's loads to be issued)
 
         // ---- early counts: per-warp digit histogram
-        if (full) radix_count_tile<true>(item, sel, kmin, my_cnt, rel0, valid);
-        else radix_count_tile<false>(item, sel, kmin, my_cnt, rel0, valid);
+        if (full) radix_count_tile<true>(item, sel, kmin, my_cnt, rel0, valid, ipt);
+        else radix_count_tile<false>(item, sel, kmin, my_cnt, rel0, valid, ipt);
         __syncthreads();
         PHASE(1);   // load latency + count
 
@@ -216,8 +243,8 @@ radix_pass_kernel(const RadixLaunch L, int pass, u32 *tile_counter, u32 *err)
         PHASE(2);   // digit totals, publish, scan
 
         // ---- rank (stable: lanes in order, rows in order, warps in order) and reorder into shared memory
-        if (full) radix_rank_tile<true>(item, sel, kmin, my_cnt, my_mask, s_items, rel0, valid, lane, lt);
-        else radix_rank_tile<false>(item, sel, kmin, my_cnt, my_mask, s_items, rel0, valid, lane, lt);
+        if (full) radix_rank_tile<true>(item, sel, kmin, my_cnt, my_mask, s_items, rel0, valid, lane, lt, ipt);
+        else radix_rank_tile<false>(item, sel, kmin, my_cnt, my_mask, s_items, rel0, valid, lane, lt, ipt);
 
         PHASE(3);   // rank + reorder (thread 0's view)
         // ---- next ticket, then this tile's look-back (predecessors published before they started ranking)
@@ -266,13 +293,14 @@ radix_pass_kernel(const RadixLaunch L, int pass, u32 *tile_counter, u32 *err)
             const bool nsecond = next >= tiles0;
             const u64 *src_in = s_in[nsecond];
             const u32 nn = nsecond ? n1 : n0;
-            const u32 g0 = (nsecond ? next - tiles0 : next) * RS_TILE + rel0;
+            const u32 g0 = (nsecond ? next - tiles0 : next) * tile_items + rel0;
 #pragma unroll
-            for (int j = 0; j < RS_IPT; j++) item[j] = (g0 + j * 32 < nn) ? src_in[g0 + j * 32] : 0ull;
+            for (int j = 0; j < RS_IPT; j++) item[j] = ((u32)j < ipt && g0 + j * 32 < nn) ? src_in[g0 + j * 32] : 0ull;
         }
 #pragma unroll
         for (int k = 0; k < RS_IPT; k++) {
             const u32 idx = tid + k * RS_THREADS;
+            if (!full && (u32)k >= ipt) break;
             if (full || idx < valid) {
                 const u64 it = s_items[idx];
                 out[s_goff[pair_digit(it, sel, kmin)] + idx] = it;
@@ -324,8 +352,11 @@ __global__ void __launch_bounds__(SMJ_KEY_PASSES * SMJ_RADIX) radix_scan_kernel(
 
 }  // namespace
 
+// tiles the status arrays of an n-pair sort hold: 8192-pair tiles, plus room for one wave of smaller ones (see radix_pass_kernel)
+constexpr u32 RS_EXTRA_TILES = 320;
 size_t smj_radix_num_tiles(u32 n) { return ((size_t)n + RS_TILE - 1) / RS_TILE; }
-size_t smj_radix_status_words(u32 n) { return smj_radix_num_tiles(n) * SMJ_RADIX; }
+static size_t radix_cap_tiles(u32 n) { return smj_radix_num_tiles(n) + RS_EXTRA_TILES; }
+size_t smj_radix_status_words(u32 n) { return radix_cap_tiles(n) * SMJ_RADIX; }
 
 size_t smj_radix_scratch_bytes(u32 n)
 {
@@ -360,11 +391,12 @@ static int launch_radix_pass(SmjCtx *c, const RadixLaunch &L, int pass, u32 *d_t
     }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    size_t tiles = 0;
-    for (int i = 0; i < L.nprob; i++) tiles += smj_radix_num_tiles(L.p[i].n_max);
+    static const int dyn_tiles = !(getenv("SMJ_RADIX_DYN_TILES") && atoi(getenv("SMJ_RADIX_DYN_TILES")) == 0);
+    size_t tiles = 0;   // the smallest tile is one item per thread
+    for (int i = 0; i < L.nprob; i++) tiles += dyn_tiles ? ((size_t)L.p[i].n_max + RS_THREADS - 1) / RS_THREADS : smj_radix_num_tiles(L.p[i].n_max);
     if (tiles == 0) return SMJ_OK;
     const u32 grid = tiles < (size_t)(sms * 2) ? (u32)tiles : (u32)(sms * 2);
-    smj_launch(c, radix_pass_kernel, grid, RS_THREADS, RS_SMEM, L, pass, d_tile_counter, c->d_err);
+    smj_launch(c, radix_pass_kernel, grid, RS_THREADS, RS_SMEM, L, pass, d_tile_counter, c->d_err, dyn_tiles);
     KERNEL_CHECK(c);
     return SMJ_OK;
 }
@@ -375,8 +407,8 @@ int smj_launch_radix_pass(SmjCtx *c, const u64 *d_in, u64 *d_out, const u64 *d_n
     RadixLaunch L = {};
     L.nprob = 1;
     // plan-less pass p reads buf[p & 1]
-    if (pass & 1) L.p[0] = {{d_out, const_cast<u64 *>(d_in)}, d_n, n_max, d_bases_pass, d_status, d_status_next, nullptr};
-    else L.p[0] = {{const_cast<u64 *>(d_in), d_out}, d_n, n_max, d_bases_pass, d_status, d_status_next, nullptr};
+    if (pass & 1) L.p[0] = {{d_out, const_cast<u64 *>(d_in)}, d_n, n_max, d_bases_pass, d_status, d_status_next, nullptr, (u32)radix_cap_tiles(n_max)};
+    else L.p[0] = {{const_cast<u64 *>(d_in), d_out}, d_n, n_max, d_bases_pass, d_status, d_status_next, nullptr, (u32)radix_cap_tiles(n_max)};
     return launch_radix_pass(c, L, pass, d_tile_counter);
 }
 
@@ -414,7 +446,7 @@ int smj_radix_sort_pairs_n(SmjCtx *c, int nprob, u64 *const *buf_a, u64 *const *
         for (int k = 0; k < live; k++) {
             const int i = idx[k];
             L.p[k] = {{buf_a[i], buf_b[i]}, d_n[i], n_max[i], d_bases[k] + p * SMJ_RADIX, d_status[k][p & 1], d_status[k][(p + 1) & 1],
-                      d_plan ? d_plan[i] : nullptr};
+                      d_plan ? d_plan[i] : nullptr, (u32)radix_cap_tiles(n_max[i])};
         }
         SMJ_TRY(launch_radix_pass(c, L, p, d_counters[0] + p));   // the shared ticket counter lives in the first problem's scratch
     }
@@ -431,4 +463,16 @@ int smj_radix_sort_pairs_n(SmjCtx *c, int nprob, u64 *const *buf_a, u64 *const *
 int smj_radix_sort_pairs(SmjCtx *c, u64 *buf_a, u64 *buf_b, const u64 *d_n, u32 n_max, const u32 *d_hist, u32 *d_scratch)
 {
     return smj_radix_sort_pairs_n(c, 1, &buf_a, &buf_b, &d_n, &n_max, &d_hist, &d_scratch);
+}
+
+// Loads this file's pipeline kernels on the current device.  CUDA loads a kernel lazily at its first launch, and that load can
+// wait for other GPUs' running kernels when peer access is enabled; a process that drives several GPUs (smj_dist.cu) must
+// not meet such a load while another rank's kernel spins on this rank's flags, so it loads everything up front.
+void smj_preload_radix(void)
+{
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, radix_pass_kernel);
+    cudaFuncGetAttributes(&a, radix_hist_kernel);
+    cudaFuncGetAttributes(&a, radix_scan_kernel);
+    cudaGetLastError();
 }

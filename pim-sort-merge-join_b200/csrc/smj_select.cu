@@ -741,3 +741,25 @@ int smj_launch_select_plan2(SmjCtx *c, const SmjSelectJob job[2])
     }
     return SMJ_OK;
 }
+
+// Loads this file's pipeline kernels on the current device.  CUDA loads a kernel lazily at its first launch, and that load can
+// wait for other GPUs' running kernels when peer access is enabled; a process that drives several GPUs (smj_dist.cu) must
+// not meet such a load while another rank's kernel spins on this rank's flags, so it loads everything up front.
+void smj_preload_select(void)
+{
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, select_pairs_kernel<true>);
+    cudaFuncGetAttributes(&a, select_pairs_kernel<false>);
+    cudaFuncGetAttributes(&a, select_tma_kernel<0>);
+    cudaFuncGetAttributes(&a, select_tma_kernel<1>);
+    cudaFuncGetAttributes(&a, select_tma_kernel<2>);
+    cudaFuncGetAttributes(&a, select_tma_kernel<2, true>);
+    cudaFuncGetAttributes(&a, tile_scan_kernel);
+    cudaFuncGetAttributes(&a, select_compact_kernel);
+    cudaFuncGetAttributes(&a, plan_scan_kernel);
+    cudaFuncGetAttributes(&a, plan_blocksum_kernel);
+    cudaFuncGetAttributes(&a, plan_apply_kernel);
+    cudaFuncGetAttributes(&a, plan_compact_kernel);
+    cudaFuncGetAttributes(&a, bloom_filter_kernel);
+    cudaGetLastError();
+}

@@ -32,8 +32,23 @@ def _perm_bits(x, bits, k0, k1, k2):
     return x
 
 
-def domains(total_rows, key_domain=0):
-    dom = key_domain if key_domain > 0 else 3 * total_rows
+ZIPF_S, ZIPF_DEFAULT_DOMAIN = 1.1, 1 << 20
+_zipf_cdf = {}
+
+
+def zipf_cdf(dom, s=ZIPF_S):
+    """The 64-bit cumulative thresholds of Zipf(s) over [1, dom], from the product's own host function
+    (smj_synth_zipf_cdf): the device generator and this twin search the same integers."""
+    if (dom, s) not in _zipf_cdf:
+        from . import smj as S
+        out = np.zeros(dom, np.uint64)
+        S.check(S.lib().smj_synth_zipf_cdf(dom, s, out.ctypes.data))
+        _zipf_cdf[(dom, s)] = out
+    return _zipf_cdf[(dom, s)]
+
+
+def domains(total_rows, key_domain=0, kind=0):
+    dom = key_domain if key_domain > 0 else (ZIPF_DEFAULT_DOMAIN if kind == 2 else 3 * total_rows)
     dom = min(dom, INT32_MAX - 1)
     vdom = max(min(3 * total_rows - 1, INT32_MAX - 1), 1)
     return dom, vdom
@@ -41,7 +56,7 @@ def domains(total_rows, key_domain=0):
 
 def table(rows, cols, seed, key_col=0, kind=0, key_domain=0, row0=0, total_rows=None):
     total_rows = total_rows or rows
-    dom, vdom = domains(total_rows, key_domain)
+    dom, vdom = domains(total_rows, key_domain, kind)
     seed_u = U(seed)
     row = np.arange(row0, row0 + rows, dtype=np.uint64)
     out = np.empty((rows, cols), np.int32)
@@ -59,6 +74,9 @@ def table(rows, cols, seed, key_col=0, kind=0, key_domain=0, row0=0, total_rows=
                         x[bad] = _perm_bits(x[bad], bits, k0, k1, k2)
                         bad = x >= U(dom)
                     v = U(1) + x
+                elif kind == 2:   # Zipf(1.1): first rank whose threshold is >= the draw (csrc/smj_synth.cu, kind 2)
+                    u = mix64(seed_u * _G + U(0x51ed270b7f4a7c15) + row)
+                    v = U(1) + np.searchsorted(zipf_cdf(dom), u, side="left").astype(np.uint64)
                 else:
                     v = U(1) + mix64(seed_u * _G + U(0x51ed270b7f4a7c15) + row) % U(dom)
             else:

@@ -61,3 +61,17 @@ def test_datagen_unique_keys_and_ranges(smj):
     assert t[:, 1:].min() >= 1 and t[:, 1:].max() < 150_000
     a = smj.datagen.table(1000, 4, 1, row0=500, total_rows=50_000)
     assert np.array_equal(a, t[500:1500])
+
+
+def test_zipf_threshold_table(smj):
+    """smj_synth_zipf_cdf (host-only): monotone 64-bit thresholds, exact end, Zipf(1.1) head mass; the numpy twin draws from it."""
+    cdf = smj.datagen.zipf_cdf(1 << 20)
+    assert cdf.dtype == np.uint64 and cdf.shape == (1 << 20,)
+    assert bool((cdf[1:] >= cdf[:-1]).all()) and int(cdf[-1]) == 2**64 - 1
+    p1 = float(cdf[0]) / 2.0**64
+    h = (np.arange(1, (1 << 20) + 1, dtype=np.float64) ** -1.1).sum()
+    assert abs(p1 - 1.0 / h) < 1e-9 and 0.12 < p1 < 0.13
+    t = smj.datagen.table(100_000, 4, 9, kind=2)
+    assert 0.11 < (t[:, 0] == 1).mean() < 0.14 and t[:, 0].min() >= 1 and t[:, 0].max() <= 1 << 20
+    u = smj.datagen.table(1000, 4, 9, kind=2, row0=500, total_rows=100_000)
+    assert np.array_equal(u[:, 0], t[500:1500, 0])

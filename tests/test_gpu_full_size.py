@@ -57,7 +57,7 @@ def run_on_device(env, t1, t2, v1, v2):
     return got, st
 
 
-def test_config4_shape_500M_x_100M_8cols_10pct(env):
+def test_config4_shape_500M_x_100M_8cols_10pct(env, port):
     """500M x 100M rows, 8 int32 cols, unique keys, 10 % select selectivity (payload-heavy gather), one GPU."""
     smj, torch = env
     n1, n2, cols = 500_000_000, 100_000_000, 8
@@ -71,6 +71,15 @@ def test_config4_shape_500M_x_100M_8cols_10pct(env):
     assert got.shape[0] > 3_000_000          # ~ m2 * m1 / (3 n1) matches
     k = got[:, 0]
     assert got.shape[1] == 15 and (k.numel() < 2 or bool((k[1:] > k[:-1]).all()))   # unique keys: strictly ascending
+    # pinned to the oracle: the C port (tests/test_oracle.py ties it to cpu_app.c) on the rows that pass the predicate
+    # (~50 M + ~10 M; select keeps order, so select(survivors) == select(table) and everything downstream is the same)
+    a = t1[t1[:, 0] > v1].cpu().numpy()
+    b = t2[t2[:, 0] > v2].cpu().numpy()
+    del want
+    want_o, sel_o, _ = port.run(a, b, 0, v1, 0, v2, 0, 0)
+    assert list(sel_o) == [m1, m2]
+    g = got.cpu().numpy()
+    assert g.shape == want_o.shape and np.array_equal(g, want_o)
 
 
 def test_heavy_duplicates_200M_x_200M(env):
@@ -85,6 +94,40 @@ def test_heavy_duplicates_200M_x_200M(env):
     assert got.shape == want.shape and bool((got == want).all())
     k = got[:, 0]
     assert bool((k[1:] >= k[:-1]).all())
+
+
+def test_config3_zipf_200M_x_200M(env, port):
+    """BASELINE config 3 at full size: 200M x 200M rows, 4 cols, Zipf(1.1) keys over 2^20 values (key 1 holds ~12 % = a
+    ~25 M-row run on each side), every row selected.  Whole result against the torch closed form; and PINNED TO THE ORACLE
+    per key: zip pairing is independent per key (cpu_app.c:213-218), so the rows of a key subset -- the heavy hitter, a
+    few mid keys, a block of tail keys -- fed to the C port must give exactly the result rows of those keys."""
+    smj, torch = env
+    n, cols = 200_000_000, 4
+    t1, t2 = synth(env, n, cols, 1, kind=2), synth(env, n, cols, 2, kind=2)
+    got, st = run_on_device(env, t1, t2, 0, 0)
+    assert st["rows_selected"] == [n, n]
+    k = got[:, 0]
+    assert bool((k[1:] >= k[:-1]).all())
+    c1 = torch.bincount(t1[:, 0].long(), minlength=(1 << 20) + 1)
+    c2 = torch.bincount(t2[:, 0].long(), minlength=(1 << 20) + 1)
+    assert got.shape[0] == int(torch.minimum(c1, c2).sum()) == st["rows_joined"]
+    assert int(c1[1]) > 20_000_000 and int(c2[1]) > 20_000_000
+    want, _, _ = torch_reference(torch, t1, t2, 0, 0)
+    assert got.shape == want.shape and bool((got == want).all())
+    del want
+
+    def subset(x):
+        kk = x[:, 0]
+        return (kk == 1) | ((kk >= 50) & (kk <= 60)) | ((kk >= 100_000) & (kk <= 120_000))
+    a, b = t1[subset(t1)].cpu().numpy(), t2[subset(t2)].cpu().numpy()
+    want_o, _, _ = port.run(a, b, 0, 0, 0, 0, 0, 0)
+    g = got[subset(got)].cpu().numpy()
+    assert g.shape == want_o.shape and np.array_equal(g, want_o)
+    # the many-to-many COUNT of the same inputs (smj_join_count on key-sorted tables), against the per-key products
+    many = int((c1.double() * c2.double()).sum().item())
+    s1, s2 = t1[torch.sort(t1[:, 0], stable=True)[1]].contiguous(), t2[torch.sort(t2[:, 0], stable=True)[1]].contiguous()
+    cnt = smj.join_count(smj.Table(s1.data_ptr(), n, cols, 1), smj.Table(s2.data_ptr(), n, cols, 1), 0, 0, mode=smj.JOIN_MANY)
+    assert abs(cnt - many) <= many * 1e-12 and cnt == int((c1.long() * c2.long()).sum().item())
 
 
 def test_zipf_3M(env, port):

@@ -32,7 +32,7 @@ def assert_same(got, want, what):
 # ------------------------------------------------------------------ synthetic generator
 @pytest.mark.parametrize("rows,cols,kind,dom,row0,total", [
     (1000, 4, 0, 0, 0, None), (5000, 5, 0, 0, 12345, 100000), (4096, 8, 1, 97, 0, None), (1, 1, 0, 0, 0, None),
-    (3000, 4, 0, 2147483646, 7, 2_000_000_000),
+    (3000, 4, 0, 2147483646, 7, 2_000_000_000), (200_000, 4, 2, 0, 0, None), (50_000, 3, 2, 5000, 1_000_000, 200_000_000),
 ])
 def test_synth_matches_numpy_twin(smj, rows, cols, kind, dom, row0, total):
     t = smj.synth_device_table(rows, cols, seed=3, kind=kind, key_domain=dom, row0=row0, total_rows=total)
@@ -42,6 +42,8 @@ def test_synth_matches_numpy_twin(smj, rows, cols, kind, dom, row0, total):
     assert_same(got, want, "synth")
     if kind == 0 and row0 == 0 and total is None:
         assert len(np.unique(got[:, 0])) == rows
+    if kind == 2 and dom == 0:   # Zipf(1.1) over 2^20 keys: key 1 holds ~12 % of the rows
+        assert 0.10 < (got[:, 0] == 1).mean() < 0.15 and got[:, 0].min() == 1 and got[:, 0].max() <= 1 << 20
 
 
 # ------------------------------------------------------------------ select

@@ -36,6 +36,41 @@ def launches(path, skip=0):
     print(f"total_us, {tot:.1f}")
 
 
+def step_bytes(path, steps, out_json=None, source=""):
+    """Launch list taken with --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum over `steps`
+    identical steps: per kernel launches / time / DRAM bytes, and the DRAM bytes of ONE step (synth_kernel excluded)."""
+    import json
+    rows = list(csv.DictReader(l for l in open(path) if l.startswith('"')))
+    agg = collections.OrderedDict()
+    for r in rows:
+        k = r["Kernel Name"].split("(")[0].replace("<unnamed>::", "").replace("void ", "")
+        a = agg.setdefault(k, {"ids": set(), "ns": 0.0, "rd": 0.0, "wr": 0.0})
+        a["ids"].add(r["ID"])
+        v = float(r["Metric Value"].replace(",", "") or 0)
+        unit = r["Metric Unit"]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1.0, "us": 1e3, "ms": 1e6}.get(unit, 1.0)
+        m = r["Metric Name"]
+        if m == "gpu__time_duration.sum": a["ns"] += v * scale
+        elif m == "dram__bytes_read.sum": a["rd"] += v * scale
+        elif m == "dram__bytes_write.sum": a["wr"] += v * scale
+    print("kernel, launches_per_step, us_per_step, dram_read_MB_per_step, dram_write_MB_per_step")
+    tot_b = tot_us = 0.0
+    per = {}
+    for k, a in agg.items():
+        if k.startswith("synth"):
+            continue
+        n = len(a["ids"]) / steps
+        us, rd, wr = a["ns"] / 1e3 / steps, a["rd"] / 1e6 / steps, a["wr"] / 1e6 / steps
+        print(f"{k}, {n:.2f}, {us:.1f}, {rd:.1f}, {wr:.1f}")
+        tot_b += (rd + wr) * 1e6
+        tot_us += us
+        per[k] = {"launches": n, "us": us, "dram_read_bytes": rd * 1e6, "dram_write_bytes": wr * 1e6}
+    print(f"per step: {tot_us:.1f} us (cold, serialised), {tot_b / 1e6:.1f} MB of DRAM traffic")
+    if out_json:
+        json.dump({"dram_bytes_per_step": tot_b, "ncu_us_per_step": tot_us, "steps_captured": steps, "source": source, "kernels": per},
+                  open(out_json, "w"), indent=1)
+
+
 def rep(path):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
@@ -53,6 +88,8 @@ def rep(path):
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 0)
+    elif sys.argv[1] == "step_bytes":   # step_bytes <csv> <steps> [out.json] [source text]
+        step_bytes(sys.argv[2], int(sys.argv[3]), sys.argv[4] if len(sys.argv) > 4 else None, sys.argv[5] if len(sys.argv) > 5 else "")
     else:
         for p in sys.argv[2:]:
             rep(p)
