@@ -270,21 +270,63 @@ dist_splitters_kernel(const DistPeers P, DistLocal *loc, int me, int G, u64 seq,
     signal_and_wait(P, me, G, PH_SAMPLES, seq, err);
     const DistWindow *mine = P.win[me];
     const int n_samples = G * 2 * S;
-    for (int i = tid; i < n_pow2; i += SPL2_THREADS)
-        s_s[i] = i < n_samples ? __ldcg(&mine->samples[i / (2 * S)][i % (2 * S)]) : 0xffffffffu;
-    __syncthreads();
-    for (int k = 2; k <= n_pow2; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < n_pow2; i += SPL2_THREADS) {
-                const int p = i ^ j;
-                if (p > i) {
-                    const u32 a = s_s[i], b = s_s[p];
-                    const bool up = (i & k) == 0;
-                    if ((a > b) == up) { s_s[i] = b; s_s[p] = a; }
+    // Bitonic sort, four elements per thread (element i = 4 * tid + e): partners closer than 4 are in the thread's own
+    // registers, closer than 128 in the same warp (shuffles), only the others go through shared memory -- 15 block-wide
+    // stages for 4096 samples instead of 78 (the first version walked every stage through shared memory: 42 us).
+    {
+        const int nthr = n_pow2 >> 2;                 // threads that hold elements (n_pow2 >= 128, a multiple of 128)
+        const bool act = tid < nthr;
+        u32 v[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int i = 4 * tid + e;
+            v[e] = (act && i < n_samples) ? __ldcg(&mine->samples[i / (2 * S)][i % (2 * S)]) : 0xffffffffu;
+        }
+        for (int k = 2; k <= n_pow2; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                if (j >= 128) {
+                    if (act) {
+#pragma unroll
+                        for (int e = 0; e < 4; e++) s_s[4 * tid + e] = v[e];
+                    }
+                    __syncthreads();
+                    if (act) {
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const int i = 4 * tid + e;
+                            const u32 o = s_s[i ^ j];
+                            const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+                            v[e] = keep_min ? (v[e] < o ? v[e] : o) : (v[e] > o ? v[e] : o);
+                        }
+                    }
+                    __syncthreads();
+                } else if (j >= 4) {
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int i = 4 * tid + e;
+                        const u32 o = __shfl_xor_sync(FULL_MASK, v[e], j >> 2);
+                        const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+                        v[e] = keep_min ? (v[e] < o ? v[e] : o) : (v[e] > o ? v[e] : o);
+                    }
+                } else {   // j = 2: pairs (0,2) (1,3); j = 1: pairs (0,1) (2,3) -- compile-time register indices
+                    const bool up = ((4 * tid) & k) == 0;   // k >= 2 > the element bits only when k > 2; for k = 2 see below
+#define CE(a, b, asc) { const u32 lo_ = v[a] < v[b] ? v[a] : v[b], hi_ = v[a] < v[b] ? v[b] : v[a]; v[a] = (asc) ? lo_ : hi_; v[b] = (asc) ? hi_ : lo_; }
+                    if (j == 2) {
+                        // direction of element i: (i & k) == 0; for k >= 8 it is the thread's, for k = 4 elements 0..3 share (i & 4) = tid's bit
+                        CE(0, 2, up) CE(1, 3, up)
+                    } else {
+                        if (k == 2) { CE(0, 1, true) CE(2, 3, false) }   // (i & 2) == 0 for e = 0,1; != 0 for e = 2,3
+                        else { CE(0, 1, up) CE(2, 3, up) }
+                    }
+#undef CE
                 }
             }
-            __syncthreads();
+        if (act) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) s_s[4 * tid + e] = v[e];
         }
+        __syncthreads();
+    }
     int local = 0;
     for (int i = tid; i < n_pow2; i += SPL2_THREADS) local += s_s[i] != 0xffffffffu;
     atomicAdd(&s_valid, local);
@@ -615,7 +657,7 @@ int dist_step_enqueue(DistRank &K, const smj_config_t *cfg, u64 seq)
     const int64_t sel_val[2] = {cfg->select_val1, cfg->select_val2};
     const int key[2] = {cfg->join_key1, cfg->join_key2};
     const int S = G <= 4 ? DIST_S_MAX : DIST_S_MAX / 2;
-    int n_pow2 = 1;
+    int n_pow2 = 128;
     while (n_pow2 < G * 2 * S) n_pow2 <<= 1;
     SampleJob sj[2];
     for (int t = 0; t < 2; t++) {
