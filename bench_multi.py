@@ -24,8 +24,12 @@ def run_multi(args, w, name):
     wv = dict(w, n1=tot1, n2=tot2)
     v1, v2 = knobs_for(wv)
     cfg = S.default_config(select_val1=v1, select_val2=v2, nr_gpus=G)
-    d1 = smj_b200.synth_device_table(n1, cols, 1, row0=rank * n1, total_rows=tot1)
-    d2 = smj_b200.synth_device_table(n2, cols, 2, row0=rank * n2, total_rows=tot2)
+    # both tables draw their keys from the same domain [1, 3 * max(rows)] (as the single-GPU arm does), so that the join has
+    # matches at any shape; rank r holds rows [r * n, (r + 1) * n) of each virtual table
+    dom_rows = max(tot1, tot2)
+    kind, kdom = w.get("kind", 0), w.get("key_domain", 0)
+    d1 = smj_b200.synth_device_table(n1, cols, 1, kind=kind, key_domain=kdom, row0=rank * n1, total_rows=dom_rows)
+    d2 = smj_b200.synth_device_table(n2, cols, 2, kind=kind, key_domain=kdom, row0=rank * n2, total_rows=dom_rows)
     args.warmup = max(args.warmup, 3)
 
     def step():
@@ -41,7 +45,7 @@ def run_multi(args, w, name):
     smj_b200.dist.barrier()
     t0 = time.perf_counter()
     dev_ms, launches, pass_ms, passes = 0.0, 0, 0.0, 0
-    stages = {k: 0.0 for k in ("sort_ms", "exchange_ms", "merge_ms", "join_ms")}
+    stages = {k: 0.0 for k in ("select_ms", "sort_ms", "exchange_ms", "merge_ms", "join_ms")}
     nvlink = 0.0
     for _ in range(args.steps):
         st = step()
@@ -100,17 +104,20 @@ def run_multi(args, w, name):
             "metric": "select+sort+merge-join throughput", "value": value, "unit": "Mrows/s", "n_gpus": G, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "config": {"workload": f"{w['desc']} per GPU ({args.scaling} scaling): {tot1} x {tot2} rows over {G} GPUs, key-range "
-                                   "partitioned, exchange fused into the compaction kernel over NVLink peer memory", "name": name, "join_mode": "zip (cpu_app.c semantics)",
+            "config": {"workload": (f"{w['desc']} per GPU (weak scaling)" if args.scaling == "weak" else f"{w['desc']} in all (strong scaling)") +
+                                   f": {tot1} x {tot2} rows over {G} GPUs ({n1} x {n2} per GPU), key-range partitioned, sample / count mailboxes and the "
+                                   "exchange stores over NVLink peer memory (no NCCL call, no host wait in a step)", "name": name, "join_mode": "zip (cpu_app.c semantics)",
                        "rows_selected": sel, "rows_joined": joined, "parallelism": f"key-range x{G}",
-                       "l2": "per-GPU inputs (2 x 160 MB) larger than the 126 MB L2; no explicit flush"},
+                       "exchange": os.environ.get("SMJ_DIST_EXCHANGE", "fabric") + ("/" + os.environ["SMJ_DIST_MODE"] if os.environ.get("SMJ_DIST_MODE") else ""),
+                       "l2": f"per-GPU inputs ({n1 * cols * 4 / 1e6:.0f} + {n2 * cols * 4 / 1e6:.0f} MB) larger than the 126 MB L2; no explicit flush"},
             "stage_ms": stage_max, "wall_ms_per_step": wall_ms, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": f"radix_pass_kernel (onesweep scatter pass; {st['sort_passes']} launches with work per step, each over both tables' pairs)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": pass_bytes, "avg_launch_ms": pass_avg_ms,
                          "nvlink_bytes_sent_per_gpu": nvlink_max,
+                         # bytes the busiest rank stored into peer memory / the exchange window (table 2's partition pass runs inside it)
                          "nvlink_gbs_per_gpu": nvlink_max / (stage_max["exchange_ms"] * 1e-3) / 1e9 if stage_max["exchange_ms"] > 0 else None,
-                         "nvlink_peak_gbs": 770.0},
+                         "nvlink_peak_gbs": 770.0, "nvlink_peak_source": "peer copy rate measured on this pool in round 1 (900 GB/s nominal per direction)"},
             "cpu_baseline": None, "e2e": e2e, "clocks": clk,
         }
         print(json.dumps(line), flush=True)

@@ -113,6 +113,12 @@ int  smj_init_dist(const smj_config_t *cfg, int rank, int world, int local_devic
  *   rank me's receive buffer (runs in source-rank order), *recv_total = rows me receives. */
 int  smj_plan_splitters(const uint32_t *samples, int64_t n_samples, int world, uint32_t *splitters);
 int  smj_plan_exchange(const int64_t *counts, int world, int me, int64_t *recv_offsets, int64_t *recv_total);
+/* The default (peer-memory) exchange's plan, host twin of the device step: row0[b] = first row of rank me's bucket b inside
+ * rank b's receive buffer; *rows_mine = rows me will hold; *verdict = 1 when some rank's share exceeds cap_rows (the
+ * receive capacity every rank allocated) -- then no rank stores anything, *rows_mine = 0, and the buffers are re-sized
+ * for *need_rows (the largest share) before the step is run again.  Identical on every rank by construction. */
+int  smj_plan_fabric(const int64_t *counts, int world, int me, int64_t cap_rows, int64_t *row0, int64_t *rows_mine,
+                     int *verdict, int64_t *need_rows);
 
 /* == select.c:63-194 (DPU select) / cpu_app.c:81-112: rows with in[row][col] > val, order preserved */
 int  smj_select(const smj_table_t *in, int col, int64_t val, smj_table_t *out);

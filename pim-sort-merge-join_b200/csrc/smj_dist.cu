@@ -152,6 +152,37 @@ extern "C" int smj_plan_exchange(const int64_t *counts, int world, int me, int64
     return SMJ_OK;
 }
 
+// The fabric path's step 3 on the host (the device twin is dist_counts_kernel): from the gathered matrix
+// counts[src * world + dst] every rank derives, identically, where ITS bucket b starts inside rank b's receive buffer
+// (row0[b] = rows the lower ranks send to b: runs sit in source-rank order), how many rows it will hold (*rows_mine) and the
+// collective verdict: 1 when some rank's share exceeds cap_rows -- then nobody stores anything (*rows_mine = 0) and the
+// buffers are re-sized for *need_rows, the largest share, before the step is run again.
+extern "C" int smj_plan_fabric(const int64_t *counts, int world, int me, int64_t cap_rows, int64_t *row0, int64_t *rows_mine,
+                               int *verdict, int64_t *need_rows)
+{
+    if (!counts || !row0 || !rows_mine || !verdict || !need_rows || world < 1 || world > SMJ_MAX_G || me < 0 || me >= world)
+        return smj_set_error(SMJ_EINVAL, "smj_plan_fabric: bad arguments");
+    int over = 0;
+    int64_t worst = 0, mine = 0;
+    for (int dst = 0; dst < world; dst++) {
+        int64_t tot = 0, before = 0;
+        for (int src = 0; src < world; src++) {
+            const int64_t c = counts[(size_t)src * world + dst];
+            if (c < 0) return smj_set_error(SMJ_EINVAL, "smj_plan_fabric: negative count");
+            tot += c;
+            if (src < me) before += c;
+        }
+        row0[dst] = before;
+        if (tot > cap_rows) over = 1;
+        if (tot > worst) worst = tot;
+        if (dst == me) mine = tot;
+    }
+    *verdict = over;
+    *rows_mine = over ? 0 : mine;
+    *need_rows = worst;
+    return SMJ_OK;
+}
+
 // ------------------------------------------------------------------ the peer fabric
 // Every rank owns a WINDOW in device memory that every other rank maps (CUDA IPC between processes, peer access inside
 // one process): flag mailboxes, the sample mailbox and the G x G count matrices.  A rank "all-gathers" by storing its

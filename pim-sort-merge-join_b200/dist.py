@@ -84,3 +84,14 @@ def plan_exchange(counts, me):
     tot = C.c_int64()
     S.check(S.lib().smj_plan_exchange(c.ctypes.data, world, me, off.ctypes.data, C.byref(tot)))
     return off, tot.value
+
+
+def plan_fabric(counts, me, cap_rows):
+    """smj_plan_fabric: (row0[world], rows_mine, verdict, need_rows) from the world x world count matrix."""
+    import numpy as np
+    c = np.ascontiguousarray(counts, dtype=np.int64)
+    world = c.shape[0]
+    row0 = np.zeros(world, np.int64)
+    rows, verdict, need = C.c_int64(), C.c_int(), C.c_int64()
+    S.check(S.lib().smj_plan_fabric(c.ctypes.data, world, me, int(cap_rows), row0.ctypes.data, C.byref(rows), C.byref(verdict), C.byref(need)))
+    return row0, rows.value, verdict.value, need.value

@@ -55,6 +55,7 @@ ABI_SYMBOLS = [
     "smj_host_alloc", "smj_host_free", "smj_device_alloc", "smj_device_free", "smj_memcpy_h2d", "smj_memcpy_d2h",
     "smj_device_sync", "smj_synth_table", "smj_kernel_launches", "smj_device_count", "smj_version",
     "smj_plan_splitters", "smj_plan_exchange", "smj_csv_parse", "smj_csv_format", "smj_synth_zipf_cdf",
+    "smj_plan_fabric",
 ]
 
 _lib = None
@@ -107,6 +108,8 @@ def lib():
     L.smj_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
     L.smj_synth_table.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_uint64, C.c_int,
                                   C.c_int64]
+    L.smj_plan_fabric.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int),
+                                  C.POINTER(C.c_int64)]
     L.smj_synth_zipf_cdf.argtypes = [C.c_int64, C.c_double, C.c_void_p]
     L.smj_kernel_launches.restype = C.c_int64
     L.smj_csv_parse.argtypes = [C.c_char_p, C.c_size_t, TP]
