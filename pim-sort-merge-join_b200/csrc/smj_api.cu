@@ -385,6 +385,10 @@ int smj_check_device_flag(SmjCtx *c)
     if (*h) {
         const u32 code = *h;
         cudaMemsetAsync(c->d_err, 0, 4, c->stream);
+        if (code >= 4)
+            return smj_set_error(SMJ_EINTERNAL, "device-side check failed (code %u: %s)", code,
+                                 code == 4 ? "a rank waited 30 s for a peer's flag: some rank did not reach this step of the exchange"
+                                           : "the local select waited 30 s for the exchange of its table to arrive");
         return smj_set_error(SMJ_EINTERNAL, "device-side check failed (code %u: look-back spin limit in %s)", code,
                              code == 1 ? "select" : code == 2 ? "radix sort" : "join");
     }
@@ -849,7 +853,8 @@ int smj_run_enqueue(SmjCtx *c, SmjRun *R)
     ScratchHeader *h = (ScratchHeader *)scr;
     u64 key_now[16] = {(u64)(uintptr_t)d_t[0], (u64)(uintptr_t)d_t[1], (u64)n[0], (u64)n[1], (u64)cc[0], (u64)cc[1],
                        (u64)sel_col[0], (u64)sel_col[1], (u64)sel_val[0], (u64)sel_val[1], (u64)key[0], (u64)key[1], c->ws_gen,
-                       (u64)(uintptr_t)scr, (u64)(uintptr_t)R->d_rows[0], (u64)(uintptr_t)R->d_rows[1]};
+                       (u64)(uintptr_t)scr, (u64)(uintptr_t)R->d_rows[0] ^ ((u64)(uintptr_t)R->wait[0].flag << 1),
+                       (u64)(uintptr_t)R->d_rows[1] ^ ((u64)(uintptr_t)R->wait[1].flag << 1)};
     static const bool graphs_on = !(getenv("SMJ_NO_GRAPH") && atoi(getenv("SMJ_NO_GRAPH")) != 0);
     if (memcmp(key_now, c->graph_key, sizeof key_now) != 0) {
         memcpy(c->graph_key, key_now, sizeof key_now);
@@ -879,7 +884,7 @@ int smj_run_enqueue(SmjCtx *c, SmjRun *R)
                 for (int t = 0; t < 2; t++)
                     job[t] = {d_t[t], n[t], cc[t], sel_col[t], sel_val[t], 0, key[t], {ping[t], pong[t]}, (u64 *)mm + (t ? n[0] : 0),
                               (u64 *)(scr + off_sel + (t ? stiles[0] * 8 : 0)), h->hist[t], &h->count[t], &h->plan[t], &h->sel_count[t], &h->kept_count[t],
-                              R->d_rows[t]};
+                              R->d_rows[t], R->wait[t]};
                 rc = smj_launch_select_plan2(c, job);
                 if (rc == 1) { planned = false; rc = SMJ_OK; }   // a table the TMA path cannot take: histograms in the select kernel, four passes
             }

@@ -222,6 +222,8 @@ struct DistLocal {                                    // private to the rank; co
     u64 matrix[2][SMJ_MAX_G][SMJ_MAX_G];              // the gathered count matrices
     u32 verdict[2];                                   // non-zero: some rank's receive buffer cannot take its share of table t
     u32 pad[2];
+    u64 seq_now;                                      // this step's sequence number (written by the step's first kernel)
+    u64 arrived[2];                                   // = seq_now once every rank's rows of table t have landed here
 };
 
 struct DistPeers { DistWindow *win[SMJ_MAX_G]; };     // every rank's window as seen from this rank's device
@@ -267,9 +269,15 @@ __device__ __forceinline__ void signal_and_wait(const DistPeers &P, int me, int 
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(32) dist_arrive_kernel(const DistPeers P, int me, int G, int phase, u64 seq, u32 *err)
+// ... and, for kernels of this rank that run on ANOTHER stream (the local pipeline's select of the table that arrives last
+// starts with a device-side wait, SmjWait), the arrival cell of table t
+__global__ void __launch_bounds__(32) dist_arrive_kernel(const DistPeers P, DistLocal *loc, int me, int G, int t, u64 seq, u32 *err)
 {
-    signal_and_wait(P, me, G, phase, seq, err);
+    signal_and_wait(P, me, G, PH_XCHG0 + t, seq, err);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(&loc->arrived[t]), "l"(seq) : "memory");
+    }
 }
 
 // ---- step 1, ONE kernel, one CTA: regular row samples of both tables (predicate applied) -> every peer's sample mailbox
@@ -285,7 +293,7 @@ dist_splitters_kernel(const DistPeers P, DistLocal *loc, int me, int G, u64 seq,
     extern __shared__ u32 s_s[];
     __shared__ int s_valid;
     const int tid = threadIdx.x;
-    if (tid == 0) { s_valid = 0; loc->verdict[0] = 0; loc->verdict[1] = 0; loc->rows[0] = 0; loc->rows[1] = 0; }
+    if (tid == 0) { s_valid = 0; loc->verdict[0] = 0; loc->verdict[1] = 0; loc->rows[0] = 0; loc->rows[1] = 0; loc->seq_now = seq; }
     if (tid < 2 * S) {
         const SampleJob &J = tid < S ? j0 : j1;
         const int i = tid < S ? tid : tid - S;
@@ -433,7 +441,7 @@ struct DistRank {
     char *pscr[2] = {};
     int none[2] = {};
 };
-enum { DE_START, DE_H2D, DE_SPLIT, DE_PART, DE_XCHG };
+enum { DE_START, DE_H2D, DE_SPLIT, DE_PART, DE_XCHG, DE_XCHG2 };
 
 struct DistState {
     bool active = false;          // smj_init_dist: one process per GPU
@@ -701,13 +709,20 @@ int dist_step_enqueue(DistRank &K, const smj_config_t *cfg, u64 seq)
     KERNEL_CHECK(c);
     CUDA_TRY(cudaEventRecord(K.ev[DE_SPLIT], c->stream));
     const bool two = dist_two_streams();
-    for (int t = 0; t < 2; t++) {
-        cudaStream_t st = (t == 1 && two) ? K.aux : c->stream;
+    // the table the local pipeline selects FIRST (the one with the smaller receive capacity, smj_launch_select_plan2's rule)
+    // takes the main stream; the other one's chain runs on the second stream and starts when the first one's partition
+    // kernel is done, so that its HBM-bound partition pass overlaps the first one's NVLink-bound exchange -- and its own
+    // exchange overlaps the local pipeline's select of the first table, which is enqueued without waiting for it
+    const int tfirst = K.cap_rows[0] <= K.cap_rows[1] ? 0 : 1;
+    const int order[2] = {tfirst, tfirst ^ 1};
+    for (int o = 0; o < 2; o++) {
+        const int t = order[o];
+        cudaStream_t st = (o == 1 && two) ? K.aux : c->stream;
         SMJ_TRY(smj_launch_select_partition(c, st, K.blk[t].data, K.blk[t].rows, K.blk[t].cols, sel_col[t], sel_val[t], key[t], K.loc->split, G,
                                             K.slots[t], K.pscr[t]));
-        if (t == 0) {
+        if (o == 0) {
             CUDA_TRY(cudaEventRecord(K.ev[DE_PART], c->stream));
-            if (two) {   // table 2's chain starts here
+            if (two) {   // the other table's chain starts here
                 CUDA_TRY(cudaEventRecord(K.ev_fork, c->stream));
                 CUDA_TRY(cudaStreamWaitEvent(K.aux, K.ev_fork, 0));
             }
@@ -721,16 +736,20 @@ int dist_step_enqueue(DistRank &K, const smj_config_t *cfg, u64 seq)
         D.skip = &K.loc->verdict[t];
         SMJ_TRY(smj_launch_partition_exchange(c, st, K.blk[t].rows, K.blk[t].cols, K.none[t], G, K.slots[t], K.pscr[t], D));
         // every rank's stores must have landed before anybody reads its receive buffer
-        dist_arrive_kernel<<<1, 32, 0, st>>>(K.peers, me, G, PH_XCHG0 + t, seq, c->d_err);
+        dist_arrive_kernel<<<1, 32, 0, st>>>(K.peers, K.loc, me, G, t, seq, c->d_err);
         KERNEL_CHECK(c);
+        CUDA_TRY(cudaEventRecord(K.ev[o == 0 ? DE_XCHG : DE_XCHG2], st));
     }
+    // the local pipeline: its select of the second table waits ON THE DEVICE for that table's arrival cell
+    K.run.wait[order[1]].flag = &K.loc->arrived[order[1]];
+    K.run.wait[order[1]].seq = &K.loc->seq_now;
+    SMJ_TRY(smj_run_enqueue(c, &K.run));
     if (two) {
         CUDA_TRY(cudaEventRecord(K.ev_join, K.aux));
         CUDA_TRY(cudaStreamWaitEvent(c->stream, K.ev_join, 0));
     }
-    CUDA_TRY(cudaEventRecord(K.ev[DE_XCHG], c->stream));
     CUDA_TRY(cudaMemcpyAsync(K.h_loc, K.loc, sizeof(DistLocal), cudaMemcpyDeviceToHost, c->stream));
-    return smj_run_enqueue(c, &K.run);
+    return SMJ_OK;
 }
 
 // finish: the one host wait.  *retry = the verdict (the same on every rank): the step stored nothing, `need` says what
@@ -767,9 +786,9 @@ int dist_step_finish(DistRank &K, const smj_config_t *cfg, smj_table_t *out, smj
     }
     static const bool trace = getenv("SMJ_DIST_TRACE") != nullptr;
     if (trace && me == 0)
-        fprintf(stderr, "[dist] fabric step %llu; dev ms: samples+splitters %.3f | select/partition t1 %.3f | both chains to exchange done %.3f | local %.3f\n",
+        fprintf(stderr, "[dist] fabric step %llu; dev ms: samples+splitters %.3f | select/partition first table %.3f | first arrival +%.3f | second arrival +%.3f | end of join +%.3f\n",
                 (unsigned long long)g_dist.seq, dist_ev_ms(K.ev[DE_H2D], K.ev[DE_SPLIT]), dist_ev_ms(K.ev[DE_SPLIT], K.ev[DE_PART]),
-                dist_ev_ms(K.ev[DE_PART], K.ev[DE_XCHG]), dist_ev_ms(K.ev[DE_XCHG], c->ev[4]));
+                dist_ev_ms(K.ev[DE_PART], K.ev[DE_XCHG]), dist_ev_ms(K.ev[DE_PART], K.ev[DE_XCHG2]), dist_ev_ms(K.ev[DE_PART], c->ev[4]));
     if (cfg->debug) {
         printf("==================\n#   exchange.cu  #\n==================\n");
         for (int t = 0; t < 2; t++)
@@ -780,9 +799,13 @@ int dist_step_finish(DistRank &K, const smj_config_t *cfg, smj_table_t *out, smj
         *stats = ls;
         stats->h2d_ms = dist_ev_ms(K.ev[DE_START], K.ev[DE_H2D]);
         stats->select_ms = dist_ev_ms(K.ev[DE_H2D], K.ev[DE_PART]);      // samples + splitters + select/partition of table 1
-        stats->exchange_ms = dist_ev_ms(K.ev[DE_PART], K.ev[DE_XCHG]);   // table 2's partition overlapped with both exchanges
+        // from the end of the first table's partition pass to the later of the two arrivals (the other table's partition pass
+        // overlaps the first exchange; the local pipeline's first select overlaps the second exchange)
+        stats->exchange_ms = dist_ev_ms(K.ev[DE_PART], K.ev[DE_XCHG]);
+        { const double x2 = dist_ev_ms(K.ev[DE_PART], K.ev[DE_XCHG2]); if (x2 > stats->exchange_ms) stats->exchange_ms = x2; }
         // pairs of the received rows + the radix passes: from the end of the exchange to the start of the join stage
-        stats->sort_ms = dist_ev_ms(K.ev[DE_XCHG], c->ev[4]) - ls.join_ms;
+        stats->sort_ms = dist_ev_ms(K.ev[DE_PART], c->ev[4]) - stats->exchange_ms - ls.join_ms;
+        if (stats->sort_ms < 0) stats->sort_ms = 0;
         stats->merge_ms = 0;
         stats->total_device_ms = dist_ev_ms(K.ev[DE_H2D], c->ev[4]);     // through the local pipeline's end-of-join event
         for (int t = 0; t < 2; t++) { stats->rows_in[t] = K.blk[t].rows; stats->rows_selected[t] = sel[t]; }

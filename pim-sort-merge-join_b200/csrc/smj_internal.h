@@ -64,11 +64,15 @@ enum SmjSlot {
     WS_ROWSTORE1, WS_ROWSTORE2, WS_ZIPF,
 };
 
+// Device-side wait in front of a table's select kernel: go on once *flag >= *seq (null flag: no wait).
+struct SmjWait { const u64 *flag = nullptr; const u64 *seq = nullptr; u32 *err = nullptr; };
+
 // One smj_run device pipeline in flight on a context: prepare -> enqueue -> finish (smj_api.cu).
 struct SmjRun {
     smj_config_t cfg;
     smj_table_t tb[2];
     const u64 *d_rows[2] = {nullptr, nullptr};   // device-resident row counts (tb[t].rows is then an upper bound)
+    SmjWait wait[2];                             // per table: its select kernel waits for this device cell (smj_dist.cu)
     const int32_t *d_t[2] = {nullptr, nullptr};
     int c_out = 0;
     int64_t j_max = 0, launches0 = 0;
@@ -171,6 +175,7 @@ struct SmjSelectJob {
     u64 *d_sel_count;     // zeroed; out: rows that passed the predicate (smj_stats_t.rows_selected)
     u64 *d_kept_count;    // zeroed; out: of those, the rows whose key bit was set in the other table's bitmap
     const u64 *n_dev;     // device-resident row count (may be null); n is then the upper bound the buffers were sized for
+    SmjWait wait;         // the table's select kernel starts with this wait (smj_dist.cu: the table is still arriving)
 };
 // returns 1 (nothing launched) when a table cannot take the TMA path
 int smj_launch_select_plan2(SmjCtx *c, const SmjSelectJob job[2]);

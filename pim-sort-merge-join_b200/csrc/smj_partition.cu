@@ -108,21 +108,19 @@ select_partition_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int
                     for (int q = 0; q < PT_MAX_G - 1; q++) b += (fk >= sp[q]) ? 1u : 0u;   // unused splitters are 0xffffffff
                     if (b > (u32)(G - 1)) b = (u32)(G - 1);   // a key equal to 0xffffffff
                 }
-                // ranks inside every bucket at once: each lane adds 1 to the byte of its bucket, one 64-bit warp scan
-                // (a row group holds at most 32 rows per warp, so a byte per bucket is enough)
-                const u64 mine = pass ? (1ull << (8 * b)) : 0ull;
-                u64 inc = mine;
+                // ranks inside every bucket: one ballot per bucket (independent of each other; the first version ran one
+                // 64-bit shuffle scan per row group, a dependent chain of five steps, and the kernel took 72 us per 160 MB table)
+                u32 mine_mask = 0, cnt_lane = 0;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const u64 up = __shfl_up_sync(FULL_MASK, inc, o);
-                    if (lane >= (u32)o) inc += up;
+                for (int q = 0; q < PT_MAX_G; q++) {
+                    if (q < G) {
+                        const u32 m = __ballot_sync(FULL_MASK, pass && b == (u32)q);
+                        if (b == (u32)q) mine_mask = m;
+                        if (lane == (u32)q) cnt_lane = __popc(m);
+                    }
                 }
-                const u64 tot = __shfl_sync(FULL_MASK, inc, 31);
-                if (pass) { rank[j >> 2] |= (u32)(((inc - mine) >> (8 * b)) & 255ull) << (8 * (j & 3)); myb = b; }
-                if (lane < (u32)G) {
-                    const u32 cnt = (u32)((tot >> (8 * lane)) & 255ull);
-                    if (cnt) s_cnt[(lane * PT_IPT + j) * PT_WARPS + w] = cnt;
-                }
+                if (pass) { rank[j >> 2] |= (u32)__popc(mine_mask & lt) << (8 * (j & 3)); myb = b; }
+                if (lane < (u32)G && cnt_lane) s_cnt[(lane * PT_IPT + j) * PT_WARPS + w] = cnt_lane;
             }
             bucket |= myb << (4 * j);
         }

@@ -142,10 +142,32 @@ template <int MODE, bool PROBE = false>
 __global__ void __launch_bounds__(SELW_THREADS, PROBE ? 2 : 3)   // shared memory allows 3 CTAs per SM; the launch uses SMJ_SEL_CTAS
 select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, int sel_col, int32_t sel_val, int select_all,
                   int key_col, u32 rowid_base, u64 *__restrict__ slots, u32 *__restrict__ tile_count, u32 *hist, u32 num_tiles,
-                  SmjSortPlan *plan, SmjBloom bloom, const u64 *__restrict__ n_dev)
+                  SmjSortPlan *plan, SmjBloom bloom, const u64 *__restrict__ n_dev, const SmjWait wait)
 {
     constexpr bool HIST = MODE == 1;
     PDL_ENTER();
+    if (wait.flag) {
+        // The table is a receive buffer that another stream's exchange is still filling (smj_dist.cu): one thread polls the
+        // arrival cell until it carries this step's sequence number, then the CTA goes on.  Both are device cells at fixed
+        // addresses, so the kernel can sit inside the replayed pipeline graph.
+        if (threadIdx.x == 0) {
+            const u64 want = *reinterpret_cast<const volatile u64 *>(wait.seq);
+            unsigned long long t0 = 0;
+            for (u32 spins = 0;; spins++) {
+                u64 v;
+                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(wait.flag) : "memory");
+                if (v >= want) break;
+                if ((spins & 1023u) == 1023u) {
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > 30ull * 1000 * 1000 * 1000) { atomicExch(wait.err, 5u); break; }
+                }
+            }
+        }
+        __syncthreads();
+        asm volatile("fence.proxy.async;" ::: "memory");   // the bulk copies below read what the peers' stores wrote
+    }
     if (n_dev) {   // the table is a receive buffer: its fill is device-resident, n / num_tiles are the upper bounds
         const u64 v = *n_dev;
         if (v < (u64)n) {
@@ -585,10 +607,10 @@ int smj_launch_select_pairs(SmjCtx *c, const int32_t *d_in, int64_t n, int cols,
         const u32 grid = tiles < (u32)(sms * SMJ_SEL_CTAS) ? tiles : (u32)(sms * SMJ_SEL_CTAS);
         if (d_hist)
             select_tma_kernel<1><<<grid, SELW_THREADS, smem, c->stream>>>(d_in, n, cols, ipt, sel_col, (int32_t)sel_val, select_all,
-                                                                         key_col, rowid_base, d_tmp, d_counts, d_hist, tiles, nullptr, SmjBloom(), nullptr);
+                                                                         key_col, rowid_base, d_tmp, d_counts, d_hist, tiles, nullptr, SmjBloom(), nullptr, SmjWait());
         else
             select_tma_kernel<0><<<grid, SELW_THREADS, smem, c->stream>>>(d_in, n, cols, ipt, sel_col, (int32_t)sel_val, select_all,
-                                                                         key_col, rowid_base, d_tmp, d_counts, nullptr, tiles, nullptr, SmjBloom(), nullptr);
+                                                                         key_col, rowid_base, d_tmp, d_counts, nullptr, tiles, nullptr, SmjBloom(), nullptr, SmjWait());
         KERNEL_CHECK(c);
         tile_scan_kernel<<<1, TS_THREADS, 0, c->stream>>>(d_counts, tiles, d_offsets, d_count);
         KERNEL_CHECK(c);
@@ -688,12 +710,14 @@ int smj_launch_select_plan2(SmjCtx *c, const SmjSelectJob job[2])
                 B.shift = 32u - (u32)lb;
             }
             const u32 grid = tiles < (u32)(sms * SMJ_SEL_CTAS) ? tiles : (u32)(sms * SMJ_SEL_CTAS);
+            SmjWait W = J.wait;
+            W.err = c->d_err;
             if (B.probe)
                 smj_launch(c, select_tma_kernel<2, true>, grid, SELW_THREADS, SELW_SMEM, J.d_in, J.n, J.cols, ipt, J.sel_col, (int32_t)sel_val, select_all,
-                           J.key_col, 0u, J.slots, d_counts, (u32 *)nullptr, tiles, J.plan, B, J.n_dev);
+                           J.key_col, 0u, J.slots, d_counts, (u32 *)nullptr, tiles, J.plan, B, J.n_dev, W);
             else
                 smj_launch(c, select_tma_kernel<2, false>, grid, SELW_THREADS, SELW_SMEM, J.d_in, J.n, J.cols, ipt, J.sel_col, (int32_t)sel_val, select_all,
-                           J.key_col, 0u, J.slots, d_counts, (u32 *)nullptr, tiles, J.plan, B, J.n_dev);
+                           J.key_col, 0u, J.slots, d_counts, (u32 *)nullptr, tiles, J.plan, B, J.n_dev, W);
             KERNEL_CHECK(c);
         }
         tiles_of[t] = tiles; counts_of[t] = d_counts; tile_rows_of[t] = tile_rows;
