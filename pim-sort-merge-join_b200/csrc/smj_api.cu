@@ -405,6 +405,8 @@ struct ScratchHeader {
     SmjSortPlan plan[2]; // smj_run: key range of each table's survivors -> radix passes to run
     u64 sel_count[2];    // smj_run: rows that passed the predicate (count[] = those that also passed the semi-join filter)
     u64 kept_count[2];   // smj_run: rows of the table selected second that passed the in-select bitmap probe
+    u32 use_store[2];    // smj_run: the table's pairs carry dense row-store indices (decided on the device, plan_scan_kernel)
+    u32 pad1[2];
 };
 
 // (key,rowid) pairs of every row of a device table (no predicate): used by sort / merge / join entry points.
@@ -814,6 +816,21 @@ int smj_run_prepare(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, c
     R->mm = mm; R->md = md;
     WS_TRY(bloom_ws, char *, c, WS_BLOOM, smj_bloom_bytes(n[0], n[1]));   // sized here: no allocation inside a graph capture
     (void)bloom_ws;
+    // dense row stores (plan_compact_kernel): worth having when the semi-join filter can leave a small fraction of a table much
+    // larger than L2; the device uses a store only if the rows that go on to the sort fit SMJ_ROWSTORE_MB (default 48) and are at
+    // most a quarter of the table
+    static const long store_mb = getenv("SMJ_ROWSTORE_MB") ? atol(getenv("SMJ_ROWSTORE_MB")) : 48;
+    for (int t = 0; t < 2; t++) {
+        const size_t row_bytes = (size_t)cc[t] * 4, table_bytes = (size_t)n[t] * row_bytes;
+        if (store_mb <= 0 || smj_bloom_bytes(n[0], n[1]) == 0 || table_bytes < ((size_t)96 << 20)) continue;
+        u64 max_rows = ((u64)store_mb << 20) / row_bytes;
+        if (max_rows > (u64)n[t] / 4) max_rows = (u64)n[t] / 4;
+        if (max_rows == 0) continue;
+        int32_t *sp = (int32_t *)smj_ws(c, t ? WS_ROWSTORE2 : WS_ROWSTORE1, max_rows * row_bytes);
+        if (!sp) return SMJ_ENOMEM;
+        R->store[t] = sp;
+        R->store_max_rows[t] = max_rows;
+    }
     R->dev_out = {nullptr, 0, R->c_out, 1};
     SMJ_TRY(smj_alloc_out(c, &R->dev_out, R->j_max, R->c_out));   // upper bound; rows is set once the count is known
     CUDA_TRY(cudaEventRecord(c->ev[E_H2D], c->stream));
@@ -884,7 +901,7 @@ int smj_run_enqueue(SmjCtx *c, SmjRun *R)
                 for (int t = 0; t < 2; t++)
                     job[t] = {d_t[t], n[t], cc[t], sel_col[t], sel_val[t], 0, key[t], {ping[t], pong[t]}, (u64 *)mm + (t ? n[0] : 0),
                               (u64 *)(scr + off_sel + (t ? stiles[0] * 8 : 0)), h->hist[t], &h->count[t], &h->plan[t], &h->sel_count[t], &h->kept_count[t],
-                              R->d_rows[t], R->wait[t]};
+                              R->d_rows[t], R->wait[t], R->store[t], &h->use_store[t], R->store_max_rows[t]};
                 rc = smj_launch_select_plan2(c, job);
                 if (rc == 1) { planned = false; rc = SMJ_OK; }   // a table the TMA path cannot take: histograms in the select kernel, four passes
             }
@@ -916,7 +933,8 @@ int smj_run_enqueue(SmjCtx *c, SmjRun *R)
             const JoinScratch jsr = join_scratch(scr + off_join, jt);
             PIPE_TRY(smj_launch_join_match(c, ping[0], ping[1], &h->count[0], (u32)n[0], (u32)n[1], SMJ_JOIN_ZIP, jsr.part, jsr.tile_count,
                                            jsr.tile_off, mm, md, &h->jcount));
-            PIPE_TRY(smj_launch_join_materialize(c, md, &h->jcount, j_max, d_t[0], cc[0], d_t[1], cc[1], key[1], nullptr, c->d_out_ptr));
+            PIPE_TRY(smj_launch_join_materialize(c, md, &h->jcount, j_max, d_t[0], cc[0], d_t[1], cc[1], key[1], nullptr, c->d_out_ptr,
+                                                 planned ? h->use_store : nullptr, R->store[0], R->store[1]));
 #undef PIPE_TRY
 #undef PIPE_CUDA
         } while (0);

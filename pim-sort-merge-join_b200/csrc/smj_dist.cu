@@ -670,7 +670,6 @@ int dist_step_prepare(DistRank &K, const smj_config_t *cfg, const smj_table_t *b
         if (!K.slots[t] || !K.pscr[t]) return SMJ_ENOMEM;
         K.none[t] = (sel_val[t] >= (int64_t)INT32_MAX) ? 1 : 0;
     }
-    CUDA_TRY(cudaEventRecord(K.ev[DE_H2D], c->stream));
     // the local pipeline on what will arrive: select disabled, row counts device-resident (loc->rows)
     smj_config_t local = *cfg;
     local.nr_gpus = 1;
@@ -681,6 +680,7 @@ int dist_step_prepare(DistRank &K, const smj_config_t *cfg, const smj_table_t *b
     SMJ_TRY(smj_run_prepare(c, &local, &r1, &r2, d_rows, &K.run));
     // one process, several ranks: no graph capture / instantiation (an allocation) between one rank's spinning kernels and the next rank's launches
     K.run.no_graph = g_dist.local;
+    CUDA_TRY(cudaEventRecord(K.ev[DE_H2D], c->stream));   // inputs staged, every buffer sized: the device part of the step starts here
     return SMJ_OK;
 }
 

@@ -80,6 +80,8 @@ struct SmjRun {
     char *scr = nullptr;
     u64 *ping[2] = {}, *pong[2] = {};
     uint2 *mm = nullptr, *md = nullptr;
+    int32_t *store[2] = {nullptr, nullptr};      // dense row stores (null: not used for this shape)
+    u64 store_max_rows[2] = {0, 0};
     smj_table_t dev_out = {nullptr, 0, 0, 1};
     bool prepared = false, replayed = false;
     bool no_graph = false;                       // run the pipeline eagerly (a process driving several GPUs: smj_dist.cu)
@@ -176,6 +178,9 @@ struct SmjSelectJob {
     u64 *d_kept_count;    // zeroed; out: of those, the rows whose key bit was set in the other table's bitmap
     const u64 *n_dev;     // device-resident row count (may be null); n is then the upper bound the buffers were sized for
     SmjWait wait;         // the table's select kernel starts with this wait (smj_dist.cu: the table is still arriving)
+    int32_t *store;       // dense row store of store_max_rows rows (null: none); *use_store (zeroed) = the device's decision
+    u32 *use_store;
+    u64 store_max_rows;
 };
 // returns 1 (nothing launched) when a table cannot take the TMA path
 int smj_launch_select_plan2(SmjCtx *c, const SmjSelectJob job[2]);
@@ -235,8 +240,11 @@ int smj_launch_join_many_expand(SmjCtx *c, const u64 *d_l, const u64 *d_r, const
                                 uint2 *d_dense);
 // d_nj: device match count or null (then nj_max is exact)
 // d_out_indirect (may be null): device cell holding the output pointer, read instead of d_out (graph replay)
+// d_use_store / d_store1 / d_store2 (may be null): device flags [2] saying which table's row ids are dense indices into
+// its row store (smj_select.cu, plan_compact_kernel), and the stores
 int smj_launch_join_materialize(SmjCtx *c, const uint2 *d_dense, const u64 *d_nj, int64_t nj_max, const int32_t *d_t1, int c1,
-                                const int32_t *d_t2, int c2, int key2, int32_t *d_out, int32_t *const *d_out_indirect = nullptr);
+                                const int32_t *d_t2, int c2, int key2, int32_t *d_out, int32_t *const *d_out_indirect = nullptr,
+                                const u32 *d_use_store = nullptr, const int32_t *d_store1 = nullptr, const int32_t *d_store2 = nullptr);
 
 // ------------------------------------------------------------------ key-range partitioning of rows (smj_partition.cu)
 #define SMJ_MAX_G 8

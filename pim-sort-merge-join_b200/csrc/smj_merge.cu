@@ -27,39 +27,81 @@ __global__ void merge_partition_kernel(const u64 *__restrict__ A, u32 na, const 
     part[t] = merge_path(A, na, B, nb, (u32)d);
 }
 
+__device__ __forceinline__ void mg_cp_async8(void *dst_smem, const void *src_gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+
+// Persistent CTAs, tiles dealt round-robin, two shared-memory buffers: while tile i is merged, the A and B segments of
+// tile i + gridDim.x travel into the other buffer with cp.async (LDGSTS), so a CTA's global loads are always one tile
+// ahead of its merge.  Inside a tile every thread finds its diagonal with a merge-path search in shared memory, merges
+// MG_VT elements serially into registers, the tile is re-assembled in the buffer it came from and leaves as one
+// contiguous, coalesced block.  (The first version was one CTA per tile with plain loads: load, barrier, merge, store,
+// nothing overlapped.)
 __global__ void __launch_bounds__(MG_THREADS)
 merge_pairs_kernel(const u64 *__restrict__ A, u32 na_all, const u64 *__restrict__ B, u32 nb_all,
-                   const u32 *__restrict__ part, u64 *__restrict__ out)
+                   const u32 *__restrict__ part, u64 *__restrict__ out, u32 num_tiles)
 {
-    __shared__ __align__(16) u64 s[MG_TILE];
-    const u32 tid = threadIdx.x, tile = blockIdx.x;
+    __shared__ __align__(16) u64 s[2][MG_TILE];
+    const u32 tid = threadIdx.x;
     const u64 total = (u64)na_all + nb_all;
-    const u64 d0 = (u64)tile * MG_TILE;
-    const u64 d1 = (d0 + MG_TILE < total) ? d0 + MG_TILE : total;
-    const u32 a0 = part[tile], a1 = part[tile + 1];
-    const u32 b0 = (u32)(d0 - a0), b1 = (u32)(d1 - a1);
-    const u32 na = a1 - a0, nb = b1 - b0, ntile = na + nb;
-    u64 *sA = s, *sB = s + na;
-    for (u32 i = tid; i < na; i += MG_THREADS) sA[i] = A[a0 + i];
-    for (u32 i = tid; i < nb; i += MG_THREADS) sB[i] = B[b0 + i];
-    __syncthreads();
-    const u32 diag = (tid * MG_VT < ntile) ? tid * MG_VT : ntile;
-    u32 a = merge_path(sA, na, sB, nb, diag);
-    u32 b = diag - a;
-    u64 va = a < na ? sA[a] : 0ull, vb = b < nb ? sB[b] : 0ull;
-    u64 r[MG_VT];
-#pragma unroll
-    for (int st = 0; st < MG_VT; st++) {
-        const bool takeA = (b >= nb) || (a < na && pair_key(va) <= pair_key(vb));
-        if (takeA) { r[st] = va; a++; va = a < na ? sA[a] : 0ull; }
-        else       { r[st] = vb; b++; vb = b < nb ? sB[b] : 0ull; }
+    struct Geo { u32 a0, na, b0, nb; u64 d0; };
+    auto geo = [&](u32 tile) {
+        Geo g;
+        g.d0 = (u64)tile * MG_TILE;
+        const u64 d1 = (g.d0 + MG_TILE < total) ? g.d0 + MG_TILE : total;
+        const u32 a1 = part[tile + 1];
+        g.a0 = part[tile];
+        g.b0 = (u32)(g.d0 - g.a0);
+        g.na = a1 - g.a0;
+        g.nb = (u32)(d1 - a1) - g.b0;
+        return g;
+    };
+    auto fetch = [&](const Geo &g, u64 *buf) {
+        for (u32 i = tid; i < g.na; i += MG_THREADS) mg_cp_async8(buf + i, A + g.a0 + i);
+        for (u32 i = tid; i < g.nb; i += MG_THREADS) mg_cp_async8(buf + g.na + i, B + g.b0 + i);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    u32 tile = blockIdx.x, cur = 0;
+    Geo g = {}, gn = {};
+    if (tile < num_tiles) {
+        g = geo(tile);
+        fetch(g, s[0]);
+        if (tile + gridDim.x < num_tiles) gn = geo(tile + gridDim.x);
     }
-    __syncthreads();
+    while (tile < num_tiles) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                   // this tile's data visible; the other buffer's stores are done
+        const u32 next = tile + gridDim.x;
+        if (next < num_tiles) fetch(gn, s[cur ^ 1]);
+        const Geo gc = g;
+        g = gn;
+        if (next + gridDim.x < num_tiles) gn = geo(next + gridDim.x);   // partition entries two tiles ahead
+        u64 *buf = s[cur];
+        const u32 na = gc.na, nb = gc.nb, ntile = na + nb;
+        const u64 *sA = buf, *sB = buf + na;
+        const u32 diag = (tid * MG_VT < ntile) ? tid * MG_VT : ntile;
+        u32 a = merge_path(sA, na, sB, nb, diag);
+        u32 b = diag - a;
+        u64 va = a < na ? sA[a] : 0ull, vb = b < nb ? sB[b] : 0ull;
+        u64 r[MG_VT];
 #pragma unroll
-    for (int st = 0; st < MG_VT; st++)
-        if (diag + st < ntile) s[diag + st] = r[st];
-    __syncthreads();
-    for (u32 i = tid; i < ntile; i += MG_THREADS) out[d0 + i] = s[i];
+        for (int st = 0; st < MG_VT; st++) {
+            const bool takeA = (b >= nb) || (a < na && pair_key(va) <= pair_key(vb));
+            if (takeA) { r[st] = va; a++; va = a < na ? sA[a] : 0ull; }
+            else       { r[st] = vb; b++; vb = b < nb ? sB[b] : 0ull; }
+        }
+        __syncthreads();                                   // every thread has read its inputs: the buffer becomes the output tile
+#pragma unroll
+        for (int st = 0; st < MG_VT; st++)
+            if (diag + st < ntile) buf[diag + st] = r[st];
+        __syncthreads();
+        u64 *dst = out + gc.d0;
+        for (u32 i = tid; i < ntile; i += MG_THREADS) dst[i] = buf[i];
+        tile = next;
+        cur ^= 1;
+        // the next iteration's first barrier orders these reads of buf before the fetch that refills it one round later
+    }
 }
 
 }  // namespace
@@ -73,7 +115,10 @@ int smj_launch_merge_pairs(SmjCtx *c, const u64 *d_a, u32 na, const u64 *d_b, u3
     const u32 tiles = (u32)smj_merge_num_tiles(total);
     merge_partition_kernel<<<(tiles + 1 + 127) / 128, 128, 0, c->stream>>>(d_a, na, d_b, nb, tiles, d_part);
     KERNEL_CHECK(c);
-    merge_pairs_kernel<<<tiles, MG_THREADS, 0, c->stream>>>(d_a, na, d_b, nb, d_part, d_out);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const u32 grid = tiles < (u32)(sms * 6) ? tiles : (u32)(sms * 6);   // 32 KB of shared memory per CTA: six fit an SM
+    merge_pairs_kernel<<<grid, MG_THREADS, 0, c->stream>>>(d_a, na, d_b, nb, d_part, d_out, tiles);
     KERNEL_CHECK(c);
     return SMJ_OK;
 }

@@ -142,32 +142,10 @@ template <int MODE, bool PROBE = false>
 __global__ void __launch_bounds__(SELW_THREADS, PROBE ? 2 : 3)   // shared memory allows 3 CTAs per SM; the launch uses SMJ_SEL_CTAS
 select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, int sel_col, int32_t sel_val, int select_all,
                   int key_col, u32 rowid_base, u64 *__restrict__ slots, u32 *__restrict__ tile_count, u32 *hist, u32 num_tiles,
-                  SmjSortPlan *plan, SmjBloom bloom, const u64 *__restrict__ n_dev, const SmjWait wait)
+                  SmjSortPlan *plan, SmjBloom bloom, const u64 *__restrict__ n_dev)
 {
     constexpr bool HIST = MODE == 1;
     PDL_ENTER();
-    if (wait.flag) {
-        // The table is a receive buffer that another stream's exchange is still filling (smj_dist.cu): one thread polls the
-        // arrival cell until it carries this step's sequence number, then the CTA goes on.  Both are device cells at fixed
-        // addresses, so the kernel can sit inside the replayed pipeline graph.
-        if (threadIdx.x == 0) {
-            const u64 want = *reinterpret_cast<const volatile u64 *>(wait.seq);
-            unsigned long long t0 = 0;
-            for (u32 spins = 0;; spins++) {
-                u64 v;
-                asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(wait.flag) : "memory");
-                if (v >= want) break;
-                if ((spins & 1023u) == 1023u) {
-                    unsigned long long now;
-                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                    if (t0 == 0) t0 = now;
-                    else if (now - t0 > 30ull * 1000 * 1000 * 1000) { atomicExch(wait.err, 5u); break; }
-                }
-            }
-        }
-        __syncthreads();
-        asm volatile("fence.proxy.async;" ::: "memory");   // the bulk copies below read what the peers' stores wrote
-    }
     if (n_dev) {   // the table is a receive buffer: its fill is device-resident, n / num_tiles are the upper bounds
         const u64 v = *n_dev;
         if (v < (u64)n) {
@@ -353,6 +331,34 @@ select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, 
     }
 }
 
+// A table that is a receive buffer may still be filling while the pipeline in front of it runs: another stream's exchange
+// sets the table's arrival cell to the step's sequence number when every rank's rows have landed (smj_dist.cu).  This
+// one-warp kernel polls the cell and only then lets the stream go on.  Both cells sit at fixed device addresses, so the
+// kernel can be part of the replayed pipeline graph.  It must be a kernel of its own, and a small one: a select kernel
+// that spun in its prologue held every SM (together with the CTAs its programmatic-launch successors parked behind it),
+// and the exchange kernels it was waiting for could not be scheduled at all (seen at 250M x 50M rows per GPU).
+// No griddepcontrol.launch_dependents here: the kernels behind it must not become resident before the wait is over.
+__global__ void __launch_bounds__(32) smj_wait_kernel(const SmjWait wait)
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x == 0) {
+        const u64 want = *reinterpret_cast<const volatile u64 *>(wait.seq);
+        unsigned long long t0 = 0;
+        for (u32 spins = 0;; spins++) {
+            u64 v;
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(wait.flag) : "memory");
+            if (v >= want) break;
+            if ((spins & 1023u) == 1023u) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 30ull * 1000 * 1000 * 1000) { atomicExch(wait.err, 5u); break; }
+            }
+        }
+        __threadfence();
+    }
+}
+
 // Exclusive scan of per-tile counts (one CTA): offsets[t] = sum of counts[0..t), *total = sum of all.
 // Each thread owns a contiguous chunk, so the block-level part is one scan of 1024 partial sums.
 constexpr int TS_THREADS = SCAN1_THREADS;
@@ -388,7 +394,9 @@ select_compact_kernel(const u64 *__restrict__ slots, const u32 *__restrict__ cou
 // from the key range the select kernel left in *plan: LSD passes run over (key - kmin), so a table whose surviving keys
 // span R values needs ceil(log2(R) / 8) passes instead of four (the reference draws its keys from [1, 3n],
 // data/generate_data.py:9).  full_passes forces four passes from key 0 (A/B measurements, SMJ_FULL_PASSES=1).
-struct PlanScanJob { const u32 *counts; u32 num_tiles; u64 *offsets; u64 *total; SmjSortPlan *plan; };
+// use_store / store_max_rows: the dense row store (see plan_compact_kernel) is used when the pairs that go on to the sort
+// are at most store_max_rows (0: never) -- decided here, on the device, where the count is first known
+struct PlanScanJob { const u32 *counts; u32 num_tiles; u64 *offsets; u64 *total; SmjSortPlan *plan; u32 *use_store; u64 store_max_rows; };
 struct PlanScanArgs { PlanScanJob t[2]; int full_passes; };
 
 __global__ void __launch_bounds__(TS_THREADS) plan_scan_kernel(const PlanScanArgs A)
@@ -408,6 +416,7 @@ __global__ void __launch_bounds__(TS_THREADS) plan_scan_kernel(const PlanScanArg
         if (A.full_passes) { kmin = 0; npass = SMJ_KEY_PASSES; }
         J.plan->kmin = kmin;
         J.plan->npass = npass;
+        if (J.use_store) *J.use_store = (J.store_max_rows && total <= J.store_max_rows) ? 1u : 0u;
     }
 }
 
@@ -443,6 +452,7 @@ __global__ void __launch_bounds__(TS_THREADS) plan_apply_kernel(const PlanScanLa
         if (A.full_passes) { kmin = 0; npass = SMJ_KEY_PASSES; }
         J.plan->kmin = kmin;
         J.plan->npass = npass;
+        if (J.use_store) *J.use_store = (J.store_max_rows && total <= J.store_max_rows) ? 1u : 0u;
     }
 }
 
@@ -473,8 +483,8 @@ __global__ void __launch_bounds__(256) plan_compact_kernel(const PlanCompactArgs
         const u32 kmin = plan->kmin, npass = plan->npass;
         const u32 cnt = (tb ? A.t[1].counts : A.t[0].counts)[t];
         const u64 *src = (tb ? A.t[1].slots : A.t[0].slots) + (size_t)t * (tb ? A.t[1].tile_rows : A.t[0].tile_rows);
-        u64 *dst = (tb ? ((npass & 1u) ? A.t[1].buf[1] : A.t[1].buf[0]) : ((npass & 1u) ? A.t[0].buf[1] : A.t[0].buf[0])) +
-                   (tb ? A.t[1].offsets : A.t[0].offsets)[t];
+        const u64 off = (tb ? A.t[1].offsets : A.t[0].offsets)[t];
+        u64 *dst = (tb ? ((npass & 1u) ? A.t[1].buf[1] : A.t[1].buf[0]) : ((npass & 1u) ? A.t[0].buf[1] : A.t[0].buf[0])) + off;
         u32 *h = s_hist[tb];
         // eight independent 256-byte loads in flight per warp before the first dependent store: the first version
         // (load, store, atomics per iteration, no __restrict__) exposed one DRAM round trip per 32 pairs
@@ -503,6 +513,56 @@ __global__ void __launch_bounds__(256) plan_compact_kernel(const PlanCompactArgs
     for (u32 i = tid; i < 2 * SMJ_KEY_PASSES * SMJ_RADIX; i += 256) {
         const u32 v = (&s_hist[0][0])[i];
         if (v) atomicAdd(&(i >= SMJ_KEY_PASSES * SMJ_RADIX ? A.t[1].hist : A.t[0].hist)[i % (SMJ_KEY_PASSES * SMJ_RADIX)], v);
+    }
+}
+
+// Dense row store.  When few rows survive select + semi-join filter (use_store, decided on the device by the scan kernel:
+// the survivors fit SMJ_ROWSTORE_MB and are at most a quarter of the table), each survivor's payload row is copied into
+// store[dense index] and its pair's payload becomes that index -- still ascending with the row id, so the stable sort keeps
+// the reference's order.  The join then gathers payload from a store of a few tens of MB that stays in the 126 MB L2,
+// instead of 16-byte rows scattered over the whole table (ncu, round 1: 395 MB of DRAM traffic for 100 MB of algorithmic
+// bytes in join_materialize_kernel, every gather pulling a whole 64..128-byte line; here the rows are read once more, in
+// ascending order, and only those the filter kept).
+struct RowStoreJob { u64 *buf[2]; const SmjSortPlan *plan; const u64 *count; const int32_t *table; int32_t *store; int cols; const u32 *use_store; };
+struct RowStoreArgs { RowStoreJob t[2]; };
+constexpr int RSK_ILP = 4;
+
+__global__ void __launch_bounds__(256) rowstore_kernel(const RowStoreArgs A)
+{
+    PDL_ENTER();
+    for (int tb = 0; tb < 2; tb++) {
+        const RowStoreJob J = tb ? A.t[1] : A.t[0];
+        if (!J.store || !J.use_store || !*J.use_store) continue;
+        const u64 m = *J.count;
+        u64 *pairs = (J.plan->npass & 1u) ? J.buf[1] : J.buf[0];      // where plan_compact_kernel put the dense pairs
+        const int cols = J.cols;
+        const bool vec = (cols % 4 == 0) && (((reinterpret_cast<uintptr_t>(J.table) | reinterpret_cast<uintptr_t>(J.store)) & 15) == 0);
+        const u64 stride = (u64)gridDim.x * blockDim.x;
+        for (u64 i0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; i0 < m; i0 += stride * RSK_ILP) {
+            u64 p[RSK_ILP];
+#pragma unroll
+            for (int k = 0; k < RSK_ILP; k++) { const u64 i = i0 + k * stride; p[k] = i < m ? pairs[i] : 0ull; }
+            if (vec && cols == 4) {       // one 16-byte row per pair: RSK_ILP independent row loads in flight per thread
+                int4 r[RSK_ILP];
+#pragma unroll
+                for (int k = 0; k < RSK_ILP; k++) { const u64 i = i0 + k * stride; if (i < m) r[k] = __ldg(reinterpret_cast<const int4 *>(J.table) + pair_row(p[k])); }
+#pragma unroll
+                for (int k = 0; k < RSK_ILP; k++) { const u64 i = i0 + k * stride; if (i < m) reinterpret_cast<int4 *>(J.store)[i] = r[k]; }
+            } else {
+#pragma unroll
+                for (int k = 0; k < RSK_ILP; k++) {
+                    const u64 i = i0 + k * stride;
+                    if (i < m) {
+                        const int32_t *rs = J.table + (size_t)pair_row(p[k]) * cols;
+                        int32_t *rd = J.store + (size_t)i * cols;
+                        if (vec) for (int q = 0; q < cols / 4; q++) reinterpret_cast<int4 *>(rd)[q] = __ldg(reinterpret_cast<const int4 *>(rs) + q);
+                        else for (int q = 0; q < cols; q++) rd[q] = __ldg(rs + q);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < RSK_ILP; k++) { const u64 i = i0 + k * stride; if (i < m) pairs[i] = (p[k] & 0xffffffff00000000ull) | (u64)(u32)i; }
+        }
     }
 }
 
@@ -607,10 +667,10 @@ int smj_launch_select_pairs(SmjCtx *c, const int32_t *d_in, int64_t n, int cols,
         const u32 grid = tiles < (u32)(sms * SMJ_SEL_CTAS) ? tiles : (u32)(sms * SMJ_SEL_CTAS);
         if (d_hist)
             select_tma_kernel<1><<<grid, SELW_THREADS, smem, c->stream>>>(d_in, n, cols, ipt, sel_col, (int32_t)sel_val, select_all,
-                                                                         key_col, rowid_base, d_tmp, d_counts, d_hist, tiles, nullptr, SmjBloom(), nullptr, SmjWait());
+                                                                         key_col, rowid_base, d_tmp, d_counts, d_hist, tiles, nullptr, SmjBloom(), nullptr);
         else
             select_tma_kernel<0><<<grid, SELW_THREADS, smem, c->stream>>>(d_in, n, cols, ipt, sel_col, (int32_t)sel_val, select_all,
-                                                                         key_col, rowid_base, d_tmp, d_counts, nullptr, tiles, nullptr, SmjBloom(), nullptr, SmjWait());
+                                                                         key_col, rowid_base, d_tmp, d_counts, nullptr, tiles, nullptr, SmjBloom(), nullptr);
         KERNEL_CHECK(c);
         tile_scan_kernel<<<1, TS_THREADS, 0, c->stream>>>(d_counts, tiles, d_offsets, d_count);
         KERNEL_CHECK(c);
@@ -681,6 +741,8 @@ int smj_launch_select_plan2(SmjCtx *c, const SmjSelectJob job[2])
 
     PlanScanArgs SA = {};
     PlanCompactArgs CA = {};
+    RowStoreArgs RA = {};
+    bool any_store = false;
     SA.full_passes = full_passes;
     u32 all_tiles = 0;
     u32 tiles_of[2] = {0, 0};
@@ -710,19 +772,25 @@ int smj_launch_select_plan2(SmjCtx *c, const SmjSelectJob job[2])
                 B.shift = 32u - (u32)lb;
             }
             const u32 grid = tiles < (u32)(sms * SMJ_SEL_CTAS) ? tiles : (u32)(sms * SMJ_SEL_CTAS);
-            SmjWait W = J.wait;
-            W.err = c->d_err;
+            if (J.wait.flag) {   // the table is still arriving on another stream (smj_dist.cu): a one-warp kernel waits for it
+                SmjWait W = J.wait;
+                W.err = c->d_err;
+                smj_launch(c, smj_wait_kernel, 1, 32, 0, W);
+                KERNEL_CHECK(c);
+            }
             if (B.probe)
                 smj_launch(c, select_tma_kernel<2, true>, grid, SELW_THREADS, SELW_SMEM, J.d_in, J.n, J.cols, ipt, J.sel_col, (int32_t)sel_val, select_all,
-                           J.key_col, 0u, J.slots, d_counts, (u32 *)nullptr, tiles, J.plan, B, J.n_dev, W);
+                           J.key_col, 0u, J.slots, d_counts, (u32 *)nullptr, tiles, J.plan, B, J.n_dev);
             else
                 smj_launch(c, select_tma_kernel<2, false>, grid, SELW_THREADS, SELW_SMEM, J.d_in, J.n, J.cols, ipt, J.sel_col, (int32_t)sel_val, select_all,
-                           J.key_col, 0u, J.slots, d_counts, (u32 *)nullptr, tiles, J.plan, B, J.n_dev, W);
+                           J.key_col, 0u, J.slots, d_counts, (u32 *)nullptr, tiles, J.plan, B, J.n_dev);
             KERNEL_CHECK(c);
         }
         tiles_of[t] = tiles; counts_of[t] = d_counts; tile_rows_of[t] = tile_rows;
-        SA.t[t] = {d_counts, tiles, d_offsets, J.d_count, J.plan};
+        SA.t[t] = {d_counts, tiles, d_offsets, J.d_count, J.plan, J.use_store, J.store ? J.store_max_rows : 0};
         CA.t[t] = {J.slots, d_counts, d_offsets, tiles, (u32)tile_rows, {J.buf[0], J.buf[1]}, J.plan, J.d_hist};
+        RA.t[t] = {{J.buf[0], J.buf[1]}, J.plan, J.d_count, J.d_in, J.store, J.cols, J.use_store};
+        any_store = any_store || (J.store != nullptr && tiles > 0);
         all_tiles += tiles;
     }
     if (semijoin && tiles_of[first]) {
@@ -763,6 +831,10 @@ int smj_launch_select_plan2(SmjCtx *c, const SmjSelectJob job[2])
         smj_launch(c, plan_compact_kernel, cgrid, 256, 0, CA);
         KERNEL_CHECK(c);
     }
+    if (any_store) {
+        smj_launch(c, rowstore_kernel, (u32)(sms * 8), 256, 0, RA);
+        KERNEL_CHECK(c);
+    }
     return SMJ_OK;
 }
 
@@ -785,5 +857,7 @@ void smj_preload_select(void)
     cudaFuncGetAttributes(&a, plan_apply_kernel);
     cudaFuncGetAttributes(&a, plan_compact_kernel);
     cudaFuncGetAttributes(&a, bloom_filter_kernel);
+    cudaFuncGetAttributes(&a, rowstore_kernel);
+    cudaFuncGetAttributes(&a, smj_wait_kernel);
     cudaGetLastError();
 }
