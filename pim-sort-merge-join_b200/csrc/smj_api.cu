@@ -175,10 +175,15 @@ extern "C" int smj_init(const smj_config_t *cfg)
     if (g_cfg.nr_gpus < 1) g_cfg.nr_gpus = 1;
     const int ndev = smj_device_count();
     if (ndev < 1) return smj_set_error(SMJ_ENODEVICE, "no CUDA device visible (libsmj has no CPU fallback)");
-    if (g_cfg.nr_gpus > ndev || g_cfg.nr_gpus > 8)
+    // SMJ_RANKS_ON_ONE_GPU=1: every rank of the one-process multi-GPU mode gets a context (streams, workspace, pool) on
+    // device 0.  The whole key-range exchange -- mailboxes, routing to G buckets, receive buffers, verdicts -- then runs
+    // on a single GPU, rank against rank on concurrent streams; what the tests and the profiler use where one GPU is all
+    // there is.  (Only one-CTA kernels ever spin on a peer, so the ranks cannot starve each other of SMs.)
+    const bool one_gpu = getenv("SMJ_RANKS_ON_ONE_GPU") && atoi(getenv("SMJ_RANKS_ON_ONE_GPU")) != 0;
+    if ((!one_gpu && g_cfg.nr_gpus > ndev) || g_cfg.nr_gpus > 8)
         return smj_set_error(SMJ_EINVAL, "nr_gpus=%d but %d CUDA devices visible (max 8)", g_cfg.nr_gpus, ndev);
     for (int g = 0; g < g_cfg.nr_gpus; g++) {
-        int r = ctx_create(g, &g_ctx[g]);
+        int r = ctx_create(one_gpu ? 0 : g, &g_ctx[g]);
         if (r != SMJ_OK) { smj_shutdown(); return r; }
         g_nctx = g + 1;
     }
@@ -816,10 +821,12 @@ int smj_run_prepare(SmjCtx *c, const smj_config_t *cfg, const smj_table_t *t1, c
     R->mm = mm; R->md = md;
     WS_TRY(bloom_ws, char *, c, WS_BLOOM, smj_bloom_bytes(n[0], n[1]));   // sized here: no allocation inside a graph capture
     (void)bloom_ws;
-    // dense row stores (plan_compact_kernel): worth having when the semi-join filter can leave a small fraction of a table much
-    // larger than L2; the device uses a store only if the rows that go on to the sort fit SMJ_ROWSTORE_MB (default 48) and are at
-    // most a quarter of the table
-    static const long store_mb = getenv("SMJ_ROWSTORE_MB") ? atol(getenv("SMJ_ROWSTORE_MB")) : 48;
+    // dense row stores (rowstore_kernel, smj_select.cu): OFF unless SMJ_ROWSTORE_MB is set.  Measured at 10M x 10M x 4 columns
+    // (profiles/r02_rowstore_ab.txt): the materialise kernel's DRAM traffic falls from 392 to 110 MB (1.1x its algorithmic
+    // bytes) and its time from 76 to 47 us, but copying the 1.67 M surviving 16-byte rows per table costs 56 us and 326 MB --
+    // a sparse ascending read still pulls whole DRAM lines -- so the step goes from 0.374 to 0.400 ms.  With the knob set the
+    // device uses a store only if the rows that go on to the sort fit it and are at most a quarter of the table.
+    static const long store_mb = getenv("SMJ_ROWSTORE_MB") ? atol(getenv("SMJ_ROWSTORE_MB")) : 0;
     for (int t = 0; t < 2; t++) {
         const size_t row_bytes = (size_t)cc[t] * 4, table_bytes = (size_t)n[t] * row_bytes;
         if (store_mb <= 0 || smj_bloom_bytes(n[0], n[1]) == 0 || table_bytes < ((size_t)96 << 20)) continue;

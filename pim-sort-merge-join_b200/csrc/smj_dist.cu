@@ -734,7 +734,7 @@ int dist_step_enqueue(DistRank &K, const smj_config_t *cfg, u64 seq)
         for (int b = 0; b < G; b++) D.base[b] = K.peer_recv[t][b];
         D.row0 = K.loc->row0[t];
         D.skip = &K.loc->verdict[t];
-        SMJ_TRY(smj_launch_partition_exchange(c, st, K.blk[t].rows, K.blk[t].cols, K.none[t], G, K.slots[t], K.pscr[t], D));
+        SMJ_TRY(smj_launch_partition_exchange(c, st, K.blk[t].rows, K.blk[t].cols, key[t], K.loc->split, K.none[t], G, K.slots[t], K.pscr[t], D));
         // every rank's stores must have landed before anybody reads its receive buffer
         dist_arrive_kernel<<<1, 32, 0, st>>>(K.peers, K.loc, me, G, t, seq, c->d_err);
         KERNEL_CHECK(c);
@@ -879,7 +879,7 @@ static int dist_init_local(int G)
     smj_dist_shutdown();
     for (int r = 0; r < G; r++)
         for (int q = 0; q < G; q++) {
-            if (r == q) continue;
+            if (r == q || g_ctx[r]->device == g_ctx[q]->device) continue;
             int can = 0;
             CUDA_TRY(cudaDeviceCanAccessPeer(&can, g_ctx[r]->device, g_ctx[q]->device));
             if (!can) return smj_set_error(SMJ_EINVAL, "GPU %d cannot access GPU %d's memory: the key-range exchange needs peer access", r, q);
@@ -1158,7 +1158,7 @@ static int smj_run_multi_nccl(const smj_config_t *cfg, const smj_table_t *t1, co
         SmjPartitionDst D = {};
         for (int b = 0; b < G; b++) D.base[b] = send[t];
         D.row0 = PS.bucket_start;
-        SMJ_TRY(smj_launch_partition_exchange(c, c->stream, tb[t]->rows, cc[t], none[t], G, slots[t], pscr[t], D));
+        SMJ_TRY(smj_launch_partition_exchange(c, c->stream, tb[t]->rows, cc[t], key[t], d_split, none[t], G, slots[t], pscr[t], D));
     }
     NCCL_TRY(g_nccl.GroupStart());
     for (int t = 0; t < 2; t++) {

@@ -9,10 +9,10 @@
 // reference's stable order.  All passes are sequential streams; no row is gathered at random before it travels.
 //
 //   select_partition_kernel : TMA-fed like select_tma_kernel (1 producer warp, 8 compute warps).  Per tile: predicate,
-//                             bucket id (<= 7 compares), per-(bucket,row group,warp) ballot counts, one 512-entry
-//                             scan, rows written to the tile's own slot ordered by bucket, G counts per tile.
+//                             ballot/popc ranks, the surviving rows written compacted (original order) into the tile's
+//                             own slot, bucket id (<= 7 compares) and G survivor counts per tile.
 //   partition_blocksum / partition_offsets_kernel: offsets of every (bucket, tile) segment + bucket totals, many CTAs.
-//   partition_exchange_kernel: one warp per tile routes the tile's survivors to their buckets' destinations.
+//   partition_exchange_kernel: one warp per tile routes the tile's surviving rows, 32 at a time, to their buckets' destinations.
 //   sample_rows_kernel      : regular row samples (predicate applied) from which the splitters are derived.
 #include "smj_internal.h"
 #include "smj_dev.cuh"
@@ -26,10 +26,26 @@ constexpr int PT_STAGES = 2;
 constexpr int PT_STAGE_BYTES = 32768;
 constexpr int PT_MAX_G = SMJ_MAX_G;
 constexpr int PTW_THREADS = PT_THREADS + 32;
-constexpr int PT_ENTRIES = PT_MAX_G * PT_IPT * PT_WARPS;   // 512 = 2 per compute thread
+
 constexpr size_t PTW_SMEM = (size_t)PT_STAGES * PT_STAGE_BYTES;
 constexpr int PT_MAX_COLS = PT_STAGE_BYTES / 4 / PT_THREADS;   // 32
 
+// bucket of a flipped key: the number of splitters <= key (unused splitters are 0xffffffff), at most G - 1
+__device__ __forceinline__ u32 pt_bucket(u32 fk, const u32 (&sp)[PT_MAX_G - 1], int G)
+{
+    u32 b = 0;
+#pragma unroll
+    for (int q = 0; q < PT_MAX_G - 1; q++) b += (q < G - 1 && fk >= sp[q]) ? 1u : 0u;
+    return b;
+}
+
+// Per tile: predicate, the survivors' ranks (one ballot per row group, exactly as select_tma_kernel), the survivors' ROWS
+// written compacted in ORIGINAL ORDER into the tile's own slot, and the tile's survivor count per destination bucket (one
+// ballot per bucket and row group; lane q keeps bucket q's count).  The rows are NOT grouped by bucket here: the first two
+// versions ordered every tile's slot by bucket (a 64-bit shuffle scan per row group, then a 512-entry scan and three
+// barriers per tile) and ncu showed the kernel issue-bound -- 150 instructions per row, 65 % issue-active, 70 us per
+// 160 MB table against 33 us for the plain select stream.  The exchange kernel routes the rows instead: it is bound by
+// NVLink and has the issue slots to spare.
 __global__ void __launch_bounds__(PTW_THREADS, 3)
 select_partition_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, int sel_col, int32_t sel_val, int select_all,
                         int key_col, const u32 *__restrict__ splitters, int G, int32_t *__restrict__ slots,
@@ -37,10 +53,11 @@ select_partition_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int
 {
     extern __shared__ __align__(128) unsigned char pt_smem[];
     __shared__ __align__(8) u64 s_full[PT_STAGES], s_empty[PT_STAGES];
-    __shared__ u32 s_cnt[PT_ENTRIES], s_off[PT_ENTRIES + 1];
-    __shared__ u32 s_wtot[PT_WARPS];
+    __shared__ u32 s_cnt[2][PT_IPT * PT_WARPS];          // [row group][warp] survivors, double-buffered: one barrier per tile
+    __shared__ u32 s_wb[2][PT_WARPS][PT_MAX_G];          // per warp: survivors per bucket
     __shared__ u32 s_split[PT_MAX_G];
 
+    PDL_ENTER();
     const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
     const u32 tile_rows = (u32)ipt * PT_THREADS;
     if (tid < (u32)PT_MAX_G) s_split[tid] = (tid < (u32)(G - 1)) ? splitters[tid] : 0xffffffffu;
@@ -53,6 +70,7 @@ select_partition_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int
     if (w == PT_WARPS) {   // ---------------- producer (one lane)
         if (lane != 0) return;
         const size_t row_bytes = (size_t)cols * 4;
+        const u64 stream_policy = l2_policy_evict_first();
         u32 stage = 0, parity = 0;
         for (u32 t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             mbar_wait(&s_empty[stage], parity ^ 1u);
@@ -66,7 +84,7 @@ select_partition_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int
                 *reinterpret_cast<int32_t *>(dst + b) = *reinterpret_cast<const int32_t *>(src + b);
             if (b16) {
                 mbar_expect_tx(&s_full[stage], b16);
-                bulk_g2s(dst, src, b16, &s_full[stage]);
+                bulk_g2s_hint(dst, src, b16, &s_full[stage], stream_policy);
             } else {
                 mbar_arrive(&s_full[stage]);
             }
@@ -81,20 +99,17 @@ select_partition_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int
     u32 sp[PT_MAX_G - 1];
 #pragma unroll
     for (int q = 0; q < PT_MAX_G - 1; q++) sp[q] = s_split[q];
-    u32 stage = 0, parity = 0;
-    for (u32 tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    u32 stage = 0, parity = 0, it = 0;
+    for (u32 tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
         mbar_wait(&s_full[stage], parity);
         const int64_t tile_base = (int64_t)tile * tile_rows;
         const u32 rows_valid = (u32)((n - tile_base < (int64_t)tile_rows) ? (n - tile_base) : (int64_t)tile_rows);
         const int32_t *s_rows = reinterpret_cast<const int32_t *>(pt_smem + (size_t)stage * PT_STAGE_BYTES);
-
-        u32 rank[PT_IPT / 4] = {};   // 8 bits per row group: position among the rows of the same (bucket, row group, warp)
-        u32 bucket = 0;              // 4 bits per row group; PT_MAX_G = dropped
-        for (u32 i = tid; i < (u32)PT_ENTRIES; i += PT_THREADS) s_cnt[i] = 0;
-        named_bar_sync(1, PT_THREADS);
+        u32 *cntbuf = s_cnt[it & 1u];
+        u32 rank[PT_IPT];
+        u32 passmask = 0, bcnt = 0;   // bcnt: lane q counts this warp's survivors of bucket q
 #pragma unroll
         for (int j = 0; j < PT_IPT; j++) {
-            u32 myb = PT_MAX_G;
             if (j < ipt) {
                 const u32 row = j * PT_THREADS + tid;
                 bool pass = false;
@@ -103,53 +118,46 @@ select_partition_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int
                     const int32_t sv = s_rows[row * cols + sel_col];
                     const int32_t kv = (key_col == sel_col) ? sv : s_rows[row * cols + key_col];
                     pass = select_all || sv > sel_val;
-                    const u32 fk = (u32)kv ^ 0x80000000u;
-#pragma unroll
-                    for (int q = 0; q < PT_MAX_G - 1; q++) b += (fk >= sp[q]) ? 1u : 0u;   // unused splitters are 0xffffffff
-                    if (b > (u32)(G - 1)) b = (u32)(G - 1);   // a key equal to 0xffffffff
+                    b = pt_bucket((u32)kv ^ 0x80000000u, sp, G);
                 }
-                // ranks inside every bucket: one ballot per bucket (independent of each other; the first version ran one
-                // 64-bit shuffle scan per row group, a dependent chain of five steps, and the kernel took 72 us per 160 MB table)
-                u32 mine_mask = 0, cnt_lane = 0;
+                const u32 m = __ballot_sync(FULL_MASK, pass);
+                if (lane == 0) cntbuf[j * PT_WARPS + w] = __popc(m);
+                rank[j] = __popc(m & lt);
+                passmask |= (pass ? 1u : 0u) << j;
 #pragma unroll
                 for (int q = 0; q < PT_MAX_G; q++) {
-                    if (q < G) {
-                        const u32 m = __ballot_sync(FULL_MASK, pass && b == (u32)q);
-                        if (b == (u32)q) mine_mask = m;
-                        if (lane == (u32)q) cnt_lane = __popc(m);
+                    if (q < G) {   // warp-uniform
+                        const u32 mq = __ballot_sync(FULL_MASK, pass && b == (u32)q);
+                        if (lane == (u32)q) bcnt += __popc(mq);
                     }
                 }
-                if (pass) { rank[j >> 2] |= (u32)__popc(mine_mask & lt) << (8 * (j & 3)); myb = b; }
-                if (lane < (u32)G && cnt_lane) s_cnt[(lane * PT_IPT + j) * PT_WARPS + w] = cnt_lane;
+            } else if (lane == 0) {
+                cntbuf[j * PT_WARPS + w] = 0;
             }
-            bucket |= myb << (4 * j);
         }
-        named_bar_sync(1, PT_THREADS);
-        {   // exclusive scan of the 512 counts (bucket-major, then row group, then warp == row order inside a bucket)
-            const u32 v0 = s_cnt[2 * tid], v1 = s_cnt[2 * tid + 1];
-            const u32 inc = warp_incl_scan(v0 + v1);
-            if (lane == 31) s_wtot[w] = inc;
-            named_bar_sync(1, PT_THREADS);
-            u32 base = inc - (v0 + v1);
-            for (u32 ww = 0; ww < w; ww++) base += s_wtot[ww];
-            s_off[2 * tid] = base;
-            s_off[2 * tid + 1] = base + v0;
-            if (tid == PT_THREADS - 1) s_off[PT_ENTRIES] = base + v0 + v1;
-        }
-        named_bar_sync(1, PT_THREADS);
+        if (lane < (u32)PT_MAX_G) s_wb[it & 1u][w][lane] = bcnt;
+        named_bar_sync(1, PT_THREADS);                 // counts complete (double-buffered: one barrier per tile)
         if (tid < (u32)PT_MAX_G) {
-            const u32 lo = s_off[tid * PT_IPT * PT_WARPS], hi = s_off[(tid + 1) * PT_IPT * PT_WARPS];
-            tile_counts[(size_t)tile * PT_MAX_G + tid] = hi - lo;
+            u32 t = 0;
+#pragma unroll
+            for (int ww = 0; ww < PT_WARPS; ww++) t += s_wb[it & 1u][ww][tid];
+            tile_counts[(size_t)tile * PT_MAX_G + tid] = t;
         }
+        // every warp scans the 64 (row group, warp) counts itself
+        const u32 v0 = cntbuf[2 * lane], v1 = cntbuf[2 * lane + 1];
+        const u32 inc = warp_incl_scan(v0 + v1);
+        const u32 ex0 = inc - (v0 + v1);
         int32_t *dst_tile = slots + (size_t)tile_base * cols;
 #pragma unroll
         for (int j = 0; j < PT_IPT; j++) {
-            const u32 myb = (bucket >> (4 * j)) & 15u;
-            if (myb < (u32)PT_MAX_G) {
+            const u32 e = (u32)j * PT_WARPS + w;       // warp-uniform entry index
+            u32 off = __shfl_sync(FULL_MASK, ex0, e >> 1);
+            const u32 add = __shfl_sync(FULL_MASK, v0, e >> 1);
+            if (e & 1u) off += add;
+            if ((passmask >> j) & 1u) {
                 const u32 row = j * PT_THREADS + tid;
-                const u32 pos = s_off[(myb * PT_IPT + j) * PT_WARPS + w] + ((rank[j >> 2] >> (8 * (j & 3))) & 255u);
                 const int32_t *src = s_rows + row * cols;
-                int32_t *dst = dst_tile + (size_t)pos * cols;
+                int32_t *dst = dst_tile + (size_t)(off + rank[j]) * cols;
                 if (vec) {
                     for (int q = 0; q < cols / 4; q++)
                         reinterpret_cast<int4 *>(dst)[q] = reinterpret_cast<const int4 *>(src)[q];
@@ -161,8 +169,6 @@ select_partition_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[stage]);   // rows copied out: the stage can be refilled
         if (++stage == PT_STAGES) { stage = 0; parity ^= 1u; }
-        // s_cnt / s_off are rewritten only after the next tile's first named barrier, which every warp reaches after
-        // finishing the reads above
     }
 }
 
@@ -284,65 +290,95 @@ partition_offsets_kernel(const u32 *__restrict__ tile_counts, u32 num_tiles, int
         }
 }
 
-// The exchange.  A tile's survivors sit bucket-ordered and contiguous at the start of the tile's slot; segment (t, b) goes to
-// dst.base[b] + (row0[b] + off32[t][b]) rows -- dst.base[b] is the local send buffer (grouped ncclSend path), the rank's own
-// receive buffer (its own bucket) or a PEER GPU's receive buffer (peer mapping: the stores travel over NVLink from the SMs,
-// so the compaction IS the exchange).  One warp per tile: the tile's 8 counts and offsets arrive with two 32-byte loads,
-// then the warp walks the slot as a flat array of cells (16-byte words when rows are whole 16-byte multiples), PX_UNROLL
-// independent loads in flight per lane before the first store, each word routed to its bucket by comparing its index with
-// the bucket boundaries held in registers.  (The first version took one warp per SEGMENT: a dependent chain of count ->
-// offset -> data loads for every ~2 KB piece, 0.30 ms for 122 MB at 8 GPUs.)
+// The exchange.  A tile's survivors sit contiguous, in original row order, at the start of the tile's slot.  One warp per
+// tile walks them 32 rows at a time: every lane takes one row, finds its bucket from the key (the same compares as the
+// partition kernel), one ballot per bucket gives the row's rank among the group's rows of that bucket, lane q keeps the
+// address where bucket q's next row goes -- D.base[q] + (row0[q] + off32[t][q]) rows, D.base[q] being the local send buffer
+// (grouped ncclSend path), the rank's own receive buffer, or a PEER GPU's receive buffer (peer mapping: the stores travel
+// over NVLink from the SMs, so the compaction IS the exchange) -- and the lane stores its row there.  Rows of one bucket
+// leave in original order and land contiguously, so neighbouring lanes' stores coalesce.  PX_UNROLL row groups are
+// loaded before the first one is routed.
 constexpr int PX_UNROLL = 4;
 
-template <typename W>   // W = int4 (rows are multiples of 16 bytes and every pointer is 16-byte aligned) or int32_t
+template <bool VEC4>   // VEC4: rows are exactly one 16-byte word and every pointer is 16-byte aligned (the 4-column shapes)
 __global__ void __launch_bounds__(256)
 partition_exchange_kernel(const int32_t *__restrict__ slots, const u32 *__restrict__ tile_counts, const u32 *__restrict__ off32,
-                          u32 num_tiles, int G, u32 tile_rows, int cols, const SmjPartitionDst D)
+                          u32 num_tiles, int G, u32 tile_rows, int cols, int key_col, const u32 *__restrict__ splitters,
+                          const SmjPartitionDst D)
 {
     PDL_ENTER();
     if (D.skip && *D.skip) return;
-    constexpr u32 CPW = sizeof(W) / 4;               // cells per word
-    const u32 wpr = (u32)cols / CPW;                 // words per row
     const u32 lane = threadIdx.x & 31u;
+    const u32 lt = lanemask_lt();
     const u32 warps = gridDim.x * (blockDim.x >> 5);
+    const u64 row_bytes = (u64)cols * 4;
+    u32 sp[PT_MAX_G - 1];
+#pragma unroll
+    for (int q = 0; q < PT_MAX_G - 1; q++) sp[q] = (q < G - 1) ? splitters[q] : 0xffffffffu;
+    // lane q: where this rank's bucket q starts counting rows (byte address)
+    u64 base_q = 0;
+    if (lane < (u32)G) {
+        int32_t *bp = D.base[0];
+#pragma unroll
+        for (int q = 1; q < PT_MAX_G; q++) if (lane == (u32)q) bp = D.base[q];
+        base_q = reinterpret_cast<u64>(bp) + (D.row0 ? D.row0[lane] : 0ull) * row_bytes;
+    }
     for (u32 t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < num_tiles; t += warps) {
-        u32 cnt = 0, off = 0;
-        u64 r0 = 0;
+        u32 cnt = 0;
+        u64 cur_q = 0;   // lane q: byte address of the next row of bucket q
         if (lane < (u32)G) {
             cnt = tile_counts[(size_t)t * PT_MAX_G + lane];
-            off = off32[(size_t)t * PT_MAX_G + lane];
-            r0 = D.row0 ? D.row0[lane] : 0ull;
+            cur_q = base_q + (u64)off32[(size_t)t * PT_MAX_G + lane] * row_bytes;
         }
-        const u32 incl = warp_incl_scan(cnt);
-        const u32 total_w = __shfl_sync(FULL_MASK, incl, PT_MAX_G - 1) * wpr;
-        if (total_w == 0) continue;
-        // per bucket: first word of its segment inside the slot, and where that word goes
-        u32 start_w[PT_MAX_G];
-        W *dstp[PT_MAX_G];
-#pragma unroll
-        for (int b = 0; b < PT_MAX_G; b++) {
-            start_w[b] = (__shfl_sync(FULL_MASK, incl, b) - __shfl_sync(FULL_MASK, cnt, b)) * wpr;
-            const u64 row = __shfl_sync(FULL_MASK, r0, b) + (u64)__shfl_sync(FULL_MASK, off, b);
-            dstp[b] = reinterpret_cast<W *>(D.base[b]) + row * wpr;
-        }
-        const W *src = reinterpret_cast<const W *>(slots + (size_t)t * tile_rows * cols);
-        for (u32 i0 = 0; i0 < total_w; i0 += 32 * PX_UNROLL) {
-            W v[PX_UNROLL];
+        const u32 total = __reduce_add_sync(FULL_MASK, cnt);
+        const int32_t *src = slots + (size_t)t * tile_rows * cols;
+        for (u32 i0 = 0; i0 < total; i0 += 32 * PX_UNROLL) {
+            int4 r4[VEC4 ? PX_UNROLL : 1];
+            int32_t kv[PX_UNROLL];
 #pragma unroll
             for (int k = 0; k < PX_UNROLL; k++) {
                 const u32 i = i0 + k * 32 + lane;
-                if (i < total_w) v[k] = __ldcs(src + i);   // read once
+                kv[k] = 0;
+                if (i < total) {
+                    if (VEC4) {
+                        const int4 r = __ldcs(reinterpret_cast<const int4 *>(src) + i);   // read once
+                        r4[VEC4 ? k : 0] = r;
+                        kv[k] = key_col == 0 ? r.x : key_col == 1 ? r.y : key_col == 2 ? r.z : r.w;
+                    } else {
+                        kv[k] = __ldcs(src + (size_t)i * cols + key_col);
+                    }
+                }
             }
 #pragma unroll
             for (int k = 0; k < PX_UNROLL; k++) {
+                if (i0 + k * 32 >= total) break;       // warp-uniform
                 const u32 i = i0 + k * 32 + lane;
-                if (i < total_w) {
-                    W *d = dstp[0];
-                    u32 s = 0;
+                const bool valid = i < total;
+                const u32 b = pt_bucket((u32)kv[k] ^ 0x80000000u, sp, G);
+                u32 mine = 0, add = 0;
 #pragma unroll
-                    for (int b = 1; b < PT_MAX_G; b++)
-                        if (b < G && i >= start_w[b]) { d = dstp[b]; s = start_w[b]; }
-                    d[i - s] = v[k];
+                for (int q = 0; q < PT_MAX_G; q++) {
+                    if (q < G) {                       // warp-uniform
+                        const u32 mq = __ballot_sync(FULL_MASK, valid && b == (u32)q);
+                        if (b == (u32)q) mine = mq;
+                        if (lane == (u32)q) add = __popc(mq);
+                    }
+                }
+                const u64 dst_b = __shfl_sync(FULL_MASK, cur_q, b);     // bucket b's cursor lives in lane b
+                cur_q += (u64)add * row_bytes;
+                if (valid) {
+                    const u64 dst = dst_b + (u64)__popc(mine & lt) * row_bytes;
+                    if (VEC4) {
+                        *reinterpret_cast<int4 *>(dst) = r4[VEC4 ? k : 0];
+                    } else {
+                        const int32_t *rs = src + (size_t)i * cols;
+                        int32_t *rd = reinterpret_cast<int32_t *>(dst);
+                        if ((cols & 3) == 0 && ((reinterpret_cast<uintptr_t>(rs) | dst) & 15) == 0) {
+                            for (int q = 0; q < cols / 4; q++) reinterpret_cast<int4 *>(rd)[q] = __ldcs(reinterpret_cast<const int4 *>(rs) + q);
+                        } else {
+                            for (int q = 0; q < cols; q++) rd[q] = __ldcs(rs + q);
+                        }
+                    }
                 }
             }
         }
@@ -477,8 +513,8 @@ int smj_launch_select_partition(SmjCtx *c, cudaStream_t st, const int32_t *d_in,
 }
 
 // Stage 2 (on stream st): every (tile, bucket) segment to its place behind D.base[bucket] (see partition_exchange_kernel).
-int smj_launch_partition_exchange(SmjCtx *c, cudaStream_t st, int64_t n, int cols, int sel_val_none, int G, const int32_t *d_slots,
-                                  char *d_scratch, const SmjPartitionDst &D)
+int smj_launch_partition_exchange(SmjCtx *c, cudaStream_t st, int64_t n, int cols, int key_col, const u32 *d_splitters, int sel_val_none,
+                                  int G, const int32_t *d_slots, char *d_scratch, const SmjPartitionDst &D)
 {
     if (n <= 0 || sel_val_none) return SMJ_OK;
     const SmjPartScratch S = smj_partition_scratch(d_scratch, n, cols);
@@ -487,10 +523,12 @@ int smj_launch_partition_exchange(SmjCtx *c, cudaStream_t st, int64_t n, int col
     const u32 cgrid = (u32)((S.tiles + 7) / 8 < (size_t)sms * 8 ? (S.tiles + 7) / 8 : (size_t)sms * 8);
     uintptr_t al = (uintptr_t)d_slots;
     for (int b = 0; b < G; b++) al |= (uintptr_t)D.base[b];
-    if (cols % 4 == 0 && (al & 15) == 0)
-        partition_exchange_kernel<int4><<<cgrid, 256, 0, st>>>(d_slots, S.counts, S.off32, (u32)S.tiles, G, smj_partition_tile_rows(cols), cols, D);
+    if (cols == 4 && (al & 15) == 0)
+        partition_exchange_kernel<true><<<cgrid, 256, 0, st>>>(d_slots, S.counts, S.off32, (u32)S.tiles, G, smj_partition_tile_rows(cols), cols, key_col,
+                                                               d_splitters, D);
     else
-        partition_exchange_kernel<int32_t><<<cgrid, 256, 0, st>>>(d_slots, S.counts, S.off32, (u32)S.tiles, G, smj_partition_tile_rows(cols), cols, D);
+        partition_exchange_kernel<false><<<cgrid, 256, 0, st>>>(d_slots, S.counts, S.off32, (u32)S.tiles, G, smj_partition_tile_rows(cols), cols, key_col,
+                                                                d_splitters, D);
     KERNEL_CHECK(c);
     return SMJ_OK;
 }
@@ -521,8 +559,8 @@ void smj_preload_partition(void)
     cudaFuncGetAttributes(&a, select_partition_kernel);
     cudaFuncGetAttributes(&a, partition_blocksum_kernel);
     cudaFuncGetAttributes(&a, partition_offsets_kernel);
-    cudaFuncGetAttributes(&a, partition_exchange_kernel<int4>);
-    cudaFuncGetAttributes(&a, partition_exchange_kernel<int32_t>);
+    cudaFuncGetAttributes(&a, partition_exchange_kernel<true>);
+    cudaFuncGetAttributes(&a, partition_exchange_kernel<false>);
     cudaFuncGetAttributes(&a, sample_rows_kernel);
     cudaFuncGetAttributes(&a, splitters_kernel);
     cudaGetLastError();

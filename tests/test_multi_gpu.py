@@ -150,19 +150,24 @@ smj_b200.lib().smj_shutdown()
 '''
 
 
-@pytest.mark.parametrize("world,variant", [(2, "default"), (2, "overflow"), (4, "default"), (8, "default")])
+@pytest.mark.parametrize("world,variant", [(2, "default"), (2, "overflow"), (4, "default"), (8, "default"),
+                                           (2, "one_gpu"), (3, "one_gpu"), (4, "one_gpu_overflow"), (8, "one_gpu")])
 def test_one_process_drives_all_gpus(world, variant, tmp_path):
     """smj_run with nr_gpus = G from ONE process (what host/app does with SMJ_NR_GPUS=G): rows dealt to G devices, the
-    exchange over peer memory, ONE result table in key order -- bit-identical to the oracle's single-process result."""
-    if _ngpus() < world:
+    exchange over peer memory, ONE result table in key order -- bit-identical to the oracle's single-process result.
+    The one_gpu variants put all G ranks on device 0 (SMJ_RANKS_ON_ONE_GPU=1): the same mailboxes, bucket routing, receive
+    buffers and verdicts, rank against rank on concurrent streams, on a box with a single GPU."""
+    if _ngpus() < world and not variant.startswith("one_gpu"):
         pytest.skip(f"needs {world} GPUs")
     script = tmp_path / "local.py"
     script.write_text(LOCAL)
     env = dict(os.environ, SMJ_ROOT=ROOT, SMJ_G=str(world))
     for k in ("SMJ_DIST_MODE", "SMJ_DIST_EXCHANGE", "SMJ_DIST_STREAMS", "SMJ_DIST_CAP_PCT"):
         env.pop(k, None)
-    if variant == "overflow":
+    if variant.endswith("overflow"):
         env["SMJ_DIST_CAP_PCT"] = "10"
+    if variant.startswith("one_gpu"):
+        env["SMJ_RANKS_ON_ONE_GPU"] = "1"
     r = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("LOCAL_OK") == 6, r.stdout[-2000:]
