@@ -173,6 +173,9 @@ extern "C" int smj_init(const smj_config_t *cfg)
     }
     if (cfg) g_cfg = *cfg; else smj_config_default(&g_cfg);
     if (g_cfg.nr_gpus < 1) g_cfg.nr_gpus = 1;
+    // all ranks on one GPU: up to 8 x 3 streams whose kernels wait for each other must not share a hardware queue (the default
+    // is 8 connections: rank 7's kernel queued behind rank 0's spinning one never starts).  Read when the context is created.
+    if (getenv("SMJ_RANKS_ON_ONE_GPU") && atoi(getenv("SMJ_RANKS_ON_ONE_GPU")) != 0) setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     const int ndev = smj_device_count();
     if (ndev < 1) return smj_set_error(SMJ_ENODEVICE, "no CUDA device visible (libsmj has no CPU fallback)");
     // SMJ_RANKS_ON_ONE_GPU=1: every rank of the one-process multi-GPU mode gets a context (streams, workspace, pool) on

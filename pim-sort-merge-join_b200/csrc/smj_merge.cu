@@ -42,7 +42,9 @@ __global__ void __launch_bounds__(MG_THREADS)
 merge_pairs_kernel(const u64 *__restrict__ A, u32 na_all, const u64 *__restrict__ B, u32 nb_all,
                    const u32 *__restrict__ part, u64 *__restrict__ out, u32 num_tiles)
 {
-    __shared__ __align__(16) u64 s[2][MG_TILE];
+    // (+ MG_TILE / 16: the merged tile is staged with one pad word per 16 elements -- thread t's eight results sit at 8 t .. 8 t + 7,
+    // a 64-byte stride that made the stores 16-way bank conflicts: 70 % of all shared-memory wavefronts in the first capture)
+    __shared__ __align__(16) u64 s[2][MG_TILE + MG_TILE / 16];
     const u32 tid = threadIdx.x;
     const u64 total = (u64)na_all + nb_all;
     struct Geo { u32 a0, na, b0, nb; u64 d0; };
@@ -94,10 +96,10 @@ merge_pairs_kernel(const u64 *__restrict__ A, u32 na_all, const u64 *__restrict_
         __syncthreads();                                   // every thread has read its inputs: the buffer becomes the output tile
 #pragma unroll
         for (int st = 0; st < MG_VT; st++)
-            if (diag + st < ntile) buf[diag + st] = r[st];
+            if (diag + st < ntile) buf[(diag + st) + ((diag + st) >> 4)] = r[st];
         __syncthreads();
         u64 *dst = out + gc.d0;
-        for (u32 i = tid; i < ntile; i += MG_THREADS) dst[i] = buf[i];
+        for (u32 i = tid; i < ntile; i += MG_THREADS) dst[i] = buf[i + (i >> 4)];
         tile = next;
         cur ^= 1;
         // the next iteration's first barrier orders these reads of buf before the fetch that refills it one round later
@@ -117,7 +119,7 @@ int smj_launch_merge_pairs(SmjCtx *c, const u64 *d_a, u32 na, const u64 *d_b, u3
     KERNEL_CHECK(c);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    const u32 grid = tiles < (u32)(sms * 6) ? tiles : (u32)(sms * 6);   // 32 KB of shared memory per CTA: six fit an SM
+    const u32 grid = tiles < (u32)(sms * 5) ? tiles : (u32)(sms * 5);   // 34 KB of shared memory, 48 registers x 256 threads: five CTAs per SM
     merge_pairs_kernel<<<grid, MG_THREADS, 0, c->stream>>>(d_a, na, d_b, nb, d_part, d_out, tiles);
     KERNEL_CHECK(c);
     return SMJ_OK;
