@@ -89,6 +89,19 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def result_checksum(a):
+    """Order-independent checksum of a result table: sum over rows of a hash of the row's cells, mod 2^64 (numpy)."""
+    import numpy as np
+    if a.size == 0:
+        return 0
+    h = np.zeros(a.shape[0], np.uint64)
+    with np.errstate(over="ignore"):
+        for c in range(a.shape[1]):
+            h = (h ^ a[:, c].astype(np.int64).astype(np.uint64)) * np.uint64(0x9E3779B97F4A7C15)
+            h ^= h >> np.uint64(29)
+        return int(h.sum(dtype=np.uint64))
+
+
 def knobs_for(w):
     """select threshold giving the configured selectivity over keys uniform in [1, 3n]."""
     def thr(n):
@@ -231,6 +244,10 @@ def main():
         L.smj_table_free(C.byref(out))
         return st
 
+    out0, _ = smj_b200.run(d1, d2, cfg=cfg, on_device=True, keep_output=True)
+    # (the multi-GPU arm prints the same pair: rows_joined + result_checksum; skipped above 2 GB of result)
+    checksum = result_checksum(S.to_numpy(out0)) if out0.rows * out0.cols * 4 <= 2e9 else None
+    L.smj_table_free(C.byref(out0))
     for _ in range(args.warmup):
         st = step_device()
     clocks = ClockSampler()
@@ -359,7 +376,7 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": w["desc"], "name": name, "join_mode": "zip (cpu_app.c semantics)",
-                   "rows_selected": st["rows_selected"], "rows_joined": st["rows_joined"],
+                   "rows_selected": st["rows_selected"], "rows_joined": st["rows_joined"], "result_checksum": None if checksum is None else f"{checksum:016x}",
                    "l2": f"inputs ({w['n1'] * w['cols'] * 4 / 1e6:.0f} + {w['n2'] * w['cols'] * 4 / 1e6:.0f} MB) larger than the 126 MB L2; no explicit flush"},
         "stage_ms": {k: v / args.steps for k, v in stages.items()}, "wall_ms_per_step": wall_ms,
         "graph_replayed": replayed, "eager_ms_per_step": eager_ms,

@@ -37,6 +37,19 @@ def run_multi(args, w, name):
         L.smj_table_free(C.byref(out))
         return st
 
+    # order-independent checksum of the whole result (sum over rows of a hash of the row's cells, mod 2^64) and its row
+    # count, summed over the ranks: the same virtual tables must give the same pair at every N (strong scaling) -- a
+    # cheap end-to-end parity check at sizes no CPU oracle reaches (bench.py prints the same pair at N=1)
+    from bench import result_checksum
+    out, st = smj_b200.run(d1, d2, cfg=cfg, on_device=True, keep_output=True)
+    big = smj_b200.dist.max_over_ranks(out.rows * out.cols * 4) > 2e9      # (skipped where a shard would not fit comfortably in host memory)
+    ck = 0 if big else result_checksum(smj_b200.smj.to_numpy(out))
+    L.smj_table_free(C.byref(out))
+    ck_lo = int(smj_b200.dist.sum_over_ranks(ck & 0xffffff)) & 0xffffff          # (float64 all-reduce: 24-bit pieces stay exact)
+    ck_mid = int(smj_b200.dist.sum_over_ranks((ck >> 24) & 0xffffff))
+    ck_hi = int(smj_b200.dist.sum_over_ranks(ck >> 48))
+    checksum = (ck_lo + (ck_mid << 24) + (ck_hi << 48)) & 0xffffffffffffffff
+
     for _ in range(args.warmup):
         st = step()
     clocks = ClockSampler(local)
@@ -107,7 +120,7 @@ def run_multi(args, w, name):
             "config": {"workload": (f"{w['desc']} per GPU (weak scaling)" if args.scaling == "weak" else f"{w['desc']} in all (strong scaling)") +
                                    f": {tot1} x {tot2} rows over {G} GPUs ({n1} x {n2} per GPU), key-range partitioned, sample / count mailboxes and the "
                                    "exchange stores over NVLink peer memory (no NCCL call, no host wait in a step)", "name": name, "join_mode": "zip (cpu_app.c semantics)",
-                       "rows_selected": sel, "rows_joined": joined, "parallelism": f"key-range x{G}",
+                       "rows_selected": sel, "rows_joined": joined, "result_checksum": None if big else f"{checksum:016x}", "parallelism": f"key-range x{G}",
                        "exchange": os.environ.get("SMJ_DIST_EXCHANGE", "fabric") + ("/" + os.environ["SMJ_DIST_MODE"] if os.environ.get("SMJ_DIST_MODE") else ""),
                        "l2": f"per-GPU inputs ({n1 * cols * 4 / 1e6:.0f} + {n2 * cols * 4 / 1e6:.0f} MB) larger than the 126 MB L2; no explicit flush"},
             "stage_ms": stage_max, "wall_ms_per_step": wall_ms, "gpu_launches": launches,

@@ -273,6 +273,7 @@ __device__ __forceinline__ void signal_and_wait(const DistPeers &P, int me, int 
 // starts with a device-side wait, SmjWait), the arrival cell of table t
 __global__ void __launch_bounds__(32) dist_arrive_kernel(const DistPeers P, DistLocal *loc, int me, int G, int t, u64 seq, u32 *err)
 {
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // (launched with programmatic serialization; it never triggers its successor early)
     signal_and_wait(P, me, G, PH_XCHG0 + t, seq, err);
     if (threadIdx.x == 0) {
         __threadfence();
@@ -292,6 +293,7 @@ dist_splitters_kernel(const DistPeers P, DistLocal *loc, int me, int G, u64 seq,
 {
     extern __shared__ u32 s_s[];
     __shared__ int s_valid;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tid = threadIdx.x;
     if (tid == 0) { s_valid = 0; loc->verdict[0] = 0; loc->verdict[1] = 0; loc->rows[0] = 0; loc->rows[1] = 0; loc->seq_now = seq; }
     if (tid < 2 * S) {
@@ -392,6 +394,7 @@ dist_counts_kernel(const DistPeers P, DistLocal *loc, int me, int G, u64 seq, in
 {
     __shared__ u64 s_m[SMJ_MAX_G][SMJ_MAX_G];
     __shared__ u32 s_over;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tid = threadIdx.x;
     if (tid == 0) s_over = 0;
     if (tid < G * G) P.win[tid / G]->counts[t][me][tid % G] = bucket_total[tid % G];
@@ -705,7 +708,7 @@ int dist_step_enqueue(DistRank &K, const smj_config_t *cfg, u64 seq)
         if (!select_all && sel_val[t] >= (int64_t)INT32_MAX) n = 0;
         sj[t] = {K.blk[t].data, n, K.blk[t].cols, sel_col[t], (int32_t)sel_val[t], select_all, key[t]};
     }
-    dist_splitters_kernel<<<1, SPL2_THREADS, (size_t)n_pow2 * 4, c->stream>>>(K.peers, K.loc, me, G, seq, S, sj[0], sj[1], n_pow2, c->d_err);
+    smj_launch_on(c, c->stream, dist_splitters_kernel, 1, SPL2_THREADS, (size_t)n_pow2 * 4, K.peers, K.loc, me, G, seq, S, sj[0], sj[1], n_pow2, c->d_err);
     KERNEL_CHECK(c);
     CUDA_TRY(cudaEventRecord(K.ev[DE_SPLIT], c->stream));
     const bool two = dist_two_streams();
@@ -728,7 +731,7 @@ int dist_step_enqueue(DistRank &K, const smj_config_t *cfg, u64 seq)
             }
         }
         const SmjPartScratch PS = smj_partition_scratch(K.pscr[t], K.none[t] ? 0 : K.blk[t].rows, K.blk[t].cols);
-        dist_counts_kernel<<<1, 64, 0, st>>>(K.peers, K.loc, me, G, seq, t, PS.bucket_total, (u64)K.cap_rows[t], c->d_err);
+        smj_launch_on(c, st, dist_counts_kernel, 1, 64, 0, K.peers, K.loc, me, G, seq, t, (const u64 *)PS.bucket_total, (u64)K.cap_rows[t], c->d_err);
         KERNEL_CHECK(c);
         SmjPartitionDst D = {};
         for (int b = 0; b < G; b++) D.base[b] = K.peer_recv[t][b];
@@ -736,7 +739,7 @@ int dist_step_enqueue(DistRank &K, const smj_config_t *cfg, u64 seq)
         D.skip = &K.loc->verdict[t];
         SMJ_TRY(smj_launch_partition_exchange(c, st, K.blk[t].rows, K.blk[t].cols, key[t], K.loc->split, K.none[t], G, K.slots[t], K.pscr[t], D));
         // every rank's stores must have landed before anybody reads its receive buffer
-        dist_arrive_kernel<<<1, 32, 0, st>>>(K.peers, K.loc, me, G, t, seq, c->d_err);
+        smj_launch_on(c, st, dist_arrive_kernel, 1, 32, 0, K.peers, K.loc, me, G, t, seq, c->d_err);
         KERNEL_CHECK(c);
         CUDA_TRY(cudaEventRecord(K.ev[o == 0 ? DE_XCHG : DE_XCHG2], st));
     }

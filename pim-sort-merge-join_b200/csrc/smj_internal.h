@@ -120,6 +120,18 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 bool smj_pdl_enabled(void);
 bool smj_stage_events(void);
 template <typename... KArgs, typename... Args>
+static inline void smj_launch_on(SmjCtx *c, cudaStream_t st, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (smj_pdl_enabled() && !c->capturing) ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
 static inline void smj_launch(SmjCtx *c, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args)
 {
     cudaLaunchConfig_t cfg = {};

@@ -16,6 +16,7 @@
 //   sample_rows_kernel      : regular row samples (predicate applied) from which the splitters are derived.
 #include "smj_internal.h"
 #include "smj_dev.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -383,6 +384,104 @@ partition_exchange_kernel(const int32_t *__restrict__ slots, const u32 *__restri
             }
         }
     }
+    // Every thread waits until its own stores -- most of them into peer memory, posted over NVLink -- have been performed
+    // system-wide before the kernel may count as finished: the arrival flag that the next kernel on the stream sends must
+    // not overtake a row still in flight.  (Without it, 14 of 3.33 M joined rows were missing at 250M x 50M rows per GPU on
+    // two GPUs: the largest exchange that had been run; every smaller one had passed.)
+    __threadfence_system();
+}
+
+// The same routing with the rows of every bucket STAGED in shared memory, 32 at a time: with G destinations a group of 32
+// rows holds ~32 / G rows per bucket, so the direct version above stores runs of 64 bytes (G = 8) that start anywhere --
+// partial lines, two NVLink packets per run.  Here a warp keeps a 32-row (512-byte) buffer per bucket; rows go into their
+// bucket's buffer at (fill + rank), a full buffer leaves as ONE 512-byte coalesced warp store, rows that did not fit go
+// into the emptied buffer, and what is left at the end of the tile is flushed.  4-column tables only (16-byte rows).
+constexpr int PXS_WARPS = 8;
+constexpr size_t PXS_SMEM = (size_t)PXS_WARPS * PT_MAX_G * 32 * 16;   // 32 KB
+
+__global__ void __launch_bounds__(PXS_WARPS * 32)
+partition_exchange_staged_kernel(const int32_t *__restrict__ slots, const u32 *__restrict__ tile_counts, const u32 *__restrict__ off32,
+                                 u32 num_tiles, int G, u32 tile_rows, int key_col, const u32 *__restrict__ splitters, const SmjPartitionDst D)
+{
+    extern __shared__ __align__(16) int4 pxs_stage[];
+    PDL_ENTER();
+    if (D.skip && *D.skip) return;
+    const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const u32 lt = lanemask_lt();
+    const u32 warps = gridDim.x * PXS_WARPS;
+    int4 *stage = pxs_stage + (size_t)w * PT_MAX_G * 32;     // [bucket][32 rows]
+    u32 sp[PT_MAX_G - 1];
+#pragma unroll
+    for (int q = 0; q < PT_MAX_G - 1; q++) sp[q] = (q < G - 1) ? splitters[q] : 0xffffffffu;
+    u64 base_q = 0;
+    if (lane < (u32)G) {
+        int32_t *bp = D.base[0];
+#pragma unroll
+        for (int q = 1; q < PT_MAX_G; q++) if (lane == (u32)q) bp = D.base[q];
+        base_q = reinterpret_cast<u64>(bp) + (D.row0 ? D.row0[lane] : 0ull) * 16ull;
+    }
+    for (u32 t = blockIdx.x * PXS_WARPS + w; t < num_tiles; t += warps) {
+        u32 cnt = 0, fill_q = 0;   // lane q: rows of bucket q waiting in its buffer
+        u64 cur_q = 0;             // lane q: byte address of the next row of bucket q that leaves
+        if (lane < (u32)G) {
+            cnt = tile_counts[(size_t)t * PT_MAX_G + lane];
+            cur_q = base_q + (u64)off32[(size_t)t * PT_MAX_G + lane] * 16ull;
+        }
+        const u32 total = __reduce_add_sync(FULL_MASK, cnt);
+        const int4 *src = reinterpret_cast<const int4 *>(slots + (size_t)t * tile_rows * 4);
+        for (u32 i0 = 0; i0 < total; i0 += 32 * PX_UNROLL) {
+            int4 r4[PX_UNROLL];
+#pragma unroll
+            for (int k = 0; k < PX_UNROLL; k++) {
+                const u32 i = i0 + k * 32 + lane;
+                r4[k] = i < total ? __ldcs(src + i) : make_int4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int k = 0; k < PX_UNROLL; k++) {
+                if (i0 + k * 32 >= total) break;       // warp-uniform
+                const u32 i = i0 + k * 32 + lane;
+                const bool valid = i < total;
+                const int32_t kv = key_col == 0 ? r4[k].x : key_col == 1 ? r4[k].y : key_col == 2 ? r4[k].z : r4[k].w;
+                const u32 b = pt_bucket((u32)kv ^ 0x80000000u, sp, G);
+                u32 mine = 0, add = 0;
+#pragma unroll
+                for (int q = 0; q < PT_MAX_G; q++) {
+                    if (q < G) {                       // warp-uniform
+                        const u32 mq = __ballot_sync(FULL_MASK, valid && b == (u32)q);
+                        if (b == (u32)q) mine = mq;
+                        if (lane == (u32)q) add = __popc(mq);
+                    }
+                }
+                const u32 pos = __shfl_sync(FULL_MASK, fill_q, b) + __popc(mine & lt);   // slot in bucket b's buffer (may reach 62)
+                if (valid && pos < 32u) stage[b * 32 + pos] = r4[k];
+                __syncwarp();
+                // buffers that are full now leave as one 512-byte store each
+                u32 full = __ballot_sync(FULL_MASK, lane < (u32)G && fill_q + add >= 32u);
+                while (full) {
+                    const int q = __ffs(full) - 1;
+                    full &= full - 1;
+                    const u64 dst = __shfl_sync(FULL_MASK, cur_q, q);
+                    reinterpret_cast<int4 *>(dst)[lane] = stage[q * 32 + lane];
+                    if (lane == (u32)q) cur_q += 512ull;
+                }
+                __syncwarp();
+                if (valid && pos >= 32u) stage[b * 32 + (pos - 32u)] = r4[k];          // the rows that did not fit: into the emptied buffer
+                if (lane < (u32)G) { fill_q += add; if (fill_q >= 32u) fill_q -= 32u; }
+                __syncwarp();
+            }
+        }
+        // what is left of the tile
+#pragma unroll
+        for (int q = 0; q < PT_MAX_G; q++) {
+            if (q < G) {
+                const u32 f = __shfl_sync(FULL_MASK, fill_q, q);
+                const u64 dst = __shfl_sync(FULL_MASK, cur_q, q);
+                if (lane < f) reinterpret_cast<int4 *>(dst)[lane] = stage[q * 32 + lane];
+            }
+        }
+        __syncwarp();
+    }
+    __threadfence_system();   // see partition_exchange_kernel
 }
 
 // samples[i] = flipped key of row floor((2i+1) n / 2S) if it passes the predicate, else 0xffffffff
@@ -501,13 +600,22 @@ int smj_launch_select_partition(SmjCtx *c, cudaStream_t st, const int32_t *d_in,
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     const int ipt = pt_ipt(cols);
-    const u32 grid = S.tiles < (size_t)(sms * 3) ? (u32)S.tiles : (u32)(sms * 3);
-    select_partition_kernel<<<grid, PTW_THREADS, PTW_SMEM, st>>>(d_in, n, cols, ipt, sel_col, (int32_t)sel_val, select_all, key_col,
-                                                                d_splitters, G, d_slots, S.counts, (u32)S.tiles);
+    // Two CTAs per SM, not the three that fit: this kernel's persistent CTAs hold their SM for the whole pass, and with three
+    // of them (3 x 288 threads x 72 registers = the whole register file) the OTHER table's exchange kernel, launched on the
+    // second stream to overlap with this pass, could not place a single CTA until this kernel drained -- the two chains ran
+    // one after the other (first arrival 166 us after the first partition pass at two GPUs, 105 us without the overlap).
+    static const int pt_ctas = getenv("SMJ_PT_CTAS") ? atoi(getenv("SMJ_PT_CTAS")) : 2;
+    const u32 per_sm = (u32)(pt_ctas >= 1 && pt_ctas <= 3 ? pt_ctas : 2);
+    const u32 grid = S.tiles < (size_t)(sms * per_sm) ? (u32)S.tiles : (u32)(sms * per_sm);
+    // (the chain's kernels are launched with programmatic stream serialization: each becomes resident while its predecessor
+    // drains and starts with griddepcontrol.wait, which takes the launch latency out of a chain of seven kernels per table)
+    smj_launch_on(c, st, select_partition_kernel, grid, PTW_THREADS, PTW_SMEM, d_in, n, cols, ipt, sel_col, (int32_t)sel_val, select_all, key_col,
+                  d_splitters, G, d_slots, S.counts, (u32)S.tiles);
     KERNEL_CHECK(c);
-    partition_blocksum_kernel<<<(u32)S.ctas, PS_THREADS, 0, st>>>(S.counts, (u32)S.tiles, S.blocksum);
+    smj_launch_on(c, st, partition_blocksum_kernel, (u32)S.ctas, PS_THREADS, 0, (const u32 *)S.counts, (u32)S.tiles, S.blocksum);
     KERNEL_CHECK(c);
-    partition_offsets_kernel<<<(u32)S.ctas, PS_THREADS, 0, st>>>(S.counts, (u32)S.tiles, G, S.blocksum, S.off32, S.bucket_total, S.bucket_start);
+    smj_launch_on(c, st, partition_offsets_kernel, (u32)S.ctas, PS_THREADS, 0, (const u32 *)S.counts, (u32)S.tiles, G, (const u64 *)S.blocksum, S.off32,
+                  S.bucket_total, S.bucket_start);
     KERNEL_CHECK(c);
     return SMJ_OK;
 }
@@ -523,12 +631,21 @@ int smj_launch_partition_exchange(SmjCtx *c, cudaStream_t st, int64_t n, int col
     const u32 cgrid = (u32)((S.tiles + 7) / 8 < (size_t)sms * 8 ? (S.tiles + 7) / 8 : (size_t)sms * 8);
     uintptr_t al = (uintptr_t)d_slots;
     for (int b = 0; b < G; b++) al |= (uintptr_t)D.base[b];
-    if (cols == 4 && (al & 15) == 0)
-        partition_exchange_kernel<true><<<cgrid, 256, 0, st>>>(d_slots, S.counts, S.off32, (u32)S.tiles, G, smj_partition_tile_rows(cols), cols, key_col,
-                                                               d_splitters, D);
+    static const int stage_min_g = getenv("SMJ_DIST_STAGE_MIN_G") ? atoi(getenv("SMJ_DIST_STAGE_MIN_G")) : 3;
+    if (cols == 4 && (al & 15) == 0 && G >= stage_min_g) {
+        static bool attr_set[16] = {};
+        if (!attr_set[c->device & 15]) {
+            CUDA_TRY(cudaFuncSetAttribute(partition_exchange_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PXS_SMEM));
+            attr_set[c->device & 15] = true;
+        }
+        smj_launch_on(c, st, partition_exchange_staged_kernel, cgrid, PXS_WARPS * 32, PXS_SMEM, d_slots, (const u32 *)S.counts, (const u32 *)S.off32,
+                      (u32)S.tiles, G, smj_partition_tile_rows(cols), key_col, d_splitters, D);
+    } else if (cols == 4 && (al & 15) == 0)
+        smj_launch_on(c, st, partition_exchange_kernel<true>, cgrid, 256, 0, d_slots, (const u32 *)S.counts, (const u32 *)S.off32, (u32)S.tiles, G,
+                      smj_partition_tile_rows(cols), cols, key_col, d_splitters, D);
     else
-        partition_exchange_kernel<false><<<cgrid, 256, 0, st>>>(d_slots, S.counts, S.off32, (u32)S.tiles, G, smj_partition_tile_rows(cols), cols, key_col,
-                                                                d_splitters, D);
+        smj_launch_on(c, st, partition_exchange_kernel<false>, cgrid, 256, 0, d_slots, (const u32 *)S.counts, (const u32 *)S.off32, (u32)S.tiles, G,
+                      smj_partition_tile_rows(cols), cols, key_col, d_splitters, D);
     KERNEL_CHECK(c);
     return SMJ_OK;
 }
@@ -561,6 +678,7 @@ void smj_preload_partition(void)
     cudaFuncGetAttributes(&a, partition_offsets_kernel);
     cudaFuncGetAttributes(&a, partition_exchange_kernel<true>);
     cudaFuncGetAttributes(&a, partition_exchange_kernel<false>);
+    cudaFuncGetAttributes(&a, partition_exchange_staged_kernel);
     cudaFuncGetAttributes(&a, sample_rows_kernel);
     cudaFuncGetAttributes(&a, splitters_kernel);
     cudaGetLastError();
