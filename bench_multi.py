@@ -45,7 +45,7 @@ def run_multi(args, w, name):
     big = smj_b200.dist.max_over_ranks(out.rows * out.cols * 4) > 2e9      # (skipped where a shard would not fit comfortably in host memory)
     ck = 0 if big else result_checksum(smj_b200.smj.to_numpy(out))
     L.smj_table_free(C.byref(out))
-    ck_lo = int(smj_b200.dist.sum_over_ranks(ck & 0xffffff)) & 0xffffff          # (float64 all-reduce: 24-bit pieces stay exact)
+    ck_lo = int(smj_b200.dist.sum_over_ranks(ck & 0xffffff))                     # (float64 all-reduce: 24-bit pieces stay exact; carries kept)
     ck_mid = int(smj_b200.dist.sum_over_ranks((ck >> 24) & 0xffffff))
     ck_hi = int(smj_b200.dist.sum_over_ranks(ck >> 48))
     checksum = (ck_lo + (ck_mid << 24) + (ck_hi << 48)) & 0xffffffffffffffff

@@ -26,8 +26,12 @@ __device__ unsigned long long g_phase_cycles[16];
 
 namespace {
 
-constexpr int RS_THREADS = 512;
+#ifndef SMJ_RS_THREADS
+#define SMJ_RS_THREADS 512
+#endif
+constexpr int RS_THREADS = SMJ_RS_THREADS;   // 512: two CTAs of 8192 pairs per SM; 256: four of 4096 (tools/build_variant.sh rs256)
 constexpr int RS_IPT = 16;
+constexpr int RS_CTAS_PER_SM = 1024 / RS_THREADS;
 constexpr int RS_TILE = RS_THREADS * RS_IPT;   // 8192 pairs = 64 KB
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr u32 RS_FLAG_LOCAL = 1u << 30, RS_FLAG_INCL = 2u << 30, RS_VAL_MASK = (1u << 30) - 1;
@@ -102,7 +106,7 @@ struct RadixProblem {
 };
 struct RadixLaunch { RadixProblem p[2]; int nprob; };
 
-__global__ void __launch_bounds__(RS_THREADS, 2)
+__global__ void __launch_bounds__(RS_THREADS, RS_CTAS_PER_SM)
 radix_pass_kernel(const RadixLaunch L, int pass, u32 *tile_counter, u32 *err, int dyn_tiles)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -397,7 +401,7 @@ static int launch_radix_pass(SmjCtx *c, const RadixLaunch &L, int pass, u32 *d_t
     size_t tiles = 0;   // the smallest tile is one item per thread
     for (int i = 0; i < L.nprob; i++) tiles += dyn_tiles ? ((size_t)L.p[i].n_max + RS_THREADS - 1) / RS_THREADS : smj_radix_num_tiles(L.p[i].n_max);
     if (tiles == 0) return SMJ_OK;
-    const u32 grid = tiles < (size_t)(sms * 2) ? (u32)tiles : (u32)(sms * 2);
+    const u32 grid = tiles < (size_t)(sms * RS_CTAS_PER_SM) ? (u32)tiles : (u32)(sms * RS_CTAS_PER_SM);
     smj_launch(c, radix_pass_kernel, grid, RS_THREADS, RS_SMEM, L, pass, d_tile_counter, c->d_err, dyn_tiles);
     KERNEL_CHECK(c);
     return SMJ_OK;

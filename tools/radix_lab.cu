@@ -10,7 +10,6 @@
 int smj_set_error(int code, const char *fmt, ...) { va_list ap; va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap); fprintf(stderr, "\n"); return code; }
 bool smj_pdl_enabled(void) { return false; }
 bool smj_stage_events(void) { return true; }
-bool smj_stage_events(void) { return true; }
 int smj_cuda_fail(cudaError_t e, const char *what, const char *file, int line) { fprintf(stderr, "CUDA %s at %s:%d (%s)\n", cudaGetErrorString(e), file, line, what); return SMJ_ECUDA; }
 
 int main(int argc, char **argv)
