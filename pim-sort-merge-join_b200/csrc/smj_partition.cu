@@ -8,11 +8,11 @@
 // the receiver's runs arrive in source-rank order, and a stable sort by key on the receiver reproduces the
 // reference's stable order.  All passes are sequential streams; no row is gathered at random before it travels.
 //
-//   select_partition_kernel : TMA-fed like select_tma_kernel (1 producer warp, 8 compute warps).  Per tile: predicate,
-//                             ballot/popc ranks, the surviving rows written compacted (original order) into the tile's
-//                             own slot, bucket id (<= 7 compares) and G survivor counts per tile.
+//   partition_pass_kernel   : TMA-fed like select_tma_kernel (1 producer warp, 8 compute warps), run twice over the table:
+//                             the count pass (predicate, bucket id, G survivor counts per tile) and, once the offsets
+//                             and the peers' counts are known, the route pass that stores every surviving row straight
+//                             to its destination.
 //   partition_blocksum / partition_offsets_kernel: offsets of every (bucket, tile) segment + bucket totals, many CTAs.
-//   partition_exchange_kernel: one warp per tile routes the tile's surviving rows, 32 at a time, to their buckets' destinations.
 //   sample_rows_kernel      : regular row samples (predicate applied) from which the splitters are derived.
 #include "smj_internal.h"
 #include "smj_dev.cuh"
@@ -40,28 +40,49 @@ __device__ __forceinline__ u32 pt_bucket(u32 fk, const u32 (&sp)[PT_MAX_G - 1], 
     return b;
 }
 
-// Per tile: predicate, the survivors' ranks (one ballot per row group, exactly as select_tma_kernel), the survivors' ROWS
-// written compacted in ORIGINAL ORDER into the tile's own slot, and the tile's survivor count per destination bucket (one
-// ballot per bucket and row group; lane q keeps bucket q's count).  The rows are NOT grouped by bucket here: the first two
-// versions ordered every tile's slot by bucket (a 64-bit shuffle scan per row group, then a 512-entry scan and three
-// barriers per tile) and ncu showed the kernel issue-bound -- 150 instructions per row, 65 % issue-active, 70 us per
-// 160 MB table against 33 us for the plain select stream.  The exchange kernel routes the rows instead: it is bound by
-// NVLink and has the issue slots to spare.
-__global__ void __launch_bounds__(PTW_THREADS, 3)
-select_partition_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, int sel_col, int32_t sel_val, int select_all,
-                        int key_col, const u32 *__restrict__ splitters, int G, int32_t *__restrict__ slots,
-                        u32 *__restrict__ tile_counts /*[tiles][PT_MAX_G]*/, u32 num_tiles)
+// The partition is TWO streaming passes over the table, both TMA-fed like select_tma_kernel (one producer warp, a two-stage
+// ring of 32 KB tiles, eight compute warps), and NO intermediate copy of the rows:
+//   count pass (ROUTE = false): predicate + bucket per row, the tile's survivor count per bucket (tile_counts);
+//   route pass (ROUTE = true) : the same evaluation again, then every surviving row is stored from shared memory straight
+//                               to its place behind D.base[bucket] -- the local send buffer (ncclSend path), the rank's own
+//                               receive buffer, or a PEER GPU's receive buffer (peer mapping: NVLink stores from the SMs,
+//                               the compaction IS the exchange).
+// Inside a tile warp w owns 32 * ipt CONSECUTIVE rows, so original order inside a bucket is warp-major: one barrier per tile
+// shares the eight warps' bucket counts, after which a warp knows where its first row of every bucket goes (the segment's
+// offset from the scan + the counts of the warps before it) and walks its row groups with running cursors: one ballot per
+// bucket ranks a group's rows, lane q keeps bucket q's cursor, every lane stores its own row.
+// History: the first versions wrote the survivors into per-tile slots (bucket-ordered: a 64-bit shuffle scan per row group,
+// a 512-entry scan and three barriers per tile; then order-preserving with routing in a second kernel).  Both spent
+// 70-80 us per 160 MB table in the slot-writing pass -- the per-tile dependency chain, not bandwidth, with two or three CTAs
+// per SM -- plus 80 MB of slot traffic each way.  Reading the table twice costs less than writing and re-reading the slots.
+// STAGED (route pass, 16-byte rows): the rows of every bucket are collected in a 512-byte buffer per warp and leave as one
+// coalesced store; without it a group of 32 rows leaves as G runs of ~32 / G rows that start anywhere (partial lines over
+// NVLink).
+struct PartPassArgs {
+    const int32_t *in; int64_t n; int cols, ipt, sel_col; int32_t sel_val; int select_all, key_col; const u32 *splitters; int G;
+    u32 *tile_counts;            // count pass: out [tiles][PT_MAX_G]
+    const u32 *off32;            // route pass: offsets of the (tile, bucket) segments inside their buckets
+    u32 num_tiles;
+};
+constexpr size_t PTW_SMEM_STAGED = PTW_SMEM + (size_t)PT_WARPS * PT_MAX_G * 32 * 16;
+
+template <bool ROUTE, bool STAGED>
+__global__ void __launch_bounds__(PTW_THREADS, 2)
+partition_pass_kernel(const PartPassArgs A, const SmjPartitionDst D)
 {
     extern __shared__ __align__(128) unsigned char pt_smem[];
     __shared__ __align__(8) u64 s_full[PT_STAGES], s_empty[PT_STAGES];
-    __shared__ u32 s_cnt[2][PT_IPT * PT_WARPS];          // [row group][warp] survivors, double-buffered: one barrier per tile
-    __shared__ u32 s_wb[2][PT_WARPS][PT_MAX_G];          // per warp: survivors per bucket
+    __shared__ u32 s_wb[2][PT_WARPS][PT_MAX_G];          // per warp: survivors per bucket (double-buffered: one barrier per tile)
     __shared__ u32 s_split[PT_MAX_G];
 
     PDL_ENTER();
+    if (ROUTE && D.skip && *D.skip) return;
+    const int cols = A.cols, ipt = A.ipt, G = A.G;
+    const int64_t n = A.n;
+    const u32 num_tiles = A.num_tiles;
     const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
     const u32 tile_rows = (u32)ipt * PT_THREADS;
-    if (tid < (u32)PT_MAX_G) s_split[tid] = (tid < (u32)(G - 1)) ? splitters[tid] : 0xffffffffu;
+    if (tid < (u32)PT_MAX_G) s_split[tid] = (tid < (u32)(G - 1)) ? A.splitters[tid] : 0xffffffffu;
     if (tid == 0) {
         for (int st = 0; st < PT_STAGES; st++) { mbar_init(&s_full[st], 1); mbar_init(&s_empty[st], PT_WARPS); }
         mbar_fence_init();
@@ -79,7 +100,7 @@ select_partition_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int
             const int64_t rows = (n - row0 < (int64_t)tile_rows) ? (n - row0) : (int64_t)tile_rows;
             const u32 bytes = (u32)(rows * row_bytes);
             const u32 b16 = bytes & ~15u;
-            const unsigned char *src = reinterpret_cast<const unsigned char *>(in) + (size_t)row0 * row_bytes;
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(A.in) + (size_t)row0 * row_bytes;
             unsigned char *dst = pt_smem + (size_t)stage * PT_STAGE_BYTES;
             for (u32 b = b16; b < bytes; b += 4)
                 *reinterpret_cast<int32_t *>(dst + b) = *reinterpret_cast<const int32_t *>(src + b);
@@ -96,35 +117,43 @@ select_partition_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int
 
     // ---------------------------------------- compute warps
     const u32 lt = lanemask_lt();
-    const bool vec = (cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(slots) & 15) == 0);
+    const u64 row_bytes = (u64)cols * 4;
     u32 sp[PT_MAX_G - 1];
 #pragma unroll
     for (int q = 0; q < PT_MAX_G - 1; q++) sp[q] = s_split[q];
+    u64 base_q = 0;        // route pass, lane q: byte address where this rank's bucket q starts counting rows
+    if (ROUTE && lane < (u32)G) {
+        int32_t *bp = D.base[0];
+#pragma unroll
+        for (int q = 1; q < PT_MAX_G; q++) if (lane == (u32)q) bp = D.base[q];
+        base_q = reinterpret_cast<u64>(bp) + (D.row0 ? D.row0[lane] : 0ull) * row_bytes;
+    }
+    const bool vec = (cols % 4 == 0);   // (the launcher checks the 16-byte alignment of every destination for this)
+    int4 *stage_buf = STAGED ? reinterpret_cast<int4 *>(pt_smem + PTW_SMEM) + (size_t)w * PT_MAX_G * 32 : nullptr;   // [bucket][32 rows]
     u32 stage = 0, parity = 0, it = 0;
     for (u32 tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, it++) {
+        u32 off_q = 0;     // route pass: in flight while the tile is waited for
+        if (ROUTE && lane < (u32)G) off_q = A.off32[(size_t)tile * PT_MAX_G + lane];
         mbar_wait(&s_full[stage], parity);
         const int64_t tile_base = (int64_t)tile * tile_rows;
         const u32 rows_valid = (u32)((n - tile_base < (int64_t)tile_rows) ? (n - tile_base) : (int64_t)tile_rows);
         const int32_t *s_rows = reinterpret_cast<const int32_t *>(pt_smem + (size_t)stage * PT_STAGE_BYTES);
-        u32 *cntbuf = s_cnt[it & 1u];
-        u32 rank[PT_IPT];
-        u32 passmask = 0, bcnt = 0;   // bcnt: lane q counts this warp's survivors of bucket q
+        const u32 wrow0 = w * (u32)ipt * 32u;          // this warp's first row inside the tile
+        u32 passmask = 0, bpack = 0, bcnt = 0;         // bpack: 3 bits of bucket per row group; bcnt: lane q counts bucket q
 #pragma unroll
         for (int j = 0; j < PT_IPT; j++) {
             if (j < ipt) {
-                const u32 row = j * PT_THREADS + tid;
+                const u32 row = wrow0 + (u32)j * 32u + lane;
                 bool pass = false;
                 u32 b = 0;
                 if (row < rows_valid) {
-                    const int32_t sv = s_rows[row * cols + sel_col];
-                    const int32_t kv = (key_col == sel_col) ? sv : s_rows[row * cols + key_col];
-                    pass = select_all || sv > sel_val;
+                    const int32_t sv = s_rows[row * cols + A.sel_col];
+                    const int32_t kv = (A.key_col == A.sel_col) ? sv : s_rows[row * cols + A.key_col];
+                    pass = A.select_all || sv > A.sel_val;
                     b = pt_bucket((u32)kv ^ 0x80000000u, sp, G);
                 }
-                const u32 m = __ballot_sync(FULL_MASK, pass);
-                if (lane == 0) cntbuf[j * PT_WARPS + w] = __popc(m);
-                rank[j] = __popc(m & lt);
                 passmask |= (pass ? 1u : 0u) << j;
+                bpack |= b << (3 * j);
 #pragma unroll
                 for (int q = 0; q < PT_MAX_G; q++) {
                     if (q < G) {   // warp-uniform
@@ -132,45 +161,89 @@ select_partition_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int
                         if (lane == (u32)q) bcnt += __popc(mq);
                     }
                 }
-            } else if (lane == 0) {
-                cntbuf[j * PT_WARPS + w] = 0;
             }
         }
         if (lane < (u32)PT_MAX_G) s_wb[it & 1u][w][lane] = bcnt;
-        named_bar_sync(1, PT_THREADS);                 // counts complete (double-buffered: one barrier per tile)
-        if (tid < (u32)PT_MAX_G) {
-            u32 t = 0;
+        named_bar_sync(1, PT_THREADS);                 // the eight warps' counts are complete (one barrier per tile)
+        if (!ROUTE) {
+            if (tid < (u32)PT_MAX_G) {
+                u32 t = 0;
 #pragma unroll
-            for (int ww = 0; ww < PT_WARPS; ww++) t += s_wb[it & 1u][ww][tid];
-            tile_counts[(size_t)tile * PT_MAX_G + tid] = t;
-        }
-        // every warp scans the 64 (row group, warp) counts itself
-        const u32 v0 = cntbuf[2 * lane], v1 = cntbuf[2 * lane + 1];
-        const u32 inc = warp_incl_scan(v0 + v1);
-        const u32 ex0 = inc - (v0 + v1);
-        int32_t *dst_tile = slots + (size_t)tile_base * cols;
+                for (int ww = 0; ww < PT_WARPS; ww++) t += s_wb[it & 1u][ww][tid];
+                A.tile_counts[(size_t)tile * PT_MAX_G + tid] = t;
+            }
+        } else {
+            u64 cur_q = 0;     // lane q: byte address of bucket q's next row from this warp
+            u32 fill_q = 0;    // STAGED, lane q: rows of bucket q waiting in the warp's buffer
+            if (lane < (u32)G) {
+                u32 before = off_q;
+                for (u32 ww = 0; ww < w; ww++) before += s_wb[it & 1u][ww][lane];
+                cur_q = base_q + (u64)before * row_bytes;
+            }
 #pragma unroll
-        for (int j = 0; j < PT_IPT; j++) {
-            const u32 e = (u32)j * PT_WARPS + w;       // warp-uniform entry index
-            u32 off = __shfl_sync(FULL_MASK, ex0, e >> 1);
-            const u32 add = __shfl_sync(FULL_MASK, v0, e >> 1);
-            if (e & 1u) off += add;
-            if ((passmask >> j) & 1u) {
-                const u32 row = j * PT_THREADS + tid;
-                const int32_t *src = s_rows + row * cols;
-                int32_t *dst = dst_tile + (size_t)(off + rank[j]) * cols;
-                if (vec) {
-                    for (int q = 0; q < cols / 4; q++)
-                        reinterpret_cast<int4 *>(dst)[q] = reinterpret_cast<const int4 *>(src)[q];
-                } else {
-                    for (int q = 0; q < cols; q++) dst[q] = src[q];
+            for (int j = 0; j < PT_IPT; j++) {
+                if (j < ipt) {
+                    const bool pass = (passmask >> j) & 1u;
+                    const u32 b = (bpack >> (3 * j)) & 7u;
+                    if (__ballot_sync(FULL_MASK, pass) == 0u) continue;   // warp-uniform: nothing survives in this group
+                    u32 mine = 0, add = 0;
+#pragma unroll
+                    for (int q = 0; q < PT_MAX_G; q++) {
+                        if (q < G) {
+                            const u32 mq = __ballot_sync(FULL_MASK, pass && b == (u32)q);
+                            if (b == (u32)q) mine = mq;
+                            if (lane == (u32)q) add = __popc(mq);
+                        }
+                    }
+                    const int32_t *srow = s_rows + (wrow0 + (u32)j * 32u + lane) * cols;
+                    if (STAGED) {
+                        const u32 pos = __shfl_sync(FULL_MASK, fill_q, b) + __popc(mine & lt);   // slot in bucket b's buffer (may reach 62)
+                        const int4 r = pass ? *reinterpret_cast<const int4 *>(srow) : make_int4(0, 0, 0, 0);
+                        if (pass && pos < 32u) stage_buf[b * 32 + pos] = r;
+                        __syncwarp();
+                        u32 full = __ballot_sync(FULL_MASK, lane < (u32)G && fill_q + add >= 32u);   // full buffers leave as 512-byte stores
+                        while (full) {
+                            const int q = __ffs(full) - 1;
+                            full &= full - 1;
+                            const u64 dst = __shfl_sync(FULL_MASK, cur_q, q);
+                            reinterpret_cast<int4 *>(dst)[lane] = stage_buf[q * 32 + lane];
+                            if (lane == (u32)q) cur_q += 512ull;
+                        }
+                        __syncwarp();
+                        if (pass && pos >= 32u) stage_buf[b * 32 + (pos - 32u)] = r;           // rows that did not fit: into the emptied buffer
+                        if (lane < (u32)G) { fill_q += add; if (fill_q >= 32u) fill_q -= 32u; }
+                        __syncwarp();
+                    } else {
+                        const u64 dst_b = __shfl_sync(FULL_MASK, cur_q, b);     // bucket b's cursor lives in lane b
+                        cur_q += (u64)add * row_bytes;
+                        if (pass) {
+                            int32_t *rd = reinterpret_cast<int32_t *>(dst_b + (u64)__popc(mine & lt) * row_bytes);
+                            if (vec) for (int q = 0; q < cols / 4; q++) reinterpret_cast<int4 *>(rd)[q] = reinterpret_cast<const int4 *>(srow)[q];
+                            else for (int q = 0; q < cols; q++) rd[q] = srow[q];
+                        }
+                    }
+                }
+            }
+            if (STAGED) {   // what is left of this warp's part of the tile
+#pragma unroll
+                for (int q = 0; q < PT_MAX_G; q++) {
+                    if (q < G) {
+                        const u32 f = __shfl_sync(FULL_MASK, fill_q, q);
+                        const u64 dst = __shfl_sync(FULL_MASK, cur_q, q);
+                        if (lane < f) reinterpret_cast<int4 *>(dst)[lane] = stage_buf[q * 32 + lane];
+                    }
                 }
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[stage]);   // rows copied out: the stage can be refilled
+        if (lane == 0) mbar_arrive(&s_empty[stage]);   // this warp is done with the tile's rows: the stage can be refilled
         if (++stage == PT_STAGES) { stage = 0; parity ^= 1u; }
     }
+    // Route pass: every thread waits until its own stores -- most of them into peer memory, posted over NVLink -- have been
+    // performed system-wide before the kernel may count as finished: the arrival flag that the next kernel on the stream
+    // sends must not overtake a row still in flight.  (Without it, 14 of 3.33 M joined rows were missing at 250M x 50M rows
+    // per GPU on two GPUs: the largest exchange that had been run; every smaller one had passed.)
+    if (ROUTE) __threadfence_system();
 }
 
 // ---- offsets of every (tile, bucket) segment, over many CTAs.
@@ -291,199 +364,6 @@ partition_offsets_kernel(const u32 *__restrict__ tile_counts, u32 num_tiles, int
         }
 }
 
-// The exchange.  A tile's survivors sit contiguous, in original row order, at the start of the tile's slot.  One warp per
-// tile walks them 32 rows at a time: every lane takes one row, finds its bucket from the key (the same compares as the
-// partition kernel), one ballot per bucket gives the row's rank among the group's rows of that bucket, lane q keeps the
-// address where bucket q's next row goes -- D.base[q] + (row0[q] + off32[t][q]) rows, D.base[q] being the local send buffer
-// (grouped ncclSend path), the rank's own receive buffer, or a PEER GPU's receive buffer (peer mapping: the stores travel
-// over NVLink from the SMs, so the compaction IS the exchange) -- and the lane stores its row there.  Rows of one bucket
-// leave in original order and land contiguously, so neighbouring lanes' stores coalesce.  PX_UNROLL row groups are
-// loaded before the first one is routed.
-constexpr int PX_UNROLL = 4;
-
-template <bool VEC4>   // VEC4: rows are exactly one 16-byte word and every pointer is 16-byte aligned (the 4-column shapes)
-__global__ void __launch_bounds__(256)
-partition_exchange_kernel(const int32_t *__restrict__ slots, const u32 *__restrict__ tile_counts, const u32 *__restrict__ off32,
-                          u32 num_tiles, int G, u32 tile_rows, int cols, int key_col, const u32 *__restrict__ splitters,
-                          const SmjPartitionDst D)
-{
-    PDL_ENTER();
-    if (D.skip && *D.skip) return;
-    const u32 lane = threadIdx.x & 31u;
-    const u32 lt = lanemask_lt();
-    const u32 warps = gridDim.x * (blockDim.x >> 5);
-    const u64 row_bytes = (u64)cols * 4;
-    u32 sp[PT_MAX_G - 1];
-#pragma unroll
-    for (int q = 0; q < PT_MAX_G - 1; q++) sp[q] = (q < G - 1) ? splitters[q] : 0xffffffffu;
-    // lane q: where this rank's bucket q starts counting rows (byte address)
-    u64 base_q = 0;
-    if (lane < (u32)G) {
-        int32_t *bp = D.base[0];
-#pragma unroll
-        for (int q = 1; q < PT_MAX_G; q++) if (lane == (u32)q) bp = D.base[q];
-        base_q = reinterpret_cast<u64>(bp) + (D.row0 ? D.row0[lane] : 0ull) * row_bytes;
-    }
-    for (u32 t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < num_tiles; t += warps) {
-        u32 cnt = 0;
-        u64 cur_q = 0;   // lane q: byte address of the next row of bucket q
-        if (lane < (u32)G) {
-            cnt = tile_counts[(size_t)t * PT_MAX_G + lane];
-            cur_q = base_q + (u64)off32[(size_t)t * PT_MAX_G + lane] * row_bytes;
-        }
-        const u32 total = __reduce_add_sync(FULL_MASK, cnt);
-        const int32_t *src = slots + (size_t)t * tile_rows * cols;
-        for (u32 i0 = 0; i0 < total; i0 += 32 * PX_UNROLL) {
-            int4 r4[VEC4 ? PX_UNROLL : 1];
-            int32_t kv[PX_UNROLL];
-#pragma unroll
-            for (int k = 0; k < PX_UNROLL; k++) {
-                const u32 i = i0 + k * 32 + lane;
-                kv[k] = 0;
-                if (i < total) {
-                    if (VEC4) {
-                        const int4 r = __ldcs(reinterpret_cast<const int4 *>(src) + i);   // read once
-                        r4[VEC4 ? k : 0] = r;
-                        kv[k] = key_col == 0 ? r.x : key_col == 1 ? r.y : key_col == 2 ? r.z : r.w;
-                    } else {
-                        kv[k] = __ldcs(src + (size_t)i * cols + key_col);
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < PX_UNROLL; k++) {
-                if (i0 + k * 32 >= total) break;       // warp-uniform
-                const u32 i = i0 + k * 32 + lane;
-                const bool valid = i < total;
-                const u32 b = pt_bucket((u32)kv[k] ^ 0x80000000u, sp, G);
-                u32 mine = 0, add = 0;
-#pragma unroll
-                for (int q = 0; q < PT_MAX_G; q++) {
-                    if (q < G) {                       // warp-uniform
-                        const u32 mq = __ballot_sync(FULL_MASK, valid && b == (u32)q);
-                        if (b == (u32)q) mine = mq;
-                        if (lane == (u32)q) add = __popc(mq);
-                    }
-                }
-                const u64 dst_b = __shfl_sync(FULL_MASK, cur_q, b);     // bucket b's cursor lives in lane b
-                cur_q += (u64)add * row_bytes;
-                if (valid) {
-                    const u64 dst = dst_b + (u64)__popc(mine & lt) * row_bytes;
-                    if (VEC4) {
-                        *reinterpret_cast<int4 *>(dst) = r4[VEC4 ? k : 0];
-                    } else {
-                        const int32_t *rs = src + (size_t)i * cols;
-                        int32_t *rd = reinterpret_cast<int32_t *>(dst);
-                        if ((cols & 3) == 0 && ((reinterpret_cast<uintptr_t>(rs) | dst) & 15) == 0) {
-                            for (int q = 0; q < cols / 4; q++) reinterpret_cast<int4 *>(rd)[q] = __ldcs(reinterpret_cast<const int4 *>(rs) + q);
-                        } else {
-                            for (int q = 0; q < cols; q++) rd[q] = __ldcs(rs + q);
-                        }
-                    }
-                }
-            }
-        }
-    }
-    // Every thread waits until its own stores -- most of them into peer memory, posted over NVLink -- have been performed
-    // system-wide before the kernel may count as finished: the arrival flag that the next kernel on the stream sends must
-    // not overtake a row still in flight.  (Without it, 14 of 3.33 M joined rows were missing at 250M x 50M rows per GPU on
-    // two GPUs: the largest exchange that had been run; every smaller one had passed.)
-    __threadfence_system();
-}
-
-// The same routing with the rows of every bucket STAGED in shared memory, 32 at a time: with G destinations a group of 32
-// rows holds ~32 / G rows per bucket, so the direct version above stores runs of 64 bytes (G = 8) that start anywhere --
-// partial lines, two NVLink packets per run.  Here a warp keeps a 32-row (512-byte) buffer per bucket; rows go into their
-// bucket's buffer at (fill + rank), a full buffer leaves as ONE 512-byte coalesced warp store, rows that did not fit go
-// into the emptied buffer, and what is left at the end of the tile is flushed.  4-column tables only (16-byte rows).
-constexpr int PXS_WARPS = 8;
-constexpr size_t PXS_SMEM = (size_t)PXS_WARPS * PT_MAX_G * 32 * 16;   // 32 KB
-
-__global__ void __launch_bounds__(PXS_WARPS * 32)
-partition_exchange_staged_kernel(const int32_t *__restrict__ slots, const u32 *__restrict__ tile_counts, const u32 *__restrict__ off32,
-                                 u32 num_tiles, int G, u32 tile_rows, int key_col, const u32 *__restrict__ splitters, const SmjPartitionDst D)
-{
-    extern __shared__ __align__(16) int4 pxs_stage[];
-    PDL_ENTER();
-    if (D.skip && *D.skip) return;
-    const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    const u32 lt = lanemask_lt();
-    const u32 warps = gridDim.x * PXS_WARPS;
-    int4 *stage = pxs_stage + (size_t)w * PT_MAX_G * 32;     // [bucket][32 rows]
-    u32 sp[PT_MAX_G - 1];
-#pragma unroll
-    for (int q = 0; q < PT_MAX_G - 1; q++) sp[q] = (q < G - 1) ? splitters[q] : 0xffffffffu;
-    u64 base_q = 0;
-    if (lane < (u32)G) {
-        int32_t *bp = D.base[0];
-#pragma unroll
-        for (int q = 1; q < PT_MAX_G; q++) if (lane == (u32)q) bp = D.base[q];
-        base_q = reinterpret_cast<u64>(bp) + (D.row0 ? D.row0[lane] : 0ull) * 16ull;
-    }
-    for (u32 t = blockIdx.x * PXS_WARPS + w; t < num_tiles; t += warps) {
-        u32 cnt = 0, fill_q = 0;   // lane q: rows of bucket q waiting in its buffer
-        u64 cur_q = 0;             // lane q: byte address of the next row of bucket q that leaves
-        if (lane < (u32)G) {
-            cnt = tile_counts[(size_t)t * PT_MAX_G + lane];
-            cur_q = base_q + (u64)off32[(size_t)t * PT_MAX_G + lane] * 16ull;
-        }
-        const u32 total = __reduce_add_sync(FULL_MASK, cnt);
-        const int4 *src = reinterpret_cast<const int4 *>(slots + (size_t)t * tile_rows * 4);
-        for (u32 i0 = 0; i0 < total; i0 += 32 * PX_UNROLL) {
-            int4 r4[PX_UNROLL];
-#pragma unroll
-            for (int k = 0; k < PX_UNROLL; k++) {
-                const u32 i = i0 + k * 32 + lane;
-                r4[k] = i < total ? __ldcs(src + i) : make_int4(0, 0, 0, 0);
-            }
-#pragma unroll
-            for (int k = 0; k < PX_UNROLL; k++) {
-                if (i0 + k * 32 >= total) break;       // warp-uniform
-                const u32 i = i0 + k * 32 + lane;
-                const bool valid = i < total;
-                const int32_t kv = key_col == 0 ? r4[k].x : key_col == 1 ? r4[k].y : key_col == 2 ? r4[k].z : r4[k].w;
-                const u32 b = pt_bucket((u32)kv ^ 0x80000000u, sp, G);
-                u32 mine = 0, add = 0;
-#pragma unroll
-                for (int q = 0; q < PT_MAX_G; q++) {
-                    if (q < G) {                       // warp-uniform
-                        const u32 mq = __ballot_sync(FULL_MASK, valid && b == (u32)q);
-                        if (b == (u32)q) mine = mq;
-                        if (lane == (u32)q) add = __popc(mq);
-                    }
-                }
-                const u32 pos = __shfl_sync(FULL_MASK, fill_q, b) + __popc(mine & lt);   // slot in bucket b's buffer (may reach 62)
-                if (valid && pos < 32u) stage[b * 32 + pos] = r4[k];
-                __syncwarp();
-                // buffers that are full now leave as one 512-byte store each
-                u32 full = __ballot_sync(FULL_MASK, lane < (u32)G && fill_q + add >= 32u);
-                while (full) {
-                    const int q = __ffs(full) - 1;
-                    full &= full - 1;
-                    const u64 dst = __shfl_sync(FULL_MASK, cur_q, q);
-                    reinterpret_cast<int4 *>(dst)[lane] = stage[q * 32 + lane];
-                    if (lane == (u32)q) cur_q += 512ull;
-                }
-                __syncwarp();
-                if (valid && pos >= 32u) stage[b * 32 + (pos - 32u)] = r4[k];          // the rows that did not fit: into the emptied buffer
-                if (lane < (u32)G) { fill_q += add; if (fill_q >= 32u) fill_q -= 32u; }
-                __syncwarp();
-            }
-        }
-        // what is left of the tile
-#pragma unroll
-        for (int q = 0; q < PT_MAX_G; q++) {
-            if (q < G) {
-                const u32 f = __shfl_sync(FULL_MASK, fill_q, q);
-                const u64 dst = __shfl_sync(FULL_MASK, cur_q, q);
-                if (lane < f) reinterpret_cast<int4 *>(dst)[lane] = stage[q * 32 + lane];
-            }
-        }
-        __syncwarp();
-    }
-    __threadfence_system();   // see partition_exchange_kernel
-}
-
 // samples[i] = flipped key of row floor((2i+1) n / 2S) if it passes the predicate, else 0xffffffff
 __global__ void sample_rows_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int sel_col, int32_t sel_val, int select_all,
                                    int key_col, int S, u32 *samples)
@@ -581,36 +461,47 @@ int smj_launch_sample_rows(SmjCtx *c, const int32_t *d_in, int64_t n, int cols, 
     return SMJ_OK;
 }
 
-// Stage 1 (on stream st): rows of d_in that pass the predicate, grouped by destination bucket inside each tile's slot (d_slots:
-// n*cols cells of scratch), then the per-tile counts, every segment's offset inside its bucket, the bucket totals and
-// the bucket starts (d_scratch: smj_partition_scratch).
+static int part_set_attrs(SmjCtx *c)
+{
+    static bool attr_set[16] = {};
+    if (attr_set[c->device & 15]) return SMJ_OK;
+    CUDA_TRY(cudaFuncSetAttribute(partition_pass_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PTW_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(partition_pass_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PTW_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(partition_pass_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PTW_SMEM_STAGED));
+    attr_set[c->device & 15] = true;
+    return SMJ_OK;
+}
+
+static PartPassArgs part_args(const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val, int key_col, const u32 *d_splitters, int G,
+                              const SmjPartScratch &S)
+{
+    PartPassArgs A = {};
+    A.in = d_in; A.n = n; A.cols = cols; A.ipt = pt_ipt(cols); A.sel_col = sel_col; A.sel_val = (int32_t)sel_val;
+    A.select_all = sel_val < (int64_t)INT32_MIN; A.key_col = key_col; A.splitters = d_splitters; A.G = G;
+    A.tile_counts = S.counts; A.off32 = S.off32; A.num_tiles = (u32)S.tiles;
+    return A;
+}
+
+// Pass 1 (on stream st): survivors of every tile per destination bucket, then every (tile, bucket) segment's offset inside
+// its bucket, the bucket totals and the bucket starts (d_scratch: smj_partition_scratch).
 int smj_launch_select_partition(SmjCtx *c, cudaStream_t st, const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val,
-                                int key_col, const u32 *d_splitters, int G, int32_t *d_slots, char *d_scratch)
+                                int key_col, const u32 *d_splitters, int G, char *d_scratch)
 {
     if (G < 1 || G > PT_MAX_G) return smj_set_error(SMJ_EINVAL, "select_partition: %d buckets (max %d)", G, PT_MAX_G);
-    int select_all = sel_val < (int64_t)INT32_MIN;
+    const int select_all = sel_val < (int64_t)INT32_MIN;
     if (!select_all && sel_val >= (int64_t)INT32_MAX) n = 0;
     const SmjPartScratch S = smj_partition_scratch(d_scratch, n > 0 ? n : 0, cols);
     if (n <= 0) { CUDA_TRY(cudaMemsetAsync(S.bucket_total, 0, (size_t)(2 * PT_MAX_G + 1) * 8, st)); return SMJ_OK; }
-    static bool attr_set[16] = {};
-    if (!attr_set[c->device & 15]) {
-        CUDA_TRY(cudaFuncSetAttribute(select_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PTW_SMEM));
-        attr_set[c->device & 15] = true;
-    }
+    SMJ_TRY(part_set_attrs(c));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    const int ipt = pt_ipt(cols);
-    // Two CTAs per SM, not the three that fit: this kernel's persistent CTAs hold their SM for the whole pass, and with three
-    // of them (3 x 288 threads x 72 registers = the whole register file) the OTHER table's exchange kernel, launched on the
-    // second stream to overlap with this pass, could not place a single CTA until this kernel drained -- the two chains ran
-    // one after the other (first arrival 166 us after the first partition pass at two GPUs, 105 us without the overlap).
-    static const int pt_ctas = getenv("SMJ_PT_CTAS") ? atoi(getenv("SMJ_PT_CTAS")) : 2;
-    const u32 per_sm = (u32)(pt_ctas >= 1 && pt_ctas <= 3 ? pt_ctas : 2);
-    const u32 grid = S.tiles < (size_t)(sms * per_sm) ? (u32)S.tiles : (u32)(sms * per_sm);
+    // two CTAs per SM (64 KB of ring each): the other table's route pass, launched on the second stream to overlap, must be
+    // able to place its CTAs next to this pass's persistent ones
+    const u32 grid = S.tiles < (size_t)(sms * 2) ? (u32)S.tiles : (u32)(sms * 2);
     // (the chain's kernels are launched with programmatic stream serialization: each becomes resident while its predecessor
     // drains and starts with griddepcontrol.wait, which takes the launch latency out of a chain of seven kernels per table)
-    smj_launch_on(c, st, select_partition_kernel, grid, PTW_THREADS, PTW_SMEM, d_in, n, cols, ipt, sel_col, (int32_t)sel_val, select_all, key_col,
-                  d_splitters, G, d_slots, S.counts, (u32)S.tiles);
+    smj_launch_on(c, st, partition_pass_kernel<false, false>, grid, PTW_THREADS, PTW_SMEM,
+                  part_args(d_in, n, cols, sel_col, sel_val, key_col, d_splitters, G, S), SmjPartitionDst());
     KERNEL_CHECK(c);
     smj_launch_on(c, st, partition_blocksum_kernel, (u32)S.ctas, PS_THREADS, 0, (const u32 *)S.counts, (u32)S.tiles, S.blocksum);
     KERNEL_CHECK(c);
@@ -620,32 +511,27 @@ int smj_launch_select_partition(SmjCtx *c, cudaStream_t st, const int32_t *d_in,
     return SMJ_OK;
 }
 
-// Stage 2 (on stream st): every (tile, bucket) segment to its place behind D.base[bucket] (see partition_exchange_kernel).
-int smj_launch_partition_exchange(SmjCtx *c, cudaStream_t st, int64_t n, int cols, int key_col, const u32 *d_splitters, int sel_val_none,
-                                  int G, const int32_t *d_slots, char *d_scratch, const SmjPartitionDst &D)
+// Pass 2 (on stream st): the table is streamed again and every surviving row goes straight to its place behind
+// D.base[bucket] (see partition_pass_kernel).
+int smj_launch_partition_exchange(SmjCtx *c, cudaStream_t st, const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val, int key_col,
+                                  const u32 *d_splitters, int G, char *d_scratch, const SmjPartitionDst &D)
 {
-    if (n <= 0 || sel_val_none) return SMJ_OK;
+    const int select_all = sel_val < (int64_t)INT32_MIN;
+    if (n <= 0 || (!select_all && sel_val >= (int64_t)INT32_MAX)) return SMJ_OK;
     const SmjPartScratch S = smj_partition_scratch(d_scratch, n, cols);
+    SMJ_TRY(part_set_attrs(c));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    const u32 cgrid = (u32)((S.tiles + 7) / 8 < (size_t)sms * 8 ? (S.tiles + 7) / 8 : (size_t)sms * 8);
-    uintptr_t al = (uintptr_t)d_slots;
+    const u32 grid = S.tiles < (size_t)(sms * 2) ? (u32)S.tiles : (u32)(sms * 2);
+    uintptr_t al = 0;
     for (int b = 0; b < G; b++) al |= (uintptr_t)D.base[b];
+    if (cols % 4 == 0 && (al & 15) != 0) return smj_set_error(SMJ_EINVAL, "partition route pass: destinations must be 16-byte aligned");
     static const int stage_min_g = getenv("SMJ_DIST_STAGE_MIN_G") ? atoi(getenv("SMJ_DIST_STAGE_MIN_G")) : 3;
-    if (cols == 4 && (al & 15) == 0 && G >= stage_min_g) {
-        static bool attr_set[16] = {};
-        if (!attr_set[c->device & 15]) {
-            CUDA_TRY(cudaFuncSetAttribute(partition_exchange_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PXS_SMEM));
-            attr_set[c->device & 15] = true;
-        }
-        smj_launch_on(c, st, partition_exchange_staged_kernel, cgrid, PXS_WARPS * 32, PXS_SMEM, d_slots, (const u32 *)S.counts, (const u32 *)S.off32,
-                      (u32)S.tiles, G, smj_partition_tile_rows(cols), key_col, d_splitters, D);
-    } else if (cols == 4 && (al & 15) == 0)
-        smj_launch_on(c, st, partition_exchange_kernel<true>, cgrid, 256, 0, d_slots, (const u32 *)S.counts, (const u32 *)S.off32, (u32)S.tiles, G,
-                      smj_partition_tile_rows(cols), cols, key_col, d_splitters, D);
+    const PartPassArgs A = part_args(d_in, n, cols, sel_col, sel_val, key_col, d_splitters, G, S);
+    if (cols == 4 && G >= stage_min_g)
+        smj_launch_on(c, st, partition_pass_kernel<true, true>, grid, PTW_THREADS, PTW_SMEM_STAGED, A, D);
     else
-        smj_launch_on(c, st, partition_exchange_kernel<false>, cgrid, 256, 0, d_slots, (const u32 *)S.counts, (const u32 *)S.off32, (u32)S.tiles, G,
-                      smj_partition_tile_rows(cols), cols, key_col, d_splitters, D);
+        smj_launch_on(c, st, partition_pass_kernel<true, false>, grid, PTW_THREADS, PTW_SMEM, A, D);
     KERNEL_CHECK(c);
     return SMJ_OK;
 }
@@ -673,12 +559,11 @@ int smj_launch_splitters(SmjCtx *c, const u32 *d_samples, int n_samples, int G, 
 void smj_preload_partition(void)
 {
     cudaFuncAttributes a;
-    cudaFuncGetAttributes(&a, select_partition_kernel);
+    cudaFuncGetAttributes(&a, partition_pass_kernel<false, false>);
+    cudaFuncGetAttributes(&a, partition_pass_kernel<true, false>);
+    cudaFuncGetAttributes(&a, partition_pass_kernel<true, true>);
     cudaFuncGetAttributes(&a, partition_blocksum_kernel);
     cudaFuncGetAttributes(&a, partition_offsets_kernel);
-    cudaFuncGetAttributes(&a, partition_exchange_kernel<true>);
-    cudaFuncGetAttributes(&a, partition_exchange_kernel<false>);
-    cudaFuncGetAttributes(&a, partition_exchange_staged_kernel);
     cudaFuncGetAttributes(&a, sample_rows_kernel);
     cudaFuncGetAttributes(&a, splitters_kernel);
     cudaGetLastError();
