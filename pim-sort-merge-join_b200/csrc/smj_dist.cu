@@ -440,6 +440,7 @@ struct DistRank {
     SmjRun run;
     smj_table_t blk[2];
     int64_t launches0 = 0;
+    int32_t *slots[2] = {};
     char *pscr[2] = {};
     int none[2] = {};
 };
@@ -666,8 +667,10 @@ int dist_step_prepare(DistRank &K, const smj_config_t *cfg, const smj_table_t *b
         }
         K.blk[t].data = const_cast<int32_t *>(d);
         K.blk[t].on_device = 1;
+        const size_t cells = (size_t)tt.rows * tt.cols;
+        K.slots[t] = (int32_t *)smj_ws(c, t ? WS_TMP_ROWS2 : WS_TMP_ROWS, cells * 4);
         K.pscr[t] = (char *)smj_ws(c, t ? WS_MERGE_B : WS_MERGE_A, smj_partition_scratch_bytes(tt.rows, tt.cols));
-        if (!K.pscr[t]) return SMJ_ENOMEM;
+        if (!K.slots[t] || !K.pscr[t]) return SMJ_ENOMEM;
         K.none[t] = (sel_val[t] >= (int64_t)INT32_MAX) ? 1 : 0;
     }
     // the local pipeline on what will arrive: select disabled, row counts device-resident (loc->rows)
@@ -719,7 +722,7 @@ int dist_step_enqueue(DistRank &K, const smj_config_t *cfg, u64 seq)
         const int t = order[o];
         cudaStream_t st = (o == 1 && two) ? K.aux : c->stream;
         SMJ_TRY(smj_launch_select_partition(c, st, K.blk[t].data, K.blk[t].rows, K.blk[t].cols, sel_col[t], sel_val[t], key[t], K.loc->split, G,
-                                            K.pscr[t]));
+                                            K.slots[t], K.pscr[t]));
         if (o == 0) {
             CUDA_TRY(cudaEventRecord(K.ev[DE_PART], c->stream));
             if (two) {   // the other table's chain starts here
@@ -734,8 +737,7 @@ int dist_step_enqueue(DistRank &K, const smj_config_t *cfg, u64 seq)
         for (int b = 0; b < G; b++) D.base[b] = K.peer_recv[t][b];
         D.row0 = K.loc->row0[t];
         D.skip = &K.loc->verdict[t];
-        SMJ_TRY(smj_launch_partition_exchange(c, st, K.blk[t].data, K.blk[t].rows, K.blk[t].cols, sel_col[t], sel_val[t], key[t], K.loc->split, G,
-                                              K.pscr[t], D));
+        SMJ_TRY(smj_launch_partition_exchange(c, st, K.blk[t].rows, K.blk[t].cols, K.none[t], G, K.slots[t], K.pscr[t], D));
         // every rank's stores must have landed before anybody reads its receive buffer
         smj_launch_on(c, st, dist_arrive_kernel, 1, 32, 0, K.peers, K.loc, me, G, t, seq, c->d_err);
         KERNEL_CHECK(c);
@@ -1105,13 +1107,16 @@ static int smj_run_multi_nccl(const smj_config_t *cfg, const smj_table_t *t1, co
     SMJ_TRY(smj_launch_splitters(c, d_samp_all, G * 2 * S, G, d_split));   // same samples, same kernel, same splitters on every rank
 
     // ---- 2. select + partition of the rows by destination rank (rows grouped by bucket inside every tile's slot)
+    int32_t *slots[2];
     char *pscr[2];
     int none[2];
     for (int t = 0; t < 2; t++) {
+        const size_t cells = (size_t)tb[t]->rows * cc[t];
+        slots[t] = (int32_t *)smj_ws(c, t ? WS_TMP_ROWS2 : WS_TMP_ROWS, cells * 4);
         pscr[t] = (char *)smj_ws(c, t ? WS_MERGE_B : WS_MERGE_A, smj_partition_scratch_bytes(tb[t]->rows, cc[t]));
-        if (!pscr[t]) return SMJ_ENOMEM;
+        if (!slots[t] || !pscr[t]) return SMJ_ENOMEM;
         none[t] = (sel_val[t] >= (int64_t)INT32_MAX) ? 1 : 0;
-        SMJ_TRY(smj_launch_select_partition(c, c->stream, d_t[t], tb[t]->rows, cc[t], sel_col[t], sel_val[t], key[t], d_split, G, pscr[t]));
+        SMJ_TRY(smj_launch_select_partition(c, c->stream, d_t[t], tb[t]->rows, cc[t], sel_col[t], sel_val[t], key[t], d_split, G, slots[t], pscr[t]));
         const SmjPartScratch PS = smj_partition_scratch(pscr[t], none[t] ? 0 : tb[t]->rows, cc[t]);
         CUDA_TRY(cudaMemcpyAsync(d_msg + t * (G + 1), PS.bucket_start, (size_t)(G + 1) * 8, cudaMemcpyDeviceToDevice, c->stream));
     }
@@ -1156,7 +1161,7 @@ static int smj_run_multi_nccl(const smj_config_t *cfg, const smj_table_t *t1, co
         SmjPartitionDst D = {};
         for (int b = 0; b < G; b++) D.base[b] = send[t];
         D.row0 = PS.bucket_start;
-        SMJ_TRY(smj_launch_partition_exchange(c, c->stream, d_t[t], tb[t]->rows, cc[t], sel_col[t], sel_val[t], key[t], d_split, G, pscr[t], D));
+        SMJ_TRY(smj_launch_partition_exchange(c, c->stream, tb[t]->rows, cc[t], none[t], G, slots[t], pscr[t], D));
     }
     NCCL_TRY(g_nccl.GroupStart());
     for (int t = 0; t < 2; t++) {

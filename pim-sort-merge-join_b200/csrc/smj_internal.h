@@ -275,9 +275,9 @@ size_t smj_partition_scratch_bytes(int64_t n, int cols);
 int smj_launch_sample_rows(SmjCtx *c, const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val, int key_col, int S,
                            u32 *d_samples);
 int smj_launch_select_partition(SmjCtx *c, cudaStream_t st, const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val,
-                                int key_col, const u32 *d_splitters, int G, char *d_scratch);
-int smj_launch_partition_exchange(SmjCtx *c, cudaStream_t st, const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val, int key_col,
-                                  const u32 *d_splitters, int G, char *d_scratch, const SmjPartitionDst &D);
+                                int key_col, const u32 *d_splitters, int G, int32_t *d_slots, char *d_scratch);
+int smj_launch_partition_exchange(SmjCtx *c, cudaStream_t st, int64_t n, int cols, int sel_val_none, int G, const int32_t *d_slots,
+                                  char *d_scratch, const SmjPartitionDst &D);
 int smj_launch_splitters(SmjCtx *c, const u32 *d_samples, int n_samples, int G, u32 *d_splitters);
 
 // ------------------------------------------------------------------ synth (smj_synth.cu)

@@ -8,10 +8,11 @@
 // the receiver's runs arrive in source-rank order, and a stable sort by key on the receiver reproduces the
 // reference's stable order.  All passes are sequential streams; no row is gathered at random before it travels.
 //
-//   partition_count_kernel  : first pass over the table: predicate, bucket id, G survivor counts per 256-row warp tile.
-//   partition_route_kernel  : second pass, once the offsets and the peers' counts are known: every surviving row is stored
-//                             straight to its destination (send buffer, own or PEER receive buffer).
+//   select_partition_kernel : TMA-fed like select_tma_kernel (1 producer warp, 8 compute warps).  Per tile: predicate,
+//                             bucket id (<= 7 compares), per-(bucket,row group,warp) ballot counts, one 512-entry
+//                             scan, rows written to the tile's own slot ordered by bucket, G counts per tile.
 //   partition_blocksum / partition_offsets_kernel: offsets of every (bucket, tile) segment + bucket totals, many CTAs.
+//   partition_exchange_kernel: one warp per tile routes the tile's survivors to their buckets' destinations.
 //   sample_rows_kernel      : regular row samples (predicate applied) from which the splitters are derived.
 #include "smj_internal.h"
 #include "smj_dev.cuh"
@@ -19,206 +20,153 @@
 
 namespace {
 
+constexpr int PT_THREADS = 256;
+constexpr int PT_WARPS = PT_THREADS / 32;
+constexpr int PT_IPT = 8;
+constexpr int PT_STAGES = 2;
+constexpr int PT_STAGE_BYTES = 32768;
 constexpr int PT_MAX_G = SMJ_MAX_G;
-constexpr int PT_MAX_COLS = 32;   // (the local pipeline's TMA select takes tables of up to 32 columns)
+constexpr int PTW_THREADS = PT_THREADS + 32;
+constexpr int PT_ENTRIES = PT_MAX_G * PT_IPT * PT_WARPS;   // 512 = 2 per compute thread
+constexpr size_t PTW_SMEM = (size_t)PT_STAGES * PT_STAGE_BYTES;
+constexpr int PT_MAX_COLS = PT_STAGE_BYTES / 4 / PT_THREADS;   // 32
 
-// bucket of a flipped key: the number of splitters <= key (unused splitters are 0xffffffff), at most G - 1
-__device__ __forceinline__ u32 pt_bucket(u32 fk, const u32 (&sp)[PT_MAX_G - 1], int G)
+__global__ void __launch_bounds__(PTW_THREADS, 3)
+select_partition_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, int sel_col, int32_t sel_val, int select_all,
+                        int key_col, const u32 *__restrict__ splitters, int G, int32_t *__restrict__ slots,
+                        u32 *__restrict__ tile_counts /*[tiles][PT_MAX_G]*/, u32 num_tiles)
 {
-    u32 b = 0;
-#pragma unroll
-    for (int q = 0; q < PT_MAX_G - 1; q++) b += (q < G - 1 && fk >= sp[q]) ? 1u : 0u;
-    return b;
-}
+    extern __shared__ __align__(128) unsigned char pt_smem[];
+    __shared__ __align__(8) u64 s_full[PT_STAGES], s_empty[PT_STAGES];
+    __shared__ u32 s_cnt[PT_ENTRIES], s_off[PT_ENTRIES + 1];
+    __shared__ u32 s_wtot[PT_WARPS];
+    __shared__ u32 s_split[PT_MAX_G];
 
-// The partition is TWO streaming passes over the table and NO intermediate copy of the rows.  The unit of work is a WARP
-// TILE: 256 consecutive rows (eight groups of 32, lane = row inside a group), so a warp needs nobody else -- no shared-memory
-// ring, no barrier -- and an SM runs as many of them as its registers hold:
-//   count pass: predicate + bucket per row, the tile's survivor count per bucket (one ballot per bucket and row group, lane q
-//               keeps bucket q's count) -> tile_counts;
-//   route pass: once the scan has given every (tile, bucket) segment its offset and the count exchange has said where this
-//               rank's bucket b starts at rank b, the same evaluation again; one ballot per bucket ranks a group's rows, lane q
-//               keeps bucket q's cursor, and every lane stores its own row straight behind D.base[bucket] -- the local send
-//               buffer (ncclSend path), the rank's own receive buffer, or a PEER GPU's receive buffer (peer mapping: NVLink
-//               stores from the SMs, the compaction IS the exchange).  Rows of one bucket leave in original order.
-// 16-byte rows (4 columns) are loaded whole, all eight groups of a tile in flight before the first one is routed; other
-// shapes load the select and key cells first and copy each surviving row cell by cell (16 bytes at a time when they can).
-// History (profiles/r02_partition_history.md): slot-writing passes fed by a TMA ring -- bucket-ordered slots with a 512-entry
-// scan per tile, then order-preserving slots with routing in a second kernel, then the two passes of today but on 2048-row
-// CTA tiles -- all ran at 40-110 us per 160 MB table: two or three CTAs of eight warps per SM could not hide the per-tile
-// dependency chain (ring wait, barrier, ballots, cursor shuffles, stores).
-// STAGED (route pass, 16-byte rows, three or more buckets): the rows of every bucket are collected in a 512-byte
-// shared-memory buffer per warp and leave as one coalesced store; without it a group of 32 rows leaves as G runs of ~32 / G
-// rows that start anywhere (partial lines over NVLink).
-constexpr int PW_GROUPS = 8;                       // row groups of 32 per warp tile
-constexpr int PW_TILE = PW_GROUPS * 32;            // 256 rows
-constexpr int PW_THREADS = 256;
-constexpr int PW_WARPS = PW_THREADS / 32;
-constexpr size_t PW_SMEM_STAGED = (size_t)PW_WARPS * PT_MAX_G * 32 * 16;   // 32 KB
+    PDL_ENTER();
+    const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+    const u32 tile_rows = (u32)ipt * PT_THREADS;
+    if (tid < (u32)PT_MAX_G) s_split[tid] = (tid < (u32)(G - 1)) ? splitters[tid] : 0xffffffffu;
+    if (tid == 0) {
+        for (int st = 0; st < PT_STAGES; st++) { mbar_init(&s_full[st], 1); mbar_init(&s_empty[st], PT_WARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
 
-struct PartPassArgs {
-    const int32_t *in; int64_t n; int cols, sel_col; int32_t sel_val; int select_all, key_col; const u32 *splitters; int G;
-    u32 *tile_counts;            // count pass: out [tiles][PT_MAX_G]
-    const u32 *off32;            // route pass: offsets of the (tile, bucket) segments inside their buckets
-    u32 num_tiles;
-};
-
-// select and key cells of the tile's rows (COLS4: the whole 16-byte rows), predicate and bucket per row group
-template <bool COLS4>
-__device__ __forceinline__ void pw_load_tile(const PartPassArgs &A, u32 tile, u32 lane, const u32 (&sp)[PT_MAX_G - 1], int4 (&r4)[COLS4 ? PW_GROUPS : 1],
-                                             u32 &passmask, u32 &bpack)
-{
-    const int64_t row0 = (int64_t)tile * PW_TILE + lane;
-    int32_t sv[PW_GROUPS], kv[PW_GROUPS];
-#pragma unroll
-    for (int j = 0; j < PW_GROUPS; j++) {
-        const int64_t row = row0 + j * 32;
-        sv[j] = 0; kv[j] = 0;
-        if (row < A.n) {
-            if (COLS4) {
-                const int4 r = __ldcs(reinterpret_cast<const int4 *>(A.in) + row);   // read once per pass
-                r4[COLS4 ? j : 0] = r;
-                sv[j] = A.sel_col == 0 ? r.x : A.sel_col == 1 ? r.y : A.sel_col == 2 ? r.z : r.w;
-                kv[j] = A.key_col == 0 ? r.x : A.key_col == 1 ? r.y : A.key_col == 2 ? r.z : r.w;
+    if (w == PT_WARPS) {   // ---------------- producer (one lane)
+        if (lane != 0) return;
+        const size_t row_bytes = (size_t)cols * 4;
+        const u64 stream_policy = l2_policy_evict_first();
+        u32 stage = 0, parity = 0;
+        for (u32 t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            mbar_wait(&s_empty[stage], parity ^ 1u);
+            const int64_t row0 = (int64_t)t * tile_rows;
+            const int64_t rows = (n - row0 < (int64_t)tile_rows) ? (n - row0) : (int64_t)tile_rows;
+            const u32 bytes = (u32)(rows * row_bytes);
+            const u32 b16 = bytes & ~15u;
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(in) + (size_t)row0 * row_bytes;
+            unsigned char *dst = pt_smem + (size_t)stage * PT_STAGE_BYTES;
+            for (u32 b = b16; b < bytes; b += 4)
+                *reinterpret_cast<int32_t *>(dst + b) = *reinterpret_cast<const int32_t *>(src + b);
+            if (b16) {
+                mbar_expect_tx(&s_full[stage], b16);
+                bulk_g2s_hint(dst, src, b16, &s_full[stage], stream_policy);
             } else {
-                const int32_t *p = A.in + row * A.cols;
-                sv[j] = __ldg(p + A.sel_col);
-                kv[j] = (A.key_col == A.sel_col) ? sv[j] : __ldg(p + A.key_col);
+                mbar_arrive(&s_full[stage]);
             }
+            if (++stage == PT_STAGES) { stage = 0; parity ^= 1u; }
         }
+        return;
     }
-    passmask = 0; bpack = 0;
-#pragma unroll
-    for (int j = 0; j < PW_GROUPS; j++) {
-        const bool pass = (row0 + j * 32 < A.n) && (A.select_all || sv[j] > A.sel_val);
-        passmask |= (pass ? 1u : 0u) << j;
-        bpack |= pt_bucket((u32)kv[j] ^ 0x80000000u, sp, A.G) << (3 * j);
-    }
-}
 
-__global__ void __launch_bounds__(PW_THREADS)
-partition_count_kernel(const PartPassArgs A, int cols4)
-{
-    PDL_ENTER();
-    const u32 lane = threadIdx.x & 31u;
-    const u32 warps = gridDim.x * PW_WARPS;
-    u32 sp[PT_MAX_G - 1];
-#pragma unroll
-    for (int q = 0; q < PT_MAX_G - 1; q++) sp[q] = (q < A.G - 1) ? A.splitters[q] : 0xffffffffu;
-    for (u32 t = blockIdx.x * PW_WARPS + (threadIdx.x >> 5); t < A.num_tiles; t += warps) {
-        u32 passmask, bpack, bcnt = 0;
-        if (cols4) { int4 r4[PW_GROUPS]; pw_load_tile<true>(A, t, lane, sp, r4, passmask, bpack); }
-        else { int4 r1[1]; pw_load_tile<false>(A, t, lane, sp, r1, passmask, bpack); }
-#pragma unroll
-        for (int j = 0; j < PW_GROUPS; j++) {
-            const bool pass = (passmask >> j) & 1u;
-            const u32 b = (bpack >> (3 * j)) & 7u;
-#pragma unroll
-            for (int q = 0; q < PT_MAX_G; q++) {
-                if (q < A.G) {   // warp-uniform
-                    const u32 mq = __ballot_sync(FULL_MASK, pass && b == (u32)q);
-                    if (lane == (u32)q) bcnt += __popc(mq);
-                }
-            }
-        }
-        if (lane < (u32)PT_MAX_G) A.tile_counts[(size_t)t * PT_MAX_G + lane] = bcnt;
-    }
-}
-
-template <bool COLS4, bool STAGED>
-__global__ void __launch_bounds__(PW_THREADS)
-partition_route_kernel(const PartPassArgs A, const SmjPartitionDst D)
-{
-    extern __shared__ __align__(16) int4 pw_stage[];
-    PDL_ENTER();
-    if (D.skip && *D.skip) return;
-    const int cols = A.cols, G = A.G;
-    const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    // ---------------------------------------- compute warps
     const u32 lt = lanemask_lt();
-    const u32 warps = gridDim.x * PW_WARPS;
-    const u64 row_bytes = (u64)cols * 4;
+    const bool vec = (cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(slots) & 15) == 0);
     u32 sp[PT_MAX_G - 1];
 #pragma unroll
-    for (int q = 0; q < PT_MAX_G - 1; q++) sp[q] = (q < G - 1) ? A.splitters[q] : 0xffffffffu;
-    u64 base_q = 0;        // lane q: byte address where this rank's bucket q starts counting rows
-    if (lane < (u32)G) {
-        int32_t *bp = D.base[0];
+    for (int q = 0; q < PT_MAX_G - 1; q++) sp[q] = s_split[q];
+    u32 stage = 0, parity = 0;
+    for (u32 tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&s_full[stage], parity);
+        const int64_t tile_base = (int64_t)tile * tile_rows;
+        const u32 rows_valid = (u32)((n - tile_base < (int64_t)tile_rows) ? (n - tile_base) : (int64_t)tile_rows);
+        const int32_t *s_rows = reinterpret_cast<const int32_t *>(pt_smem + (size_t)stage * PT_STAGE_BYTES);
+
+        u32 rank[PT_IPT / 4] = {};   // 8 bits per row group: position among the rows of the same (bucket, row group, warp)
+        u32 bucket = 0;              // 4 bits per row group; PT_MAX_G = dropped
+        for (u32 i = tid; i < (u32)PT_ENTRIES; i += PT_THREADS) s_cnt[i] = 0;
+        named_bar_sync(1, PT_THREADS);
 #pragma unroll
-        for (int q = 1; q < PT_MAX_G; q++) if (lane == (u32)q) bp = D.base[q];
-        base_q = reinterpret_cast<u64>(bp) + (D.row0 ? D.row0[lane] : 0ull) * row_bytes;
-    }
-    const bool vec = (cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(A.in) & 15) == 0);   // (the launcher checks the destinations)
-    int4 *stage_buf = STAGED ? pw_stage + (size_t)w * PT_MAX_G * 32 : nullptr;   // [bucket][32 rows]
-    for (u32 t = blockIdx.x * PW_WARPS + w; t < A.num_tiles; t += warps) {
-        u64 cur_q = 0;     // lane q: byte address of bucket q's next row from this tile
-        u32 fill_q = 0;    // STAGED, lane q: rows of bucket q waiting in the warp's buffer
-        if (lane < (u32)G) cur_q = base_q + (u64)A.off32[(size_t)t * PT_MAX_G + lane] * row_bytes;
-        int4 r4[COLS4 ? PW_GROUPS : 1];
-        u32 passmask, bpack;
-        pw_load_tile<COLS4>(A, t, lane, sp, r4, passmask, bpack);
+        for (int j = 0; j < PT_IPT; j++) {
+            u32 myb = PT_MAX_G;
+            if (j < ipt) {
+                const u32 row = j * PT_THREADS + tid;
+                bool pass = false;
+                u32 b = 0;
+                if (row < rows_valid) {
+                    const int32_t sv = s_rows[row * cols + sel_col];
+                    const int32_t kv = (key_col == sel_col) ? sv : s_rows[row * cols + key_col];
+                    pass = select_all || sv > sel_val;
+                    const u32 fk = (u32)kv ^ 0x80000000u;
 #pragma unroll
-        for (int j = 0; j < PW_GROUPS; j++) {
-            const bool pass = (passmask >> j) & 1u;
-            const u32 b = (bpack >> (3 * j)) & 7u;
-            if (__ballot_sync(FULL_MASK, pass) == 0u) continue;   // warp-uniform: nothing survives in this group
-            u32 mine = 0, add = 0;
-#pragma unroll
-            for (int q = 0; q < PT_MAX_G; q++) {
-                if (q < G) {   // warp-uniform
-                    const u32 mq = __ballot_sync(FULL_MASK, pass && b == (u32)q);
-                    if (b == (u32)q) mine = mq;
-                    if (lane == (u32)q) add = __popc(mq);
+                    for (int q = 0; q < PT_MAX_G - 1; q++) b += (fk >= sp[q]) ? 1u : 0u;   // unused splitters are 0xffffffff
+                    if (b > (u32)(G - 1)) b = (u32)(G - 1);   // a key equal to 0xffffffff
                 }
-            }
-            if (STAGED) {
-                const u32 pos = __shfl_sync(FULL_MASK, fill_q, b) + __popc(mine & lt);   // slot in bucket b's buffer (may reach 62)
-                if (pass && pos < 32u) stage_buf[b * 32 + pos] = r4[COLS4 ? j : 0];
-                __syncwarp();
-                u32 full = __ballot_sync(FULL_MASK, lane < (u32)G && fill_q + add >= 32u);   // full buffers leave as 512-byte stores
-                while (full) {
-                    const int q = __ffs(full) - 1;
-                    full &= full - 1;
-                    const u64 dst = __shfl_sync(FULL_MASK, cur_q, q);
-                    reinterpret_cast<int4 *>(dst)[lane] = stage_buf[q * 32 + lane];
-                    if (lane == (u32)q) cur_q += 512ull;
-                }
-                __syncwarp();
-                if (pass && pos >= 32u) stage_buf[b * 32 + (pos - 32u)] = r4[COLS4 ? j : 0];   // rows that did not fit: into the emptied buffer
-                if (lane < (u32)G) { fill_q += add; if (fill_q >= 32u) fill_q -= 32u; }
-                __syncwarp();
-            } else {
-                const u64 dst_b = __shfl_sync(FULL_MASK, cur_q, b);     // bucket b's cursor lives in lane b
-                cur_q += (u64)add * row_bytes;
-                if (pass) {
-                    const u64 dst = dst_b + (u64)__popc(mine & lt) * row_bytes;
-                    if (COLS4) {
-                        *reinterpret_cast<int4 *>(dst) = r4[COLS4 ? j : 0];
-                    } else {
-                        const int32_t *rs = A.in + ((int64_t)t * PW_TILE + j * 32 + lane) * cols;
-                        int32_t *rd = reinterpret_cast<int32_t *>(dst);
-                        if (vec) for (int q = 0; q < cols / 4; q++) reinterpret_cast<int4 *>(rd)[q] = __ldcs(reinterpret_cast<const int4 *>(rs) + q);
-                        else for (int q = 0; q < cols; q++) rd[q] = __ldcs(rs + q);
+                // ranks inside every bucket: one ballot per bucket (independent of each other; the first version ran one
+                // 64-bit shuffle scan per row group, a dependent chain of five steps, and the kernel took 72 us per 160 MB table)
+                u32 mine_mask = 0, cnt_lane = 0;
+#pragma unroll
+                for (int q = 0; q < PT_MAX_G; q++) {
+                    if (q < G) {
+                        const u32 m = __ballot_sync(FULL_MASK, pass && b == (u32)q);
+                        if (b == (u32)q) mine_mask = m;
+                        if (lane == (u32)q) cnt_lane = __popc(m);
                     }
                 }
+                if (pass) { rank[j >> 2] |= (u32)__popc(mine_mask & lt) << (8 * (j & 3)); myb = b; }
+                if (lane < (u32)G && cnt_lane) s_cnt[(lane * PT_IPT + j) * PT_WARPS + w] = cnt_lane;
             }
+            bucket |= myb << (4 * j);
         }
-        if (STAGED) {   // what is left of the tile
+        named_bar_sync(1, PT_THREADS);
+        {   // exclusive scan of the 512 counts (bucket-major, then row group, then warp == row order inside a bucket)
+            const u32 v0 = s_cnt[2 * tid], v1 = s_cnt[2 * tid + 1];
+            const u32 inc = warp_incl_scan(v0 + v1);
+            if (lane == 31) s_wtot[w] = inc;
+            named_bar_sync(1, PT_THREADS);
+            u32 base = inc - (v0 + v1);
+            for (u32 ww = 0; ww < w; ww++) base += s_wtot[ww];
+            s_off[2 * tid] = base;
+            s_off[2 * tid + 1] = base + v0;
+            if (tid == PT_THREADS - 1) s_off[PT_ENTRIES] = base + v0 + v1;
+        }
+        named_bar_sync(1, PT_THREADS);
+        if (tid < (u32)PT_MAX_G) {
+            const u32 lo = s_off[tid * PT_IPT * PT_WARPS], hi = s_off[(tid + 1) * PT_IPT * PT_WARPS];
+            tile_counts[(size_t)tile * PT_MAX_G + tid] = hi - lo;
+        }
+        int32_t *dst_tile = slots + (size_t)tile_base * cols;
 #pragma unroll
-            for (int q = 0; q < PT_MAX_G; q++) {
-                if (q < G) {
-                    const u32 f = __shfl_sync(FULL_MASK, fill_q, q);
-                    const u64 dst = __shfl_sync(FULL_MASK, cur_q, q);
-                    if (lane < f) reinterpret_cast<int4 *>(dst)[lane] = stage_buf[q * 32 + lane];
+        for (int j = 0; j < PT_IPT; j++) {
+            const u32 myb = (bucket >> (4 * j)) & 15u;
+            if (myb < (u32)PT_MAX_G) {
+                const u32 row = j * PT_THREADS + tid;
+                const u32 pos = s_off[(myb * PT_IPT + j) * PT_WARPS + w] + ((rank[j >> 2] >> (8 * (j & 3))) & 255u);
+                const int32_t *src = s_rows + row * cols;
+                int32_t *dst = dst_tile + (size_t)pos * cols;
+                if (vec) {
+                    for (int q = 0; q < cols / 4; q++)
+                        reinterpret_cast<int4 *>(dst)[q] = reinterpret_cast<const int4 *>(src)[q];
+                } else {
+                    for (int q = 0; q < cols; q++) dst[q] = src[q];
                 }
             }
-            __syncwarp();
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[stage]);   // rows copied out: the stage can be refilled
+        if (++stage == PT_STAGES) { stage = 0; parity ^= 1u; }
+        // s_cnt / s_off are rewritten only after the next tile's first named barrier, which every warp reaches after
+        // finishing the reads above
     }
-    // Every thread waits until its own stores -- most of them into peer memory, posted over NVLink -- have been performed
-    // system-wide before the kernel may count as finished: the arrival flag that the next kernel on the stream sends must not
-    // overtake a row still in flight.  (Without it, 14 of 3.33 M joined rows were missing at 250M x 50M rows per GPU on two
-    // GPUs: the largest exchange that had been run; every smaller one had passed.)
-    __threadfence_system();
 }
 
 // ---- offsets of every (tile, bucket) segment, over many CTAs.
@@ -339,6 +287,76 @@ partition_offsets_kernel(const u32 *__restrict__ tile_counts, u32 num_tiles, int
         }
 }
 
+// The exchange.  A tile's survivors sit bucket-ordered and contiguous at the start of the tile's slot; segment (t, b) goes to
+// dst.base[b] + (row0[b] + off32[t][b]) rows -- dst.base[b] is the local send buffer (grouped ncclSend path), the rank's own
+// receive buffer (its own bucket) or a PEER GPU's receive buffer (peer mapping: the stores travel over NVLink from the SMs,
+// so the compaction IS the exchange).  One warp per tile: the tile's 8 counts and offsets arrive with two 32-byte loads,
+// then the warp walks the slot as a flat array of cells (16-byte words when rows are whole 16-byte multiples), PX_UNROLL
+// independent loads in flight per lane before the first store, each word routed to its bucket by comparing its index with
+// the bucket boundaries held in registers.  (The first version took one warp per SEGMENT: a dependent chain of count ->
+// offset -> data loads for every ~2 KB piece, 0.30 ms for 122 MB at 8 GPUs.)
+constexpr int PX_UNROLL = 4;
+
+template <typename W>   // W = int4 (rows are multiples of 16 bytes and every pointer is 16-byte aligned) or int32_t
+__global__ void __launch_bounds__(256)
+partition_exchange_kernel(const int32_t *__restrict__ slots, const u32 *__restrict__ tile_counts, const u32 *__restrict__ off32,
+                          u32 num_tiles, int G, u32 tile_rows, int cols, const SmjPartitionDst D)
+{
+    PDL_ENTER();
+    if (D.skip && *D.skip) return;
+    constexpr u32 CPW = sizeof(W) / 4;               // cells per word
+    const u32 wpr = (u32)cols / CPW;                 // words per row
+    const u32 lane = threadIdx.x & 31u;
+    const u32 warps = gridDim.x * (blockDim.x >> 5);
+    for (u32 t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < num_tiles; t += warps) {
+        u32 cnt = 0, off = 0;
+        u64 r0 = 0;
+        if (lane < (u32)G) {
+            cnt = tile_counts[(size_t)t * PT_MAX_G + lane];
+            off = off32[(size_t)t * PT_MAX_G + lane];
+            r0 = D.row0 ? D.row0[lane] : 0ull;
+        }
+        const u32 incl = warp_incl_scan(cnt);
+        const u32 total_w = __shfl_sync(FULL_MASK, incl, PT_MAX_G - 1) * wpr;
+        if (total_w == 0) continue;
+        // per bucket: first word of its segment inside the slot, and where that word goes
+        u32 start_w[PT_MAX_G];
+        W *dstp[PT_MAX_G];
+#pragma unroll
+        for (int b = 0; b < PT_MAX_G; b++) {
+            start_w[b] = (__shfl_sync(FULL_MASK, incl, b) - __shfl_sync(FULL_MASK, cnt, b)) * wpr;
+            const u64 row = __shfl_sync(FULL_MASK, r0, b) + (u64)__shfl_sync(FULL_MASK, off, b);
+            dstp[b] = reinterpret_cast<W *>(D.base[b]) + row * wpr;
+        }
+        const W *src = reinterpret_cast<const W *>(slots + (size_t)t * tile_rows * cols);
+        for (u32 i0 = 0; i0 < total_w; i0 += 32 * PX_UNROLL) {
+            W v[PX_UNROLL];
+#pragma unroll
+            for (int k = 0; k < PX_UNROLL; k++) {
+                const u32 i = i0 + k * 32 + lane;
+                if (i < total_w) v[k] = __ldcs(src + i);   // read once
+            }
+#pragma unroll
+            for (int k = 0; k < PX_UNROLL; k++) {
+                const u32 i = i0 + k * 32 + lane;
+                if (i < total_w) {
+                    W *d = dstp[0];
+                    u32 s = 0;
+#pragma unroll
+                    for (int b = 1; b < PT_MAX_G; b++)
+                        if (b < G && i >= start_w[b]) { d = dstp[b]; s = start_w[b]; }
+                    d[i - s] = v[k];
+                }
+            }
+        }
+    }
+    // Every thread waits until its own stores -- most of them into peer memory, posted over NVLink -- have been performed
+    // system-wide before the kernel may count as finished: the arrival flag that the next kernel on the stream sends must not
+    // overtake a row still in flight.  (Without it, 14 of 3.33 M joined rows were missing at 250M x 50M rows per GPU on two
+    // GPUs: the largest exchange that had been run; every smaller one had passed.)
+    __threadfence_system();
+}
+
 // samples[i] = flipped key of row floor((2i+1) n / 2S) if it passes the predicate, else 0xffffffff
 __global__ void sample_rows_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int sel_col, int32_t sel_val, int select_all,
                                    int key_col, int S, u32 *samples)
@@ -395,11 +413,18 @@ __global__ void __launch_bounds__(SPL_THREADS) splitters_kernel(const u32 *__res
     }
 }
 
+int pt_ipt(int cols)
+{
+    int ipt = PT_IPT;
+    while (ipt > 1 && (size_t)ipt * PT_THREADS * cols * 4 > PT_STAGE_BYTES) ipt >>= 1;
+    return ipt;
+}
+
 }  // namespace
 
 bool smj_partition_supported(const int32_t *d_in, int cols) { return cols <= PT_MAX_COLS && ((uintptr_t)d_in & 15) == 0; }
-size_t smj_partition_tiles(int64_t n, int cols) { (void)cols; return (size_t)((n + PW_TILE - 1) / PW_TILE); }
-u32 smj_partition_tile_rows(int cols) { (void)cols; return (u32)PW_TILE; }
+size_t smj_partition_tiles(int64_t n, int cols) { const int64_t tr = (int64_t)pt_ipt(cols) * PT_THREADS; return (size_t)((n + tr - 1) / tr); }
+u32 smj_partition_tile_rows(int cols) { return (u32)(pt_ipt(cols) * PT_THREADS); }
 
 // scratch of one table: [tile_counts u32 tiles*8][off32 u32 tiles*8][blocksum u64 ctas*8][bucket_total u64 8][bucket_start u64 9]
 SmjPartScratch smj_partition_scratch(char *base, int64_t n, int cols)
@@ -429,43 +454,36 @@ int smj_launch_sample_rows(SmjCtx *c, const int32_t *d_in, int64_t n, int cols, 
     return SMJ_OK;
 }
 
-static PartPassArgs part_args(const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val, int key_col, const u32 *d_splitters, int G,
-                              const SmjPartScratch &S)
-{
-    PartPassArgs A = {};
-    A.in = d_in; A.n = n; A.cols = cols; A.sel_col = sel_col; A.sel_val = (int32_t)sel_val;
-    A.select_all = sel_val < (int64_t)INT32_MIN; A.key_col = key_col; A.splitters = d_splitters; A.G = G;
-    A.tile_counts = S.counts; A.off32 = S.off32; A.num_tiles = (u32)S.tiles;
-    return A;
-}
-
-// CTAs per SM of the two passes.  Both kernels are persistent (a warp takes tiles with a grid stride), and the count pass of
-// one table is meant to run NEXT TO the route pass of the other (second stream): each takes about half an SM's warps and
-// registers, so neither waits for the other to drain.
-static u32 part_grid(SmjCtx *c, size_t tiles, int per_sm)
-{
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    const size_t ctas = (tiles + PW_WARPS - 1) / PW_WARPS;
-    return (u32)(ctas < (size_t)sms * per_sm ? ctas : (size_t)sms * per_sm);
-}
-
-// Pass 1 (on stream st): survivors of every warp tile per destination bucket, then every (tile, bucket) segment's offset
-// inside its bucket, the bucket totals and the bucket starts (d_scratch: smj_partition_scratch).
+// Stage 1 (on stream st): rows of d_in that pass the predicate, grouped by destination bucket inside each tile's slot (d_slots:
+// n*cols cells of scratch), then the per-tile counts, every segment's offset inside its bucket, the bucket totals and
+// the bucket starts (d_scratch: smj_partition_scratch).
 int smj_launch_select_partition(SmjCtx *c, cudaStream_t st, const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val,
-                                int key_col, const u32 *d_splitters, int G, char *d_scratch)
+                                int key_col, const u32 *d_splitters, int G, int32_t *d_slots, char *d_scratch)
 {
     if (G < 1 || G > PT_MAX_G) return smj_set_error(SMJ_EINVAL, "select_partition: %d buckets (max %d)", G, PT_MAX_G);
-    const int select_all = sel_val < (int64_t)INT32_MIN;
+    int select_all = sel_val < (int64_t)INT32_MIN;
     if (!select_all && sel_val >= (int64_t)INT32_MAX) n = 0;
     const SmjPartScratch S = smj_partition_scratch(d_scratch, n > 0 ? n : 0, cols);
     if (n <= 0) { CUDA_TRY(cudaMemsetAsync(S.bucket_total, 0, (size_t)(2 * PT_MAX_G + 1) * 8, st)); return SMJ_OK; }
-    static const int count_ctas = getenv("SMJ_PT_COUNT_CTAS") ? atoi(getenv("SMJ_PT_COUNT_CTAS")) : 4;
-    const int cols4 = (cols == 4 && ((uintptr_t)d_in & 15) == 0) ? 1 : 0;
+    static bool attr_set[16] = {};
+    if (!attr_set[c->device & 15]) {
+        CUDA_TRY(cudaFuncSetAttribute(select_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PTW_SMEM));
+        attr_set[c->device & 15] = true;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const int ipt = pt_ipt(cols);
+    // CTAs per SM (SMJ_PT_CTAS, default 3 = what the registers allow).  This kernel's persistent CTAs hold their SM for the whole
+    // pass, and with three of them the OTHER table's exchange kernel, launched on the second stream to overlap with this
+    // pass, finds no room until this kernel drains; two leave room (measured at two GPUs: first arrival 148 instead of 162 us
+    // after the first pass, but the pass itself 98 instead of 86 us -- a wash, so the default stays at three).
+    static const int pt_ctas = getenv("SMJ_PT_CTAS") ? atoi(getenv("SMJ_PT_CTAS")) : 3;
+    const u32 per_sm = (u32)(pt_ctas >= 1 && pt_ctas <= 3 ? pt_ctas : 3);
+    const u32 grid = S.tiles < (size_t)(sms * per_sm) ? (u32)S.tiles : (u32)(sms * per_sm);
     // (the chain's kernels are launched with programmatic stream serialization: each becomes resident while its predecessor
     // drains and starts with griddepcontrol.wait, which takes the launch latency out of a chain of seven kernels per table)
-    smj_launch_on(c, st, partition_count_kernel, part_grid(c, S.tiles, count_ctas), PW_THREADS, 0,
-                  part_args(d_in, n, cols, sel_col, sel_val, key_col, d_splitters, G, S), cols4);
+    smj_launch_on(c, st, select_partition_kernel, grid, PTW_THREADS, PTW_SMEM, d_in, n, cols, ipt, sel_col, (int32_t)sel_val, select_all, key_col,
+                  d_splitters, G, d_slots, S.counts, (u32)S.tiles);
     KERNEL_CHECK(c);
     smj_launch_on(c, st, partition_blocksum_kernel, (u32)S.ctas, PS_THREADS, 0, (const u32 *)S.counts, (u32)S.tiles, S.blocksum);
     KERNEL_CHECK(c);
@@ -475,28 +493,23 @@ int smj_launch_select_partition(SmjCtx *c, cudaStream_t st, const int32_t *d_in,
     return SMJ_OK;
 }
 
-// Pass 2 (on stream st): the table is streamed again and every surviving row goes straight to its place behind
-// D.base[bucket] (see partition_route_kernel).
-int smj_launch_partition_exchange(SmjCtx *c, cudaStream_t st, const int32_t *d_in, int64_t n, int cols, int sel_col, int64_t sel_val, int key_col,
-                                  const u32 *d_splitters, int G, char *d_scratch, const SmjPartitionDst &D)
+// Stage 2 (on stream st): every (tile, bucket) segment to its place behind D.base[bucket] (see partition_exchange_kernel).
+int smj_launch_partition_exchange(SmjCtx *c, cudaStream_t st, int64_t n, int cols, int sel_val_none, int G, const int32_t *d_slots,
+                                  char *d_scratch, const SmjPartitionDst &D)
 {
-    const int select_all = sel_val < (int64_t)INT32_MIN;
-    if (n <= 0 || (!select_all && sel_val >= (int64_t)INT32_MAX)) return SMJ_OK;
+    if (n <= 0 || sel_val_none) return SMJ_OK;
     const SmjPartScratch S = smj_partition_scratch(d_scratch, n, cols);
-    uintptr_t al = 0;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const u32 cgrid = (u32)((S.tiles + 7) / 8 < (size_t)sms * 8 ? (S.tiles + 7) / 8 : (size_t)sms * 8);
+    uintptr_t al = (uintptr_t)d_slots;
     for (int b = 0; b < G; b++) al |= (uintptr_t)D.base[b];
-    if (cols % 4 == 0 && (al & 15) != 0) return smj_set_error(SMJ_EINVAL, "partition route pass: destinations must be 16-byte aligned");
-    static const int stage_min_g = getenv("SMJ_DIST_STAGE_MIN_G") ? atoi(getenv("SMJ_DIST_STAGE_MIN_G")) : 3;
-    static const int route_ctas = getenv("SMJ_PT_ROUTE_CTAS") ? atoi(getenv("SMJ_PT_ROUTE_CTAS")) : 2;
-    const PartPassArgs A = part_args(d_in, n, cols, sel_col, sel_val, key_col, d_splitters, G, S);
-    const u32 grid = part_grid(c, S.tiles, route_ctas);
-    const bool cols4 = cols == 4 && ((uintptr_t)d_in & 15) == 0;
-    if (cols4 && G >= stage_min_g)
-        smj_launch_on(c, st, partition_route_kernel<true, true>, grid, PW_THREADS, PW_SMEM_STAGED, A, D);
-    else if (cols4)
-        smj_launch_on(c, st, partition_route_kernel<true, false>, grid, PW_THREADS, 0, A, D);
+    if (cols % 4 == 0 && (al & 15) == 0)
+        smj_launch_on(c, st, partition_exchange_kernel<int4>, cgrid, 256, 0, d_slots, (const u32 *)S.counts, (const u32 *)S.off32, (u32)S.tiles, G,
+                      smj_partition_tile_rows(cols), cols, D);
     else
-        smj_launch_on(c, st, partition_route_kernel<false, false>, grid, PW_THREADS, 0, A, D);
+        smj_launch_on(c, st, partition_exchange_kernel<int32_t>, cgrid, 256, 0, d_slots, (const u32 *)S.counts, (const u32 *)S.off32, (u32)S.tiles, G,
+                      smj_partition_tile_rows(cols), cols, D);
     KERNEL_CHECK(c);
     return SMJ_OK;
 }
@@ -524,12 +537,11 @@ int smj_launch_splitters(SmjCtx *c, const u32 *d_samples, int n_samples, int G, 
 void smj_preload_partition(void)
 {
     cudaFuncAttributes a;
-    cudaFuncGetAttributes(&a, partition_count_kernel);
-    cudaFuncGetAttributes(&a, partition_route_kernel<true, true>);
-    cudaFuncGetAttributes(&a, partition_route_kernel<true, false>);
-    cudaFuncGetAttributes(&a, partition_route_kernel<false, false>);
+    cudaFuncGetAttributes(&a, select_partition_kernel);
     cudaFuncGetAttributes(&a, partition_blocksum_kernel);
     cudaFuncGetAttributes(&a, partition_offsets_kernel);
+    cudaFuncGetAttributes(&a, partition_exchange_kernel<int4>);
+    cudaFuncGetAttributes(&a, partition_exchange_kernel<int32_t>);
     cudaFuncGetAttributes(&a, sample_rows_kernel);
     cudaFuncGetAttributes(&a, splitters_kernel);
     cudaGetLastError();
