@@ -878,7 +878,14 @@ int smj_run_enqueue(SmjCtx *c, SmjRun *R)
     // tables, shapes and knobs replays it as ONE CUDA graph (the launch gaps are ~8 % of a 0.6 ms step); the output
     // buffer is new every call, so the materialise kernel reads its pointer from a device cell written just before.
     ScratchHeader *h = (ScratchHeader *)scr;
-    u64 key_now[16] = {(u64)(uintptr_t)d_t[0], (u64)(uintptr_t)d_t[1], (u64)n[0], (u64)n[1], (u64)cc[0], (u64)cc[1],
+    // The tables' addresses reach the kernels through device cells (like the output pointer), so a graph captured for one pair
+    // of tables serves any other pair of the same shape, alignment and knobs.  Paths that bake the addresses into kernel
+    // arguments (a table the TMA select cannot take, the opt-in row store) keep them in the key.
+    const bool ind_ok = smj_select_takes_tma(d_t[0], cc[0]) && smj_select_takes_tma(d_t[1], cc[1]) && !R->store[0] && !R->store[1];
+    const int32_t *const *d_tab_ind = ind_ok ? (const int32_t *const *)(c->d_out_ptr + 1) : nullptr;
+    const u64 tkey[2] = {ind_ok ? ((u64)(uintptr_t)d_t[0] & 15u) | 16u : (u64)(uintptr_t)d_t[0],
+                         ind_ok ? ((u64)(uintptr_t)d_t[1] & 15u) | 16u : (u64)(uintptr_t)d_t[1]};
+    u64 key_now[16] = {tkey[0], tkey[1], (u64)n[0], (u64)n[1], (u64)cc[0], (u64)cc[1],
                        (u64)sel_col[0], (u64)sel_col[1], (u64)sel_val[0], (u64)sel_val[1], (u64)key[0], (u64)key[1], c->ws_gen,
                        (u64)(uintptr_t)scr, (u64)(uintptr_t)R->d_rows[0] ^ ((u64)(uintptr_t)R->wait[0].flag << 1),
                        (u64)(uintptr_t)R->d_rows[1] ^ ((u64)(uintptr_t)R->wait[1].flag << 1)};
@@ -893,8 +900,10 @@ int smj_run_enqueue(SmjCtx *c, SmjRun *R)
     const bool capture = graphs_on && !R->no_graph && !replay && c->graph_seen >= 2;   // the first call warms attributes and slots eagerly
     R->replayed = replay || capture;
     int32_t **h_ptr = (int32_t **)((char *)c->h_pinned + c->h_pinned_bytes - 128);
-    *h_ptr = R->dev_out.data;
-    CUDA_TRY(cudaMemcpyAsync(c->d_out_ptr, h_ptr, sizeof(int32_t *), cudaMemcpyHostToDevice, c->stream));
+    h_ptr[0] = R->dev_out.data;
+    h_ptr[1] = const_cast<int32_t *>(d_t[0]);
+    h_ptr[2] = const_cast<int32_t *>(d_t[1]);
+    CUDA_TRY(cudaMemcpyAsync(c->d_out_ptr, h_ptr, 3 * sizeof(int32_t *), cudaMemcpyHostToDevice, c->stream));
     if (!replay) {
         const int64_t l0 = c->launches;
         if (capture) CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
@@ -911,7 +920,7 @@ int smj_run_enqueue(SmjCtx *c, SmjRun *R)
                 for (int t = 0; t < 2; t++)
                     job[t] = {d_t[t], n[t], cc[t], sel_col[t], sel_val[t], 0, key[t], {ping[t], pong[t]}, (u64 *)mm + (t ? n[0] : 0),
                               (u64 *)(scr + off_sel + (t ? stiles[0] * 8 : 0)), h->hist[t], &h->count[t], &h->plan[t], &h->sel_count[t], &h->kept_count[t],
-                              R->d_rows[t], R->wait[t], R->store[t], &h->use_store[t], R->store_max_rows[t]};
+                              R->d_rows[t], R->wait[t], d_tab_ind ? d_tab_ind + t : nullptr, R->store[t], &h->use_store[t], R->store_max_rows[t]};
                 rc = smj_launch_select_plan2(c, job);
                 if (rc == 1) { planned = false; rc = SMJ_OK; }   // a table the TMA path cannot take: histograms in the select kernel, four passes
             }
@@ -944,7 +953,7 @@ int smj_run_enqueue(SmjCtx *c, SmjRun *R)
             PIPE_TRY(smj_launch_join_match(c, ping[0], ping[1], &h->count[0], (u32)n[0], (u32)n[1], SMJ_JOIN_ZIP, jsr.part, jsr.tile_count,
                                            jsr.tile_off, mm, md, &h->jcount));
             PIPE_TRY(smj_launch_join_materialize(c, md, &h->jcount, j_max, d_t[0], cc[0], d_t[1], cc[1], key[1], nullptr, c->d_out_ptr,
-                                                 planned ? h->use_store : nullptr, R->store[0], R->store[1]));
+                                                 planned ? h->use_store : nullptr, R->store[0], R->store[1], d_tab_ind));
 #undef PIPE_TRY
 #undef PIPE_CUDA
         } while (0);

@@ -47,7 +47,7 @@ struct SmjCtx {
     int graph_seen = 0;              // consecutive calls with this key: 1st runs eagerly, 2nd captures, later ones replay
     cudaGraphExec_t graph_exec = nullptr;
     int64_t graph_launches = 0;      // kernels inside the captured pipeline
-    int32_t **d_out_ptr = nullptr;   // device cell holding the output pointer the materialise kernel writes through
+    int32_t **d_out_ptr = nullptr;   // device cells: [0] the output pointer the materialise kernel writes through, [1], [2] the input tables' addresses
 };
 
 enum SmjSlot {
@@ -190,12 +190,14 @@ struct SmjSelectJob {
     u64 *d_kept_count;    // zeroed; out: of those, the rows whose key bit was set in the other table's bitmap
     const u64 *n_dev;     // device-resident row count (may be null); n is then the upper bound the buffers were sized for
     SmjWait wait;         // the table's select kernel starts with this wait (smj_dist.cu: the table is still arriving)
+    const int32_t *const *d_in_ind;   // device cell holding the table's address (null: d_in is used): graph replay on new tables
     int32_t *store;       // dense row store of store_max_rows rows (null: none); *use_store (zeroed) = the device's decision
     u32 *use_store;
     u64 store_max_rows;
 };
 // returns 1 (nothing launched) when a table cannot take the TMA path
 int smj_launch_select_plan2(SmjCtx *c, const SmjSelectJob job[2]);
+bool smj_select_takes_tma(const int32_t *d_in, int cols);   // 16-byte aligned table of at most 32 columns
 size_t smj_bloom_bytes(int64_t n0, int64_t n1);   // WS_BLOOM bytes the call above uses (0: no semi-join filter)
 
 // ------------------------------------------------------------------ radix sort (smj_radix.cu)
@@ -256,7 +258,8 @@ int smj_launch_join_many_expand(SmjCtx *c, const u64 *d_l, const u64 *d_r, const
 // its row store (smj_select.cu, plan_compact_kernel), and the stores
 int smj_launch_join_materialize(SmjCtx *c, const uint2 *d_dense, const u64 *d_nj, int64_t nj_max, const int32_t *d_t1, int c1,
                                 const int32_t *d_t2, int c2, int key2, int32_t *d_out, int32_t *const *d_out_indirect = nullptr,
-                                const u32 *d_use_store = nullptr, const int32_t *d_store1 = nullptr, const int32_t *d_store2 = nullptr);
+                                const u32 *d_use_store = nullptr, const int32_t *d_store1 = nullptr, const int32_t *d_store2 = nullptr,
+                                const int32_t *const *d_tables_indirect = nullptr /* device [2]: the tables' addresses */);
 
 // ------------------------------------------------------------------ key-range partitioning of rows (smj_partition.cu)
 #define SMJ_MAX_G 8

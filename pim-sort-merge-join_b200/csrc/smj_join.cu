@@ -360,10 +360,12 @@ __global__ void __launch_bounds__(MT_THREADS)
 join_materialize_kernel(const uint2 *__restrict__ matches, const u64 *__restrict__ nj_dev, int64_t nj_max,
                         const int32_t *__restrict__ t1, int c1, const int32_t *__restrict__ t2, int c2, int key2,
                         int32_t *__restrict__ out_direct, int32_t *const *__restrict__ out_indirect, int rows_per_block,
-                        const u32 *__restrict__ use_store, const int32_t *__restrict__ store1, const int32_t *__restrict__ store2)
+                        const u32 *__restrict__ use_store, const int32_t *__restrict__ store1, const int32_t *__restrict__ store2,
+                        const int32_t *const *__restrict__ tables_ind)
 {
     __shared__ __align__(16) int32_t s_out[MT_SMEM_CELLS];
     PDL_ENTER();
+    if (tables_ind) { t1 = tables_ind[0]; t2 = tables_ind[1]; }   // (graph replay on new tables of the same shape)
     if (use_store) {   // the match list's row ids of a table are dense indices into its row store when the flag is set
         if (use_store[0]) t1 = store1;
         if (use_store[1]) t2 = store2;
@@ -609,7 +611,7 @@ int smj_launch_join_match(SmjCtx *c, const u64 *d_l, const u64 *d_r, const u64 *
 // Joined rows from the dense match list (*d_nj of them, at most nj_max).
 int smj_launch_join_materialize(SmjCtx *c, const uint2 *d_dense, const u64 *d_nj, int64_t nj_max, const int32_t *d_t1, int c1,
                                 const int32_t *d_t2, int c2, int key2, int32_t *d_out, int32_t *const *d_out_indirect,
-                                const u32 *d_use_store, const int32_t *d_store1, const int32_t *d_store2)
+                                const u32 *d_use_store, const int32_t *d_store1, const int32_t *d_store2, const int32_t *const *d_tables_indirect)
 {
     if (nj_max <= 0) return SMJ_OK;
     const int c_out = c1 + c2 - 1;
@@ -623,10 +625,10 @@ int smj_launch_join_materialize(SmjCtx *c, const uint2 *d_dense, const u64 *d_nj
                      ((((uintptr_t)d_t1) | ((uintptr_t)d_t2) | ((uintptr_t)d_store1) | ((uintptr_t)d_store2)) & 15) == 0;
     if (vec)
         smj_launch(c, join_materialize_kernel<true>, grid, MT_THREADS, 0, d_dense, d_nj, nj_max, d_t1, c1, d_t2, c2, key2, d_out, d_out_indirect, rpb,
-                   d_use_store, d_store1, d_store2);
+                   d_use_store, d_store1, d_store2, d_tables_indirect);
     else
         smj_launch(c, join_materialize_kernel<false>, grid, MT_THREADS, 0, d_dense, d_nj, nj_max, d_t1, c1, d_t2, c2, key2, d_out, d_out_indirect, rpb,
-                   d_use_store, d_store1, d_store2);
+                   d_use_store, d_store1, d_store2, d_tables_indirect);
     KERNEL_CHECK(c);
     return SMJ_OK;
 }

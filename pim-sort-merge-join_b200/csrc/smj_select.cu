@@ -142,10 +142,11 @@ template <int MODE, bool PROBE = false>
 __global__ void __launch_bounds__(SELW_THREADS, PROBE ? 2 : 3)   // shared memory allows 3 CTAs per SM; the launch uses SMJ_SEL_CTAS
 select_tma_kernel(const int32_t *__restrict__ in, int64_t n, int cols, int ipt, int sel_col, int32_t sel_val, int select_all,
                   int key_col, u32 rowid_base, u64 *__restrict__ slots, u32 *__restrict__ tile_count, u32 *hist, u32 num_tiles,
-                  SmjSortPlan *plan, SmjBloom bloom, const u64 *__restrict__ n_dev)
+                  SmjSortPlan *plan, SmjBloom bloom, const u64 *__restrict__ n_dev, const int32_t *const *__restrict__ in_ind)
 {
     constexpr bool HIST = MODE == 1;
     PDL_ENTER();
+    if (in_ind) in = *in_ind;   // the table's address comes from a device cell: the replayed pipeline graph serves any table of this shape
     if (n_dev) {   // the table is a receive buffer: its fill is device-resident, n / num_tiles are the upper bounds
         const u64 v = *n_dev;
         if (v < (u64)n) {
@@ -628,6 +629,7 @@ static bool select_use_tma(const int32_t *d_in, int cols)
 {
     return cols <= SEL_MAX_COLS_TMA && (((uintptr_t)d_in) & 15) == 0;
 }
+bool smj_select_takes_tma(const int32_t *d_in, int cols) { return select_use_tma(d_in, cols); }
 
 static int select_set_attrs(SmjCtx *c)   // function attributes are per device
 {
@@ -667,10 +669,10 @@ int smj_launch_select_pairs(SmjCtx *c, const int32_t *d_in, int64_t n, int cols,
         const u32 grid = tiles < (u32)(sms * SMJ_SEL_CTAS) ? tiles : (u32)(sms * SMJ_SEL_CTAS);
         if (d_hist)
             select_tma_kernel<1><<<grid, SELW_THREADS, smem, c->stream>>>(d_in, n, cols, ipt, sel_col, (int32_t)sel_val, select_all,
-                                                                         key_col, rowid_base, d_tmp, d_counts, d_hist, tiles, nullptr, SmjBloom(), nullptr);
+                                                                         key_col, rowid_base, d_tmp, d_counts, d_hist, tiles, nullptr, SmjBloom(), nullptr, nullptr);
         else
             select_tma_kernel<0><<<grid, SELW_THREADS, smem, c->stream>>>(d_in, n, cols, ipt, sel_col, (int32_t)sel_val, select_all,
-                                                                         key_col, rowid_base, d_tmp, d_counts, nullptr, tiles, nullptr, SmjBloom(), nullptr);
+                                                                         key_col, rowid_base, d_tmp, d_counts, nullptr, tiles, nullptr, SmjBloom(), nullptr, nullptr);
         KERNEL_CHECK(c);
         tile_scan_kernel<<<1, TS_THREADS, 0, c->stream>>>(d_counts, tiles, d_offsets, d_count);
         KERNEL_CHECK(c);
@@ -780,10 +782,10 @@ int smj_launch_select_plan2(SmjCtx *c, const SmjSelectJob job[2])
             }
             if (B.probe)
                 smj_launch(c, select_tma_kernel<2, true>, grid, SELW_THREADS, SELW_SMEM, J.d_in, J.n, J.cols, ipt, J.sel_col, (int32_t)sel_val, select_all,
-                           J.key_col, 0u, J.slots, d_counts, (u32 *)nullptr, tiles, J.plan, B, J.n_dev);
+                           J.key_col, 0u, J.slots, d_counts, (u32 *)nullptr, tiles, J.plan, B, J.n_dev, J.d_in_ind);
             else
                 smj_launch(c, select_tma_kernel<2, false>, grid, SELW_THREADS, SELW_SMEM, J.d_in, J.n, J.cols, ipt, J.sel_col, (int32_t)sel_val, select_all,
-                           J.key_col, 0u, J.slots, d_counts, (u32 *)nullptr, tiles, J.plan, B, J.n_dev);
+                           J.key_col, 0u, J.slots, d_counts, (u32 *)nullptr, tiles, J.plan, B, J.n_dev, J.d_in_ind);
             KERNEL_CHECK(c);
         }
         tiles_of[t] = tiles; counts_of[t] = d_counts; tile_rows_of[t] = tile_rows;

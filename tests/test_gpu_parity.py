@@ -2,6 +2,8 @@
 reference's cpu_app.c by tests/test_oracle.py) on the same seeded inputs.  Bit-exact: integer data."""
 import hashlib
 
+import os
+
 import numpy as np
 import pytest
 
@@ -333,6 +335,28 @@ def test_run_device_resident_and_repeatable(smj, port):
         assert st["kernel_launches"] > 0 and st["total_device_ms"] > 0
     smj.free(d1)
     smj.free(d2)
+
+
+def test_run_graph_replays_on_new_tables_of_the_same_shape(smj, port):
+    """The pipeline graph captured for one pair of device tables is replayed for OTHER tables of the same shape and knobs
+    (their addresses reach the kernels through device cells): every call must still give its own tables' result."""
+    n = 300_000
+    tabs = [(smj.datagen.table(n, 4, s1), smj.datagen.table(n, 4, s2)) for s1, s2 in ((1, 2), (3, 4), (5, 6))]
+    wants = [port.run(a, b, 0, 450_000, 0, 450_000, 0, 0)[0] for a, b in tabs]
+    devs = [(smj.device_table(a), smj.device_table(b)) for a, b in tabs]
+    replayed = []
+    for i in (0, 0, 1, 2, 1, 0, 2):      # first call eager, second captures, the others replay whatever the pair
+        got, st = smj.run(devs[i][0], devs[i][1], on_device=True, select_val1=450_000, select_val2=450_000)
+        assert_same(got, wants[i], f"graph replay, pair {i}")
+        replayed.append(st["graph_replayed"])
+    if not os.environ.get("SMJ_NO_GRAPH"):
+        assert replayed[1:] == [1] * 6, replayed
+    # a different shape or knob must not replay the old graph
+    got, st = smj.run(devs[0][0], devs[0][1], on_device=True, select_val1=500_000, select_val2=450_000)
+    assert st["graph_replayed"] == 0
+    assert_same(got, port.run(tabs[0][0], tabs[0][1], 0, 500_000, 0, 450_000, 0, 0)[0], "graph replay, other knob")
+    for a, b in devs:
+        smj.free(a); smj.free(b)
 
 
 def test_run_config2_full_size(smj, port):

@@ -124,6 +124,8 @@ cases.append(("dups", rng.integers(-50, 400, size=(150_000, 3)).astype(np.int32)
               dict(select_col1=1, select_val1=-5, select_col2=2, select_val2=0, join_key1=2, join_key2=1)))
 cases.append(("zipf", smj_b200.datagen.zipf_table(200_000, 4, 31), smj_b200.datagen.zipf_table(150_000, 4, 32),
               dict(select_col1=0, select_val1=5000, select_col2=0, select_val2=5000, join_key1=0, join_key2=0)))
+cases.append(("wide", smj_b200.datagen.table(400_000, 8, 11), smj_b200.datagen.table(80_000, 8, 12, total_rows=400_000),      # C4's shape: 8 columns, 10 % select
+              dict(select_col1=0, select_val1=1_080_000, select_col2=0, select_val2=1_080_000, join_key1=0, join_key2=0)))
 cases.append(("tiny", rng.integers(0, 5, size=(37, 2)).astype(np.int32), rng.integers(0, 5, size=(11, 2)).astype(np.int32),
               dict(select_col1=0, select_val1=-1, select_col2=0, select_val2=-1, join_key1=0, join_key2=0)))
 cases.append(("empty", np.zeros((0, 3), np.int32), rng.integers(0, 5, size=(11, 2)).astype(np.int32),
@@ -170,4 +172,4 @@ def test_one_process_drives_all_gpus(world, variant, tmp_path):
         env["SMJ_RANKS_ON_ONE_GPU"] = "1"
     r = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("LOCAL_OK") == 6, r.stdout[-2000:]
+    assert r.stdout.count("LOCAL_OK") == 7, r.stdout[-2000:]
