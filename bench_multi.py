@@ -41,14 +41,19 @@ def run_multi(args, w, name):
     # count, summed over the ranks: the same virtual tables must give the same pair at every N (strong scaling) -- a
     # cheap end-to-end parity check at sizes no CPU oracle reaches (bench.py prints the same pair at N=1)
     from bench import result_checksum
-    out, st = smj_b200.run(d1, d2, cfg=cfg, on_device=True, keep_output=True)
-    big = smj_b200.dist.max_over_ranks(out.rows * out.cols * 4) > 2e9      # (skipped where a shard would not fit comfortably in host memory)
-    ck = 0 if big else result_checksum(smj_b200.smj.to_numpy(out))
-    L.smj_table_free(C.byref(out))
-    ck_lo = int(smj_b200.dist.sum_over_ranks(ck & 0xffffff))                     # (float64 all-reduce: 24-bit pieces stay exact; carries kept)
-    ck_mid = int(smj_b200.dist.sum_over_ranks((ck >> 24) & 0xffffff))
-    ck_hi = int(smj_b200.dist.sum_over_ranks(ck >> 48))
-    checksum = (ck_lo + (ck_mid << 24) + (ck_hi << 48)) & 0xffffffffffffffff
+
+    def checked_step():
+        out, st_ = smj_b200.run(d1, d2, cfg=cfg, on_device=True, keep_output=True)
+        big_ = smj_b200.dist.max_over_ranks(out.rows * out.cols * 4) > 2e9     # (skipped where a shard would not fit comfortably in host memory)
+        ck = 0 if big_ else result_checksum(smj_b200.smj.to_numpy(out))
+        rows_ = int(smj_b200.dist.sum_over_ranks(out.rows))
+        L.smj_table_free(C.byref(out))
+        ck_lo = int(smj_b200.dist.sum_over_ranks(ck & 0xffffff))                 # (float64 all-reduce: 24-bit pieces stay exact; carries kept)
+        ck_mid = int(smj_b200.dist.sum_over_ranks((ck >> 24) & 0xffffff))
+        ck_hi = int(smj_b200.dist.sum_over_ranks(ck >> 48))
+        return big_, (ck_lo + (ck_mid << 24) + (ck_hi << 48)) & 0xffffffffffffffff, rows_
+
+    big, checksum, rows_first = checked_step()      # the very first step (eager launches, fresh receive buffers)
 
     for _ in range(args.warmup):
         st = step()
@@ -72,6 +77,7 @@ def run_multi(args, w, name):
     smj_b200.dist.barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     clk = clocks.stop() if rank == 0 else None
+    _, checksum_last, rows_last = checked_step()    # ... and a step after the timed ones (graph replay): must be the same result
     ms = smj_b200.dist.max_over_ranks(dev_ms / args.steps)
     wall_ms = smj_b200.dist.max_over_ranks(wall_ms)
     launches = int(smj_b200.dist.sum_over_ranks(launches))
@@ -120,7 +126,9 @@ def run_multi(args, w, name):
             "config": {"workload": (f"{w['desc']} per GPU (weak scaling)" if args.scaling == "weak" else f"{w['desc']} in all (strong scaling)") +
                                    f": {tot1} x {tot2} rows over {G} GPUs ({n1} x {n2} per GPU), key-range partitioned, sample / count mailboxes and the "
                                    "exchange stores over NVLink peer memory (no NCCL call, no host wait in a step)", "name": name, "join_mode": "zip (cpu_app.c semantics)",
-                       "rows_selected": sel, "rows_joined": joined, "result_checksum": None if big else f"{checksum:016x}", "parallelism": f"key-range x{G}",
+                       "rows_selected": sel, "rows_joined": joined, "result_checksum": None if big else f"{checksum:016x}",
+                       "result_checksum_after_timed_steps": None if big else f"{checksum_last:016x}", "rows_joined_first_and_last_step": [rows_first, rows_last],
+                       "parallelism": f"key-range x{G}",
                        "exchange": os.environ.get("SMJ_DIST_EXCHANGE", "fabric") + ("/" + os.environ["SMJ_DIST_MODE"] if os.environ.get("SMJ_DIST_MODE") else ""),
                        "l2": f"per-GPU inputs ({n1 * cols * 4 / 1e6:.0f} + {n2 * cols * 4 / 1e6:.0f} MB) larger than the 126 MB L2; no explicit flush"},
             "stage_ms": stage_max, "wall_ms_per_step": wall_ms, "gpu_launches": launches,

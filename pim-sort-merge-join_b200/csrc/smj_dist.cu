@@ -708,6 +708,13 @@ int dist_step_enqueue(DistRank &K, const smj_config_t *cfg, u64 seq)
         if (!select_all && sel_val[t] >= (int64_t)INT32_MAX) n = 0;
         sj[t] = {K.blk[t].data, n, K.blk[t].cols, sel_col[t], (int32_t)sel_val[t], select_all, key[t]};
     }
+    // SMJ_DIST_POISON=1 (debugging): the receive buffers are filled with 0xff before the step, so a row that arrives late or
+    // not at all cannot hide behind the identical row a previous step left at the same place.  Race-free: the fill is ordered
+    // before this rank's sample flag, and no peer stores a row here before it has seen that flag.
+    static const bool poison = getenv("SMJ_DIST_POISON") && atoi(getenv("SMJ_DIST_POISON")) != 0;
+    if (poison)
+        for (int t = 0; t < 2; t++)
+            if (K.recv[t]) CUDA_TRY(cudaMemsetAsync(K.recv[t], 0xff, (size_t)K.cap_rows[t] * K.cap_cols[t] * 4, c->stream));
     smj_launch_on(c, c->stream, dist_splitters_kernel, 1, SPL2_THREADS, (size_t)n_pow2 * 4, K.peers, K.loc, me, G, seq, S, sj[0], sj[1], n_pow2, c->d_err);
     KERNEL_CHECK(c);
     CUDA_TRY(cudaEventRecord(K.ev[DE_SPLIT], c->stream));
