@@ -592,6 +592,11 @@ int dist_setup_recv_ipc(DistRank &K, const int64_t n_local[2], const int cols[2]
         if (!K.recv[t]) return SMJ_ENOMEM;
         K.cap_rows[t] = cap;
         K.cap_cols[t] = cols[t];
+        // The owner touches its buffer before any peer can: the very first step on a fresh 8-GPU allocation once returned a
+        // result whose checksum differed (row count right, every later step right, never with SMJ_DIST_POISON) -- whatever
+        // happens to device memory between cudaMalloc and its first use must not race with a peer's first stores.
+        CUDA_TRY(cudaMemsetAsync(K.recv[t], 0, (size_t)cap * cols[t] * 4, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
         CUDA_TRY(cudaIpcGetMemHandle(&hnd[t], K.recv[t]));
     }
     std::vector<cudaIpcMemHandle_t> hall((size_t)2 * G);
@@ -623,6 +628,8 @@ int dist_setup_recv_local(const int64_t n_local[][2], const int cols[2], const i
             if (!K.recv[t]) return SMJ_ENOMEM;
             K.cap_rows[t] = cap;
             K.cap_cols[t] = cols[t];
+            CUDA_TRY(cudaMemsetAsync(K.recv[t], 0, (size_t)cap * cols[t] * 4, K.c->stream));   // owner's first touch (see the IPC variant)
+            CUDA_TRY(cudaStreamSynchronize(K.c->stream));
         }
         for (int r = 0; r < G; r++)
             for (int q = 0; q < G; q++) g_dist.rk[r].peer_recv[t][q] = g_dist.rk[q].recv[t];
