@@ -308,13 +308,6 @@ def main():
     # bytes of an average executed pass launch: the sort runs ceil(bits(key range) / 8) passes per table (device sort plan)
     pass_bytes = st.get("sort_pass_bytes_avg", 0.0) or 16.0 * m_launch
     achieved = pass_bytes / (pass_avg_ms * 1e-3) / 1e9 if pass_avg_ms > 0 else 0.0
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "radix_pass_traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            pass
     dram = None   # DRAM bytes of one whole step, summed over its kernels from the committed ncu pass of this command
     dp = os.path.join(ROOT, "profiles", f"r02_{name}_dram_bytes.json")
     if os.path.exists(dp):
@@ -322,6 +315,12 @@ def main():
             dram = json.load(open(dp))
         except Exception:
             dram = None
+    # DRAM bytes of one executed radix pass launch, from the same committed ncu pass (the kernel's bytes per step / the
+    # launches that had work; the pair arrays are L2-resident at C2, so this is BELOW the algorithmic bytes)
+    traffic = None
+    if dram and "radix_pass_kernel" in dram.get("kernels", {}) and passes:
+        kd = dram["kernels"]["radix_pass_kernel"]
+        traffic = (kd["dram_read_bytes"] + kd["dram_write_bytes"]) / max(passes / max(args.steps, 1), 1)
     roofline = {"bound": "hbm", "kernel": f"radix_pass_kernel (onesweep scatter pass; {st['sort_passes']} launches with work per step, each over both tables' pairs)", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": pass_bytes, "avg_launch_ms": pass_avg_ms,

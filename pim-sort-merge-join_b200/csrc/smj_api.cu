@@ -393,6 +393,9 @@ int smj_check_device_flag(SmjCtx *c)
     if (*h) {
         const u32 code = *h;
         cudaMemsetAsync(c->d_err, 0, 4, c->stream);
+        if (code == 6)
+            return smj_set_error(SMJ_EINVAL, "an input table is not sorted by its key column (smj_join, smj_join_count and smj_merge take "
+                                             "tables sorted by key: sort them with smj_sort first)");
         if (code >= 4)
             return smj_set_error(SMJ_EINTERNAL, "device-side check failed (code %u: %s)", code,
                                  code == 4 ? "a rank waited 30 s for a peer's flag: some rank did not reach this step of the exchange"

@@ -12,6 +12,7 @@ typedef unsigned int u32;
 #define SMJ_ERR_SPIN_SELECT 1u
 #define SMJ_ERR_SPIN_RADIX  2u
 #define SMJ_ERR_SPIN_JOIN   3u
+#define SMJ_ERR_UNSORTED    6u   // smj_join / smj_join_count / smj_merge: an input is not sorted by its key column
 
 __device__ __forceinline__ u32 lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ u32 lanemask_lt()

@@ -110,7 +110,7 @@ template <int MODE>
 __global__ void __launch_bounds__(JN_THREADS)
 join_match_kernel(const u64 *__restrict__ L, const u64 *__restrict__ R, const u64 *__restrict__ counts, u32 m1_max,
                   u32 m2_max, const u32 *__restrict__ part, const u32 *__restrict__ runstart, uint2 *__restrict__ matches,
-                  u32 *__restrict__ tile_count, u64 *count, uint2 *__restrict__ many_runs)
+                  u32 *__restrict__ tile_count, u64 *count, uint2 *__restrict__ many_runs, u32 *err)
 {
     PDL_ENTER();
     u32 m1, m2;
@@ -135,6 +135,13 @@ join_match_kernel(const u64 *__restrict__ L, const u64 *__restrict__ R, const u6
         g.nb = b1 - g.b0;
         g.nbh = g.nb + (b1 < m2 ? 1u : 0u);               // right segment plus one halo element
         g.rs = rs;
+        // Inputs that are NOT sorted by their keys (a caller's mistake: smj_join / smj_join_count take sorted tables) give
+        // co-ranks that do not increase from tile to tile; such a tile is skipped and reported instead of being fetched
+        // past the shared-memory buffer.
+        if (a1 < a0 || g.na > (u32)JN_TILE || b1 < g.b0 || g.nb > (u32)JN_TILE || g.na + g.nb > (u32)JN_TILE) {
+            g.na = 0; g.nb = 0; g.nbh = 0;
+            if (threadIdx.x == 0) atomicExch(err, SMJ_ERR_UNSORTED);
+        }
         return g;
     };
     auto fetch = [&](const Geo &g, u64 *buf) {            // buf[0] = L[a0-1] (if any), buf[1..] = left, then right
@@ -583,7 +590,7 @@ int smj_launch_join_match(SmjCtx *c, const u64 *d_l, const u64 *d_r, const u64 *
     const u32 grid = tiles < (u32)(sms * SMJ_JN_GRID) ? tiles : (u32)(sms * SMJ_JN_GRID);   // ~60 registers x 256 threads: 4 CTAs per SM
     if (mode == SMJ_JOIN_ZIP) {
         smj_launch(c, join_match_kernel<SMJ_JOIN_ZIP>, grid, JN_THREADS, 0, d_l, d_r, d_counts, m1_max, m2_max, d_part, d_runstart,
-                   d_matches, d_tile_count, d_count, (uint2 *)nullptr);
+                   d_matches, d_tile_count, d_count, (uint2 *)nullptr, c->d_err);
         KERNEL_CHECK(c);
         const u32 chunk = smj_join_scan_chunk();
         if (tiles > chunk) {   // d_tile_off has smj_join_scan_blocks(tiles) spare words behind its `tiles` entries
@@ -602,7 +609,7 @@ int smj_launch_join_match(SmjCtx *c, const u64 *d_l, const u64 *d_r, const u64 *
     } else {
         // many-to-many: d_matches (if given) receives one (first right position, run length) entry per LEFT element
         smj_launch(c, join_match_kernel<SMJ_JOIN_MANY>, grid, JN_THREADS, 0, d_l, d_r, d_counts, m1_max, m2_max, d_part, d_runstart,
-                   (uint2 *)nullptr, d_tile_count, d_count, d_matches);
+                   (uint2 *)nullptr, d_tile_count, d_count, d_matches, c->d_err);
     }
     KERNEL_CHECK(c);
     return SMJ_OK;

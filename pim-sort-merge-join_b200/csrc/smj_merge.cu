@@ -57,6 +57,7 @@ merge_pairs_kernel(const u64 *__restrict__ A, u32 na_all, const u64 *__restrict_
         g.b0 = (u32)(g.d0 - g.a0);
         g.na = a1 - g.a0;
         g.nb = (u32)(d1 - a1) - g.b0;
+        if (a1 < g.a0 || g.na > (u32)MG_TILE || g.nb > (u32)MG_TILE || g.na + g.nb > (u32)MG_TILE) { g.na = 0; g.nb = 0; }   // runs that are not sorted: skip, never fetch past the buffer
         return g;
     };
     auto fetch = [&](const Geo &g, u64 *buf) {

@@ -126,6 +126,7 @@ def test_config3_zipf_200M_x_200M(env, port):
     # the many-to-many COUNT of the same inputs (smj_join_count on key-sorted tables), against the per-key products
     many = int((c1.double() * c2.double()).sum().item())
     s1, s2 = t1[torch.sort(t1[:, 0], stable=True)[1]].contiguous(), t2[torch.sort(t2[:, 0], stable=True)[1]].contiguous()
+    torch.cuda.synchronize()   # torch's stream and the library's are unrelated: the sorted copies must be complete before libsmj reads them
     cnt = smj.join_count(smj.Table(s1.data_ptr(), n, cols, 1), smj.Table(s2.data_ptr(), n, cols, 1), 0, 0, mode=smj.JOIN_MANY)
     assert abs(cnt - many) <= many * 1e-12 and cnt == int((c1.long() * c2.long()).sum().item())
 

@@ -378,6 +378,23 @@ def test_run_config2_full_size(smj, port):
     assert_same(out, want, "config 2 full size")
 
 
+def test_join_on_unsorted_input_is_an_error_code_not_a_fault(smj, port):
+    """smj_join / smj_join_count / smj_merge take tables SORTED by key (as join.c / merge_dpu.c do).  Unsorted input must not
+    take the process down: inconsistent co-ranks are skipped and reported (SMJ_EINVAL), and the library keeps working."""
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 1 << 30, size=(300_000, 4)).astype(np.int32)      # unsorted
+    b = rng.integers(0, 1 << 30, size=(200_000, 4)).astype(np.int32)
+    for call in (lambda: smj.join(a, b, 0, 0), lambda: smj.join_count(a, b, 0, 0, mode=smj.JOIN_MANY), lambda: smj.merge(a, b, 0)):
+        try:
+            call()                      # garbage in, garbage out is allowed; a device fault is not
+        except smj.SmjError as e:
+            assert e.code == -1, e
+    t1, t2 = smj.datagen.table(50_000, 4, 1), smj.datagen.table(50_000, 4, 2)
+    want, sel, _ = port.run(t1, t2, 0, 75_000, 0, 75_000, 0, 0)
+    got, st = smj.run(t1, t2, select_val1=75_000, select_val2=75_000)
+    assert_same(got, want, "run after unsorted joins")
+
+
 def test_errors_are_codes_not_exits(smj):
     t = np.zeros((10, 3), np.int32)
     with pytest.raises(smj.SmjError) as e:
