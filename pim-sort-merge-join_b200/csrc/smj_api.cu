@@ -545,8 +545,9 @@ extern "C" int smj_merge(const smj_table_t *a, const smj_table_t *b, int key_col
         SMJ_TRY(smj_launch_gather_rows2(c, pm, total, d_a, d_b, (u32)a->rows, cols, tmp));
         SMJ_TRY(emit_out_from_device(c, out, tmp, total, cols));
     }
-    SMJ_TRY(smj_check_device_flag(c));
-    return SMJ_OK;
+    const int rc = smj_check_device_flag(c);
+    if (rc != SMJ_OK) smj_table_free(out);   // runs that were not sorted: no half-merged table for the caller
+    return rc;
 }
 
 // ------------------------------------------------------------------ smj_join
@@ -590,6 +591,8 @@ static int join_sorted_pairs(SmjCtx *c, const u64 *pl, u32 m1, const u64 *pr, u3
     SMJ_TRY(smj_check_device_flag(c));
     const int64_t j = (int64_t)hm[0];
     *rows_out = j;
+    if (mode == SMJ_JOIN_ZIP && j > (int64_t)(m1 < m2 ? m1 : m2))   // impossible for sorted inputs (every left row pairs with its own right row)
+        return smj_set_error(SMJ_EINVAL, "an input table is not sorted by its key column (smj_join and smj_join_count take tables sorted by key)");
     if (count_only) return SMJ_OK;
     if (mode == SMJ_JOIN_MANY) {
         // the many-to-many result can dwarf its inputs (cL * cR rows per key): refuse what cannot be held, expand the rest

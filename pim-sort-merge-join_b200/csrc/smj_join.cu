@@ -326,7 +326,7 @@ join_apply_kernel(const u32 *__restrict__ tile_count, u32 num_tiles, u32 chunk, 
 // dense[offsets[t] + i] = slots[t * JN_TILE + i], i < tile_count[t]: the matches in result order, contiguous.
 __global__ void __launch_bounds__(256)
 join_compact_kernel(const uint2 *__restrict__ slots, const u32 *__restrict__ tile_count, const u64 *__restrict__ tile_off, u32 num_tiles,
-                    uint2 *__restrict__ dense, const u64 *__restrict__ counts, u32 m1_max, u32 m2_max)
+                    uint2 *__restrict__ dense, const u64 *__restrict__ counts, u32 m1_max, u32 m2_max, u64 dense_cap)
 {
     PDL_ENTER();
     {
@@ -340,8 +340,10 @@ join_compact_kernel(const uint2 *__restrict__ slots, const u32 *__restrict__ til
     for (u32 t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < num_tiles; t += warps) {   // one warp per tile
         const u32 cnt = tile_count[t];
         const uint2 *src = slots + (size_t)t * JN_TILE;
-        uint2 *dst = dense + tile_off[t];
-        for (u32 i = lane; i < cnt; i += 32) dst[i] = src[i];
+        const u64 off = tile_off[t];
+        uint2 *dst = dense + off;
+        // (sorted inputs give at most min(m1, m2) matches, which is what `dense` holds; unsorted ones can give more: never past the end)
+        for (u32 i = lane; i < cnt; i += 32) if (off + i < dense_cap) dst[i] = src[i];
     }
 }
 
@@ -604,7 +606,8 @@ int smj_launch_join_match(SmjCtx *c, const u64 *d_l, const u64 *d_r, const u64 *
         if (d_dense) {
             KERNEL_CHECK(c);
             const u32 cgrid = (tiles + 7) / 8 < (u32)(sms * 8) ? (tiles + 7) / 8 : (u32)(sms * 8);
-            smj_launch(c, join_compact_kernel, cgrid, 256, 0, d_matches, d_tile_count, d_tile_off, tiles, d_dense, d_counts, m1_max, m2_max);
+            smj_launch(c, join_compact_kernel, cgrid, 256, 0, d_matches, d_tile_count, d_tile_off, tiles, d_dense, d_counts, m1_max, m2_max,
+                       (u64)(m1_max < m2_max ? m1_max : m2_max));
         }
     } else {
         // many-to-many: d_matches (if given) receives one (first right position, run length) entry per LEFT element

@@ -40,14 +40,14 @@ __device__ __forceinline__ void mg_cp_async8(void *dst_smem, const void *src_gme
 // nothing overlapped.)
 __global__ void __launch_bounds__(MG_THREADS)
 merge_pairs_kernel(const u64 *__restrict__ A, u32 na_all, const u64 *__restrict__ B, u32 nb_all,
-                   const u32 *__restrict__ part, u64 *__restrict__ out, u32 num_tiles)
+                   const u32 *__restrict__ part, u64 *__restrict__ out, u32 num_tiles, u32 *__restrict__ err)
 {
     // (+ MG_TILE / 16: the merged tile is staged with one pad word per 16 elements -- thread t's eight results sit at 8 t .. 8 t + 7,
     // a 64-byte stride that made the stores 16-way bank conflicts: 70 % of all shared-memory wavefronts in the first capture)
     __shared__ __align__(16) u64 s[2][MG_TILE + MG_TILE / 16];
     const u32 tid = threadIdx.x;
     const u64 total = (u64)na_all + nb_all;
-    struct Geo { u32 a0, na, b0, nb; u64 d0; };
+    struct Geo { u32 a0, na, b0, nb, bad_out; u64 d0; };   // bad_out: output entries of a tile that is skipped (0 for a good tile)
     auto geo = [&](u32 tile) {
         Geo g;
         g.d0 = (u64)tile * MG_TILE;
@@ -57,7 +57,10 @@ merge_pairs_kernel(const u64 *__restrict__ A, u32 na_all, const u64 *__restrict_
         g.b0 = (u32)(g.d0 - g.a0);
         g.na = a1 - g.a0;
         g.nb = (u32)(d1 - a1) - g.b0;
-        if (a1 < g.a0 || g.na > (u32)MG_TILE || g.nb > (u32)MG_TILE || g.na + g.nb > (u32)MG_TILE) { g.na = 0; g.nb = 0; }   // runs that are not sorted: skip, never fetch past the buffer
+        g.bad_out = 0;
+        // Runs that are not sorted give co-ranks that do not grow: the tile is skipped (never fetch past a buffer), its output is
+        // filled with pair 0 (row 0: the gather that follows must not meet stale row ids) and the call reports SMJ_EINVAL (code 6).
+        if (a1 < g.a0 || g.na > (u32)MG_TILE || g.nb > (u32)MG_TILE || g.na + g.nb != (u32)(d1 - g.d0)) { g.na = 0; g.nb = 0; g.bad_out = (u32)(d1 - g.d0); }
         return g;
     };
     auto fetch = [&](const Geo &g, u64 *buf) {
@@ -101,6 +104,10 @@ merge_pairs_kernel(const u64 *__restrict__ A, u32 na_all, const u64 *__restrict_
         __syncthreads();
         u64 *dst = out + gc.d0;
         for (u32 i = tid; i < ntile; i += MG_THREADS) dst[i] = buf[i + (i >> 4)];
+        if (gc.bad_out) {
+            for (u32 i = tid; i < gc.bad_out; i += MG_THREADS) dst[i] = 0ull;
+            if (tid == 0) atomicExch(err, SMJ_ERR_UNSORTED);
+        }
         tile = next;
         cur ^= 1;
         // the next iteration's first barrier orders these reads of buf before the fetch that refills it one round later
@@ -121,7 +128,7 @@ int smj_launch_merge_pairs(SmjCtx *c, const u64 *d_a, u32 na, const u64 *d_b, u3
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     const u32 grid = tiles < (u32)(sms * 5) ? tiles : (u32)(sms * 5);   // 34 KB of shared memory, 48 registers x 256 threads: five CTAs per SM
-    merge_pairs_kernel<<<grid, MG_THREADS, 0, c->stream>>>(d_a, na, d_b, nb, d_part, d_out, tiles);
+    merge_pairs_kernel<<<grid, MG_THREADS, 0, c->stream>>>(d_a, na, d_b, nb, d_part, d_out, tiles, c->d_err);
     KERNEL_CHECK(c);
     return SMJ_OK;
 }
