@@ -47,6 +47,7 @@ extern "C" {
 #define SMJ_ENCCL      -6   /* NCCL error */
 #define SMJ_EINTERNAL  -7   /* device-side consistency check failed */
 #define SMJ_EIRREGULAR -8   /* smj_csv_parse: the text needs the sequential host parser to reproduce the reference exactly */
+#define SMJ_ERANGE     -9   /* smj_table_from_i64: a cell of the int64 table is not an int32 value */
 
 /* join modes */
 #define SMJ_JOIN_ZIP   0    /* == cpu_app.c:204-266 / join.c:153-248: i-th left duplicate pairs with i-th right duplicate */
@@ -149,6 +150,17 @@ void smj_device_free(void *p);
 int  smj_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes);
 int  smj_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes);
 int  smj_device_sync(void);
+
+/* ---- the reference's in-memory cell type at the boundary ----
+ * The reference keeps its tables as T[rows*cols] with T = int64_t (common.h:1-9; its UINT64 / DOUBLE branches are never
+ * selected) holding atoi() results (cpu_app.c:71, app.c:84), i.e. int32 values in 8-byte cells.  A host that keeps such
+ * T* arrays (app.c:158-159 test_array1/2) passes them as they are:
+ * smj_table_from_i64: `cells` (host pointer, or device pointer when cells_on_device) -> *out, a library-owned int32 table
+ *   (out->on_device chosen by the caller before the call, as for every output; smj_table_free).  Narrowed on the GPU; a
+ *   cell outside [INT32_MIN, INT32_MAX] is refused with SMJ_ERANGE (the message names it), never truncated.
+ * smj_table_to_i64: the int32 table t (host or device) widened into the caller's rows*cols int64 buffer. */
+int  smj_table_from_i64(const int64_t *cells, int64_t rows, int32_t cols, int cells_on_device, smj_table_t *out);
+int  smj_table_to_i64(const smj_table_t *t, int64_t *cells, int cells_on_device);
 
 /* ---- CSV text <-> tables on the GPU ----
  * smj_csv_parse == set_csv_size + load_csv (cpu_app.c:15-79 == app.c:28-92) for regular files: `text` is the whole file

@@ -3,7 +3,7 @@ host is C -- see host/app.c for the drop-in driver).  Import as ``smj_b200`` thr
 because the directory name carries hyphens."""
 from .smj import (  # noqa: F401
     SmjError, Config, Stats, Table, lib, build, lib_path, select, sort, merge, join, join_count, run,
-    device_table, synth_device_table, free, JOIN_ZIP, JOIN_MANY, csv_parse, csv_format,
+    device_table, synth_device_table, free, JOIN_ZIP, JOIN_MANY, csv_parse, csv_format, from_i64, to_i64, to_numpy,
 )
 from . import datagen  # noqa: F401
 from . import dist  # noqa: F401

@@ -60,6 +60,7 @@ extern "C" const char *smj_strerror(int code)
     case SMJ_ENCCL: return "NCCL error";
     case SMJ_EINTERNAL: return "device-side consistency check failed";
     case SMJ_EIRREGULAR: return "CSV text needs the sequential host parser";
+    case SMJ_ERANGE: return "cell value outside the int32 range of the engine's tables";
     default: return "unknown error";
     }
 }

@@ -372,6 +372,24 @@ __global__ void __launch_bounds__(TS_THREADS) tile_scan_kernel(const u32 *__rest
     if (threadIdx.x == 0) *total = t;
 }
 
+// The same over many CTAs (scan_large_* in smj_dev.cuh) for the stage entry points (smj_select / smj_sort / smj_merge / smj_join on
+// tables of more than SCAN1_STAGE tiles, ~16 M rows): the one-CTA scan walks its chunks from global memory beyond that size.
+__global__ void __launch_bounds__(TS_THREADS) tile_blocksum_kernel(const u32 *__restrict__ counts, u32 num_tiles, u32 chunk, u64 *blocksum)
+{
+    __shared__ u64 s_w[TS_THREADS / 32];
+    PDL_ENTER();
+    scan_large_blocksum(counts, num_tiles, chunk, blockIdx.x, blocksum, s_w);
+}
+__global__ void __launch_bounds__(TS_THREADS) tile_apply_kernel(const u32 *__restrict__ counts, u32 num_tiles, u32 chunk, u64 *offsets,
+                                                                const u64 *__restrict__ blocksum, u64 *total)
+{
+    __shared__ u32 s_stage[SCAN1_STAGE];
+    __shared__ u64 s_w[TS_THREADS / 32];
+    PDL_ENTER();
+    const u64 t = scan_large_apply(counts, num_tiles, chunk, blockIdx.x, offsets, blocksum, s_stage, s_w);
+    if (blockIdx.x + 1 == gridDim.x && threadIdx.x == 0) *total = t;   // the last block's running total is the grand total
+}
+
 // pairs[offsets[t] + i] = slots[t * tile_rows + i], i < counts[t]: the survivors in table order, contiguous.
 // One WARP per tile: a tile is ~1-2 K pairs, and with 64 tiles in flight per SM instead of 8 (one per CTA) the
 // dependent count/offset -> data round trips overlap.
@@ -641,6 +659,17 @@ static int select_set_attrs(SmjCtx *c)   // function attributes are per device
     return SMJ_OK;
 }
 
+// tiles one CTA scans; beyond it the many-CTA scans take over (tests force them at small sizes with a small chunk)
+static u32 scan_chunk(void)
+{
+    static const u32 chunk = [] {
+        const char *e = getenv("SMJ_SCAN_CHUNK");
+        const long v = e ? atol(e) : 0;
+        return (u32)((v >= 32 && v <= SCAN1_STAGE) ? v : SCAN1_STAGE);
+    }();
+    return chunk;
+}
+
 // scratch words (u64) per table: look-back status (fallback kernel) or tile offsets + tile counts (TMA path);
 // the smallest tile either path uses is SEL_THREADS rows
 size_t smj_select_num_tiles(int64_t n) { return 2 * (size_t)((n + SEL_THREADS - 1) / SEL_THREADS) + 2; }
@@ -674,8 +703,19 @@ int smj_launch_select_pairs(SmjCtx *c, const int32_t *d_in, int64_t n, int cols,
             select_tma_kernel<0><<<grid, SELW_THREADS, smem, c->stream>>>(d_in, n, cols, ipt, sel_col, (int32_t)sel_val, select_all,
                                                                          key_col, rowid_base, d_tmp, d_counts, nullptr, tiles, nullptr, SmjBloom(), nullptr, nullptr);
         KERNEL_CHECK(c);
-        tile_scan_kernel<<<1, TS_THREADS, 0, c->stream>>>(d_counts, tiles, d_offsets, d_count);
-        KERNEL_CHECK(c);
+        const u32 chunk = scan_chunk();
+        if (tiles > chunk) {
+            // spare words of the status region, behind [offsets u64 x tiles][counts u32 x tiles] (smj_select_num_tiles)
+            u64 *d_blocksum = d_status + tiles + (tiles + 1) / 2;
+            const u32 nb = (tiles + chunk - 1) / chunk;
+            tile_blocksum_kernel<<<nb, TS_THREADS, 0, c->stream>>>(d_counts, tiles, chunk, d_blocksum);
+            KERNEL_CHECK(c);
+            tile_apply_kernel<<<nb, TS_THREADS, 0, c->stream>>>(d_counts, tiles, chunk, d_offsets, d_blocksum, d_count);
+            KERNEL_CHECK(c);
+        } else {
+            tile_scan_kernel<<<1, TS_THREADS, 0, c->stream>>>(d_counts, tiles, d_offsets, d_count);
+            KERNEL_CHECK(c);
+        }
         const u32 cgrid = (tiles + 7) / 8 < (u32)(sms * 8) ? (tiles + 7) / 8 : (u32)(sms * 8);
         select_compact_kernel<<<cgrid, 256, 0, c->stream>>>(d_tmp, d_counts, d_offsets, tiles, (u32)tile_rows, d_pairs);
         KERNEL_CHECK(c);
@@ -803,19 +843,15 @@ int smj_launch_select_plan2(SmjCtx *c, const SmjSelectJob job[2])
         KERNEL_CHECK(c);
     }
     // tile offsets, survivor counts and sort plans: one CTA per table, or many when a table has more tiles than one CTA stages
-    static const u32 scan_chunk = [] {
-        const char *e = getenv("SMJ_SCAN_CHUNK");   // tests force the many-CTA scan at small sizes with a small chunk
-        const long v = e ? atol(e) : 0;
-        return (u32)((v >= 32 && v <= SCAN1_STAGE) ? v : SCAN1_STAGE);
-    }();
-    if (tiles_of[0] > scan_chunk || tiles_of[1] > scan_chunk) {
+    const u32 chunk = scan_chunk();
+    if (tiles_of[0] > chunk || tiles_of[1] > chunk) {
         PlanScanLargeArgs LA = {};
-        LA.chunk = scan_chunk;
+        LA.chunk = chunk;
         LA.full_passes = full_passes;
         u32 nb[2];
         for (int t = 0; t < 2; t++) {
             LA.t[t] = SA.t[t];
-            nb[t] = (tiles_of[t] + scan_chunk - 1) / scan_chunk;
+            nb[t] = (tiles_of[t] + chunk - 1) / chunk;
             // spare words of the table's status region, behind [offsets u64 x tiles][counts u32 x tiles] (smj_select_num_tiles)
             LA.blocksum[t] = job[t].d_status + tiles_of[t] + (tiles_of[t] + 1) / 2;
         }
@@ -853,6 +889,8 @@ void smj_preload_select(void)
     cudaFuncGetAttributes(&a, select_tma_kernel<2>);
     cudaFuncGetAttributes(&a, select_tma_kernel<2, true>);
     cudaFuncGetAttributes(&a, tile_scan_kernel);
+    cudaFuncGetAttributes(&a, tile_blocksum_kernel);
+    cudaFuncGetAttributes(&a, tile_apply_kernel);
     cudaFuncGetAttributes(&a, select_compact_kernel);
     cudaFuncGetAttributes(&a, plan_scan_kernel);
     cudaFuncGetAttributes(&a, plan_blocksum_kernel);

@@ -55,7 +55,7 @@ ABI_SYMBOLS = [
     "smj_host_alloc", "smj_host_free", "smj_device_alloc", "smj_device_free", "smj_memcpy_h2d", "smj_memcpy_d2h",
     "smj_device_sync", "smj_synth_table", "smj_kernel_launches", "smj_device_count", "smj_version",
     "smj_plan_splitters", "smj_plan_exchange", "smj_csv_parse", "smj_csv_format", "smj_synth_zipf_cdf",
-    "smj_plan_fabric",
+    "smj_plan_fabric", "smj_table_from_i64", "smj_table_to_i64",
 ]
 
 _lib = None
@@ -116,6 +116,8 @@ def lib():
     L.smj_csv_format.argtypes = [TP, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.smj_plan_splitters.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
     L.smj_plan_exchange.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int64)]
+    L.smj_table_from_i64.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int, TP]
+    L.smj_table_to_i64.argtypes = [TP, C.c_void_p, C.c_int]
     _lib = L
     return L
 
@@ -246,6 +248,25 @@ def run(t1, t2, cfg=None, on_device=False, keep_output=False, **knobs):
     if keep_output:
         return out, st.as_dict()
     return _take(out), st.as_dict()
+
+
+# ------------------------------------------------------------------ the reference's T = int64_t cells at the boundary
+def from_i64(a, on_device=True):
+    """numpy int64 [rows, cols] (the reference's T[rows*cols], common.h:1-9) -> library-owned int32 Table via
+    smj_table_from_i64 (narrowed on the GPU); raises SmjError(-9) when a cell is not an int32 value."""
+    a = np.ascontiguousarray(a, dtype=np.int64)
+    assert a.ndim == 2
+    out = Table(None, 0, 0, int(on_device))
+    check(lib().smj_table_from_i64(a.ctypes.data if a.size else None, a.shape[0], a.shape[1], 0, C.byref(out)))
+    return out
+
+
+def to_i64(t):
+    """int32 table (numpy or Table) -> numpy int64 [rows, cols] via smj_table_to_i64."""
+    tin, keep = _in(t)
+    out = np.empty((tin.rows, tin.cols), np.int64)
+    check(lib().smj_table_to_i64(C.byref(tin), out.ctypes.data if out.size else None, 0))
+    return out
 
 
 # ------------------------------------------------------------------ CSV on the GPU

@@ -404,3 +404,72 @@ def test_errors_are_codes_not_exits(smj):
         smj.join(t, t, 0, 5)
     with pytest.raises(smj.SmjError):
         smj.run(t, t, select_col1=9)
+
+
+# ------------------------------------------------------------------ the reference's T = int64_t cells at the boundary
+@pytest.mark.parametrize("rows,cols", [(0, 3), (1, 1), (3, 1), (5, 3), (1001, 5), (100_003, 4)])
+@pytest.mark.parametrize("to_device", [True, False])
+def test_i64_tables_round_trip(smj, rows, cols, to_device):
+    """smj_table_from_i64 / smj_table_to_i64: the reference's T[rows*cols] (T = int64_t, common.h:1-9) in and out."""
+    rng = np.random.default_rng(rows + cols)
+    a = rng.integers(I32MIN, I32MAX, size=(rows, cols), endpoint=True).astype(np.int64)
+    if rows:
+        a[0, 0], a[-1, -1] = I32MIN, I32MAX
+    t = smj.from_i64(a, on_device=to_device)
+    assert (t.rows, t.cols, t.on_device) == (rows, cols, int(to_device))
+    assert_same(smj.to_numpy(t), a.astype(np.int32), "from_i64")
+    back = smj.to_i64(t)
+    assert back.dtype == np.int64 and np.array_equal(back, a)
+    smj.lib().smj_table_free(smj.smj.C.byref(t))
+    assert np.array_equal(smj.to_i64(a.astype(np.int32)), a)          # host int32 table in
+
+
+def test_i64_tables_device_source_and_chunked_host_source(smj):
+    """Host cells travel in 64 MB chunks through two staging buffers (2.5 chunks here); device cells are narrowed in place."""
+    C = smj.smj.C
+    rows, cols = 5_000_000, 4
+    a = (np.arange(rows * cols, dtype=np.int64).reshape(rows, cols) * 2654435761 % (1 << 32)) - (1 << 31)
+    t = smj.from_i64(a)
+    assert_same(smj.to_numpy(t), a.astype(np.int32), "from_i64, chunked")
+    smj.lib().smj_table_free(C.byref(t))
+    small = a[:70_001]
+    p = C.c_void_p()
+    smj.smj.check(smj.lib().smj_device_alloc(C.byref(p), small.nbytes))
+    smj.smj.check(smj.lib().smj_memcpy_h2d(p, small.ctypes.data, small.nbytes))
+    out = smj.Table(None, 0, 0, 1)
+    smj.smj.check(smj.lib().smj_table_from_i64(p, small.shape[0], cols, 1, C.byref(out)))
+    assert_same(smj.to_numpy(out), small.astype(np.int32), "from_i64, device source")
+    back = C.c_void_p()
+    smj.smj.check(smj.lib().smj_device_alloc(C.byref(back), small.nbytes))
+    smj.smj.check(smj.lib().smj_table_to_i64(C.byref(out), back, 1))
+    got = np.empty_like(small)
+    smj.smj.check(smj.lib().smj_memcpy_d2h(got.ctypes.data, back, small.nbytes))
+    assert np.array_equal(got, small)
+    smj.lib().smj_table_free(C.byref(out))
+    smj.lib().smj_device_free(p)
+    smj.lib().smj_device_free(back)
+
+
+@pytest.mark.parametrize("bad", [1 << 31, -(1 << 31) - 1, 1 << 40, -(1 << 62)])
+def test_i64_cell_outside_int32_is_refused_not_truncated(smj, bad):
+    a = np.arange(40_000 * 3, dtype=np.int64).reshape(40_000, 3)
+    a[31_337, 2] = bad
+    with pytest.raises(smj.SmjError) as e:
+        smj.from_i64(a)
+    assert e.value.code == -9 and "[31337][2]" in str(e.value)
+    t = smj.from_i64(np.clip(a, I32MIN, I32MAX))                          # the library goes on working
+    smj.lib().smj_table_free(smj.smj.C.byref(t))
+
+
+def test_pipeline_on_the_references_int64_arrays(smj, ref):
+    """The reference's own cpu_app.c functions on its own T = int64_t arrays against from_i64 -> smj_run -> to_i64."""
+    rng = np.random.default_rng(64)
+    t1 = rng.integers(-200, 9000, size=(3000, 4)).astype(np.int64)
+    t2 = rng.integers(-200, 9000, size=(2500, 5)).astype(np.int64)
+    want = ref.join(ref.sort(ref.select(t1, 0, 5000), 0), ref.sort(ref.select(t2, 0, 5000), 0), 0, 0).astype(np.int64)
+    d1, d2 = smj.from_i64(t1), smj.from_i64(t2)
+    out, st = smj.run(d1, d2, select_val1=5000, select_val2=5000, on_device=True, keep_output=True)
+    got = smj.to_i64(out)
+    for t in (d1, d2, out):
+        smj.lib().smj_table_free(smj.smj.C.byref(t))
+    assert got.dtype == np.int64 and got.shape == want.shape and np.array_equal(got, want)

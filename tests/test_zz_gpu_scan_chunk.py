@@ -1,5 +1,5 @@
 """The many-CTA scan of the tile counts (scan_large_* in csrc/smj_dev.cuh; plan_blocksum / plan_apply in smj_select.cu,
-join_blocksum / join_apply in smj_join.cu) replaces the one-CTA scan above 8192 tiles per table, i.e. above ~16 M rows:
+join_blocksum / join_apply in smj_join.cu, tile_blocksum / tile_apply for the stage entry points) replaces the one-CTA scan above 8192 tiles per table, i.e. above ~16 M rows:
 sizes only tests/test_gpu_full_size.py reaches.  SMJ_SCAN_CHUNK shrinks the chunk so that small, oracle-checked shapes
 take the same kernels.  libsmj.so reads the knob once per process, hence the child process."""
 import os
@@ -38,6 +38,16 @@ for n1, n2, c1, c2, hi in cases:
         got, st = smj_b200.run(t1, t2, select_col1=0, select_val1=v1, select_col2=0, select_val2=v2, join_key1=0, join_key2=0)
         assert st["rows_selected"] == list(sel), (n1, n2, rep, st["rows_selected"], sel)
         assert got.shape == want.shape and np.array_equal(got, want), (n1, n2, c1, c2, hi, rep, got.shape, want.shape)
+# the stage entry points take the same many-CTA scan (tile_blocksum / tile_apply in smj_select.cu)
+t = rng.integers(-500, 500, size=(150_001, 4)).astype(np.int32)
+u = rng.integers(-500, 500, size=(90_000, 4)).astype(np.int32)
+ws, wt, wu = port.select(t, 1, 100), port.sort(t, 0), port.sort(u, 0)
+wm, wj = port.merge(wt, wu, 0), port.join(wt, wu, 0, 0)
+if not dry:
+    assert np.array_equal(smj_b200.select(t, 1, 100), ws)
+    assert np.array_equal(smj_b200.sort(t, 0), wt)
+    assert np.array_equal(smj_b200.merge(wt, wu, 0), wm)
+    assert np.array_equal(smj_b200.join(wt, wu, 0, 0), wj)
 print("SCAN_CHUNK_OK")
 '''
 
