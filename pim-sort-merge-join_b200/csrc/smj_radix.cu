@@ -318,269 +318,6 @@ radix_pass_kernel(const RadixLaunch L, int pass, u32 *tile_counter, u32 *err, in
     }
 }
 
-// ---- Two batches per tile.  A tile's fixed costs -- publishing 256 counts, the digit scan, above all the look-back, an L2
-// round-trip chain that only a quarter of the CTA's threads take part in -- are ~48 % of a tile's cycles in the kernel above
-// (profiles/r01_radix_lab_phases.txt) and do not depend on the tile's size, while registers (16 pairs per thread at 64
-// registers, two CTAs per SM) and shared memory (64 KB of reordered pairs per CTA) cap a tile at 8192 pairs.  Here a tile
-// is TWO batches of up to 8192 pairs that share ONE published count row and ONE look-back: the second batch (B, the upper
-// half of the tile's index range) is counted first, from registers that the first batch's (A) loads then reuse; A is counted,
-// the sums are published, A is ranked, the look-back runs, A is copied out while B travels in again, B is counted once
-// more (the per-warp counters were A's in between), ranked and copied out behind A's rows of the same digit.  B is read
-// twice -- 20 B of traffic per pair instead of 16, out of L2 when the pairs are few -- for half as many look-backs, and a
-// launch that fits one wave is cut into tiles of up to 2 x 8192 pairs instead of 8192: 3.3 M pairs = one tile per CTA.
-__global__ void __launch_bounds__(RS_THREADS, RS_CTAS_PER_SM)
-radix_pass2_kernel(const RadixLaunch L, int pass, u32 *tile_counter, u32 *err, int dyn_tiles)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 *s_items = reinterpret_cast<u64 *>(smem_raw);              // one BATCH in digit order
-    u32 *s_wcnt = reinterpret_cast<u32 *>(s_items + RS_TILE);      // [warp][256] counts -> running local slot
-    u32 *s_mask = s_wcnt + RS_WARPS * SMJ_RADIX;                   // [warp][256] peer masks (self-resetting); batch B's first count
-    u32 *s_goff = s_mask + RS_WARPS * SMJ_RADIX;                   // [256] global slot minus local slot per digit
-    u32 *s_wsum = s_goff + SMJ_RADIX;                              // warp totals of the bin scan
-    __shared__ u32 s_tile[2];
-    __shared__ const u64 *s_in[2];
-    __shared__ u64 *s_out[2];
-    __shared__ u32 s_kmin[2];
-    __shared__ u32 s_totb[SMJ_RADIX];    // batch B's digit totals (first count)
-    __shared__ u32 s_globb[SMJ_RADIX];   // first output slot of batch B's pairs, per digit
-
-    PDL_ENTER();
-    const u32 tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
-    const u32 lt = lanemask_lt();
-    const u32 sel = 0x4440u | (u32)pass;
-    u32 n0, n1 = 0, raw0 = 0, raw1 = 0;
-    {
-        u32 np0 = SMJ_KEY_PASSES, np1 = SMJ_KEY_PASSES, km0 = 0, km1 = 0;
-        const u64 v = L.p[0].n_dev ? *L.p[0].n_dev : (u64)L.p[0].n_max;
-        n0 = v < (u64)L.p[0].n_max ? (u32)v : L.p[0].n_max;
-        raw0 = n0;
-        if (L.p[0].plan) { np0 = L.p[0].plan->npass; km0 = L.p[0].plan->kmin; }
-        if ((u32)pass >= np0) n0 = 0;
-        if (L.nprob > 1) {
-            const u64 v1 = L.p[1].n_dev ? *L.p[1].n_dev : (u64)L.p[1].n_max;
-            n1 = v1 < (u64)L.p[1].n_max ? (u32)v1 : L.p[1].n_max;
-            raw1 = n1;
-            if (L.p[1].plan) { np1 = L.p[1].plan->npass; km1 = L.p[1].plan->kmin; }
-            if ((u32)pass >= np1) n1 = 0;
-        }
-        if (tid == 0) {
-            const bool odd0 = (np0 - (u32)pass) & 1u, odd1 = (np1 - (u32)pass) & 1u;
-            s_in[0] = odd0 ? L.p[0].buf[1] : L.p[0].buf[0];
-            s_out[0] = odd0 ? L.p[0].buf[0] : L.p[0].buf[1];
-            s_in[1] = odd1 ? L.p[1].buf[1] : L.p[1].buf[0];
-            s_out[1] = odd1 ? L.p[1].buf[0] : L.p[1].buf[1];
-            s_kmin[0] = km0;
-            s_kmin[1] = km1;
-        }
-    }
-    // Batch size of THIS launch: ipt items per thread (1..16).  Launches that fit one wave of full tiles are cut into equal
-    // tiles, one per CTA (from the raw pair counts, so every pass of a sort cuts alike); the others take full batches.
-    u32 ipt = RS_IPT;
-    {
-        const u64 total = (u64)raw0 + raw1;
-        const u64 slots = gridDim.x;
-        if (dyn_tiles && total <= slots * 2u * RS_TILE) {
-            ipt = (u32)((total + slots * 2u * RS_THREADS - 1) / (slots * 2u * RS_THREADS));
-            if (ipt < 1) ipt = 1;
-            if (ipt > (u32)RS_IPT) ipt = RS_IPT;
-            for (; ipt < (u32)RS_IPT; ipt++) {   // both problems' tiles inside the wave and inside their status arrays
-                const u64 ti = 2ull * RS_THREADS * ipt;
-                const u64 t0 = ((u64)raw0 + ti - 1) / ti, t1 = ((u64)raw1 + ti - 1) / ti;
-                if (t0 + t1 <= slots && t0 <= (u64)L.p[0].cap_tiles && (L.nprob < 2 || t1 <= (u64)L.p[1].cap_tiles)) break;
-            }
-        }
-    }
-    const u32 batch_items = ipt * RS_THREADS, tile_items = 2u * batch_items;
-    const u32 tiles0 = (u32)(((u64)n0 + tile_items - 1) / tile_items);
-    const u32 all_tiles = tiles0 + (u32)(((u64)n1 + tile_items - 1) / tile_items);
-
-    if (tid == 0) s_tile[0] = atomicAdd(tile_counter, 1u);
-    for (u32 i = tid; i < RS_WARPS * SMJ_RADIX; i += RS_THREADS) s_mask[i] = 0;
-    __syncthreads();
-    u32 ticket = s_tile[0];
-    int par = 0;
-
-    const u32 rel0 = w * 32 * ipt + lane;   // batch-relative index of item[0]; element order inside a batch is (warp, j, lane)
-    u64 item[RS_IPT];
-    // the pairs of one batch (half 0: A, 1: B) of the tile behind a ticket
-    auto load_batch = [&](u32 tk, u32 half) {
-        const bool sec = tk >= tiles0;
-        const u64 *src_in = s_in[sec];
-        const u32 nn = sec ? n1 : n0;
-        const u32 g0 = (sec ? tk - tiles0 : tk) * tile_items + half * batch_items + rel0;   // (< 2^31: at most 2^30 - 1 pairs per problem)
-#pragma unroll
-        for (int j = 0; j < RS_IPT; j++) item[j] = ((u32)j < ipt && g0 + j * 32 < nn) ? src_in[g0 + j * 32] : 0ull;
-    };
-    if (ticket < all_tiles) load_batch(ticket, 1);
-
-    u32 *my_cnt = s_wcnt + w * SMJ_RADIX;
-    u32 *my_mask = s_mask + w * SMJ_RADIX;
-    while (ticket < all_tiles) {
-        const bool second = ticket >= tiles0;
-        const RadixProblem &P = second ? L.p[1] : L.p[0];
-        const u32 n = second ? n1 : n0;
-        const u32 tile = second ? ticket - tiles0 : ticket;
-        u64 *__restrict__ out = s_out[second];
-        const u32 kmin = s_kmin[second];
-        const u32 *__restrict__ bin_base = P.bin_base;
-        u32 *status = P.status, *status_next = P.status_next;
-        const u32 base = tile * tile_items;
-        const u32 valid = (n - base < tile_items) ? (n - base) : tile_items;
-        const u32 valid_a = valid < batch_items ? valid : batch_items, valid_b = valid - valid_a;
-        const bool full_a = valid_a == (u32)RS_TILE, full_b = valid_b == (u32)RS_TILE;   // (only 8192-pair batches take the unpredicated path)
-
-        // ---- batch B's digit totals (its pairs are in registers): counted per warp in the idle mask array
-#pragma unroll
-        for (int i = 0; i < RS_WARPS * SMJ_RADIX / RS_THREADS; i++) s_wcnt[i * RS_THREADS + tid] = 0;
-        if (full_b) radix_count_tile<true>(item, sel, kmin, my_mask, rel0, valid_b, ipt);
-        else if (valid_b) radix_count_tile<false>(item, sel, kmin, my_mask, rel0, valid_b, ipt);
-        load_batch(ticket, 0);
-        __syncthreads();
-        if (tid < SMJ_RADIX) {
-            u32 tot_b = 0;
-#pragma unroll
-            for (int ww = 0; ww < RS_WARPS; ww++) { tot_b += s_mask[ww * SMJ_RADIX + tid]; s_mask[ww * SMJ_RADIX + tid] = 0; }
-            s_totb[tid] = tot_b;
-        }
-        // ---- batch A: per-warp digit histogram
-        if (full_a) radix_count_tile<true>(item, sel, kmin, my_cnt, rel0, valid_a, ipt);
-        else radix_count_tile<false>(item, sel, kmin, my_cnt, rel0, valid_a, ipt);
-        __syncthreads();
-
-        // ---- one thread per digit: totals over warps, publish the tile aggregate (A + B), scan A's digits
-        if (tid < SMJ_RADIX) {
-            u32 cnt_a = 0;
-#pragma unroll
-            for (int ww = 0; ww < RS_WARPS; ww++) cnt_a += s_wcnt[ww * SMJ_RADIX + tid];
-            const u32 cnt = cnt_a + s_totb[tid];
-            s_totb[tid] = cnt;                                 // (the tile's total from here on)
-            s_globb[tid] = cnt_a;
-            st_relaxed(&status[(size_t)tile * SMJ_RADIX + tid], (tile == 0 ? RS_FLAG_INCL : RS_FLAG_LOCAL) | cnt);
-            status_next[(size_t)tile * SMJ_RADIX + tid] = 0;   // the next pass (next kernel) reuses the other array
-            const u32 inc = warp_incl_scan(cnt_a);
-            if (lane == 31) s_wsum[w] = inc;
-            s_goff[tid] = inc - cnt_a;
-        }
-        __syncthreads();
-        if (tid < SMJ_RADIX) {
-            u32 run = s_goff[tid];
-            for (u32 ww = 0; ww < w; ww++) run += s_wsum[ww];
-            s_goff[tid] = run;                                 // A's local base, turned into (global - local) after the look-back
-#pragma unroll
-            for (int ww = 0; ww < RS_WARPS; ww++) {
-                const u32 c = s_wcnt[ww * SMJ_RADIX + tid];
-                s_wcnt[ww * SMJ_RADIX + tid] = run;
-                run += c;
-            }
-        }
-        __syncthreads();
-
-        // ---- rank A (stable: lanes in order, rows in order, warps in order) and reorder into shared memory
-        if (full_a) radix_rank_tile<true>(item, sel, kmin, my_cnt, my_mask, s_items, rel0, valid_a, lane, lt, ipt);
-        else radix_rank_tile<false>(item, sel, kmin, my_cnt, my_mask, s_items, rel0, valid_a, lane, lt, ipt);
-
-        // ---- next ticket, then the tile's look-back (predecessors published before they started ranking)
-        if (tid == RS_THREADS - 1) s_tile[par ^ 1] = atomicAdd(tile_counter, 1u);
-        if (tid < SMJ_RADIX) {
-            u32 excl = 0;
-            if (tile > 0) {
-                int t = (int)tile - 1;
-                u32 spins = 0;
-                bool done = false;
-                while (!done) {
-                    u32 v[RS_LB];
-#pragma unroll
-                    for (int r = 0; r < RS_LB; r++)
-                        v[r] = (t - r >= 0) ? ld_relaxed(&status[(size_t)(t - r) * SMJ_RADIX + tid]) : RS_FLAG_INCL;
-                    int used = 0;
-#pragma unroll
-                    for (int r = 0; r < RS_LB; r++) {
-                        if (!done && used == r) {
-                            const u32 flag = v[r] >> 30;
-                            if (flag != 0) {
-                                excl += v[r] & RS_VAL_MASK;
-                                used = r + 1;
-                                if (flag == 2) done = true;
-                            }
-                        }
-                    }
-                    t -= used;
-                    if (!done && used < RS_LB && ++spins > SMJ_SPIN_LIMIT) { atomicExch(err, SMJ_ERR_SPIN_RADIX); break; }
-                }
-                st_relaxed(&status[(size_t)tile * SMJ_RADIX + tid], RS_FLAG_INCL | ((excl + s_totb[tid]) & RS_VAL_MASK));
-            }
-            const u32 g = bin_base[tid] + excl;
-            s_globb[tid] += g;                                 // first output slot of batch B's pairs of this digit: behind A's
-            s_goff[tid] = g - s_goff[tid];                     // mod 2^32: added to a local slot >= the local base
-        }
-        __syncthreads();
-
-        // ---- B travels in again while A is copied out
-        if (valid_b) load_batch(ticket, 1);
-#pragma unroll
-        for (int k = 0; k < RS_IPT; k++) {
-            const u32 idx = tid + k * RS_THREADS;
-            if (!full_a && (u32)k >= ipt) break;
-            if (full_a || idx < valid_a) {
-                const u64 it = s_items[idx];
-                out[s_goff[pair_digit(it, sel, kmin)] + idx] = it;
-            }
-        }
-        __syncthreads();                                       // the batch buffer, the offsets and the counters are free again
-
-        if (valid_b) {                                         // (the same for every thread of the CTA)
-#pragma unroll
-            for (int i = 0; i < RS_WARPS * SMJ_RADIX / RS_THREADS; i++) s_wcnt[i * RS_THREADS + tid] = 0;
-            __syncthreads();
-            if (full_b) radix_count_tile<true>(item, sel, kmin, my_cnt, rel0, valid_b, ipt);
-            else radix_count_tile<false>(item, sel, kmin, my_cnt, rel0, valid_b, ipt);
-            __syncthreads();
-            u32 cnt_b = 0;
-            if (tid < SMJ_RADIX) {
-#pragma unroll
-                for (int ww = 0; ww < RS_WARPS; ww++) cnt_b += s_wcnt[ww * SMJ_RADIX + tid];
-                const u32 inc = warp_incl_scan(cnt_b);
-                if (lane == 31) s_wsum[w] = inc;
-                s_goff[tid] = inc - cnt_b;
-            }
-            __syncthreads();
-            if (tid < SMJ_RADIX) {
-                u32 run = s_goff[tid];
-                for (u32 ww = 0; ww < w; ww++) run += s_wsum[ww];
-                s_goff[tid] = s_globb[tid] - run;              // B's rows of a digit follow A's
-#pragma unroll
-                for (int ww = 0; ww < RS_WARPS; ww++) {
-                    const u32 c = s_wcnt[ww * SMJ_RADIX + tid];
-                    s_wcnt[ww * SMJ_RADIX + tid] = run;
-                    run += c;
-                }
-            }
-            __syncthreads();
-            if (full_b) radix_rank_tile<true>(item, sel, kmin, my_cnt, my_mask, s_items, rel0, valid_b, lane, lt, ipt);
-            else radix_rank_tile<false>(item, sel, kmin, my_cnt, my_mask, s_items, rel0, valid_b, lane, lt, ipt);
-            __syncthreads();
-        }
-
-        // ---- the next tile's batch B is requested, then this tile's B is copied out while it is in flight
-        const u32 next = s_tile[par ^ 1];
-        par ^= 1;
-        if (next < all_tiles) load_batch(next, 1);
-        if (valid_b) {
-#pragma unroll
-            for (int k = 0; k < RS_IPT; k++) {
-                const u32 idx = tid + k * RS_THREADS;
-                if (!full_b && (u32)k >= ipt) break;
-                if (full_b || idx < valid_b) {
-                    const u64 it = s_items[idx];
-                    out[s_goff[pair_digit(it, sel, kmin)] + idx] = it;
-                }
-            }
-        }
-        ticket = next;
-        // the first barrier of the next round orders these reads of the batch buffer and the offsets before their next writers
-    }
-}
-
 // Stand-alone digit histogram (used when the pairs did not come out of the select kernel).
 __global__ void __launch_bounds__(256) radix_hist_kernel(const u64 *__restrict__ pairs, u32 n, u32 *hist)
 {
@@ -656,20 +393,16 @@ static int launch_radix_pass(SmjCtx *c, const RadixLaunch &L, int pass, u32 *d_t
 {
     if (!c->radix_attr_set) {   // function attributes are per device
         CUDA_TRY(cudaFuncSetAttribute(radix_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
-        CUDA_TRY(cudaFuncSetAttribute(radix_pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
         c->radix_attr_set = true;
     }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     static const int dyn_tiles = !(getenv("SMJ_RADIX_DYN_TILES") && atoi(getenv("SMJ_RADIX_DYN_TILES")) == 0);
-    // SMJ_RADIX_BATCHES=1: the one-batch-per-tile kernel (radix_pass_kernel) instead of radix_pass2_kernel, for A/B runs
-    static const int batches = (getenv("SMJ_RADIX_BATCHES") && atoi(getenv("SMJ_RADIX_BATCHES")) == 2) ? 2 : 1;
-    size_t tiles = 0;   // the smallest tile is one item per thread (and batch)
+    size_t tiles = 0;   // the smallest tile is one item per thread
     for (int i = 0; i < L.nprob; i++) tiles += dyn_tiles ? ((size_t)L.p[i].n_max + RS_THREADS - 1) / RS_THREADS : smj_radix_num_tiles(L.p[i].n_max);
     if (tiles == 0) return SMJ_OK;
     const u32 grid = tiles < (size_t)(sms * RS_CTAS_PER_SM) ? (u32)tiles : (u32)(sms * RS_CTAS_PER_SM);
-    if (batches == 2) smj_launch(c, radix_pass2_kernel, grid, RS_THREADS, RS_SMEM, L, pass, d_tile_counter, c->d_err, dyn_tiles);
-    else smj_launch(c, radix_pass_kernel, grid, RS_THREADS, RS_SMEM, L, pass, d_tile_counter, c->d_err, dyn_tiles);
+    smj_launch(c, radix_pass_kernel, grid, RS_THREADS, RS_SMEM, L, pass, d_tile_counter, c->d_err, dyn_tiles);
     KERNEL_CHECK(c);
     return SMJ_OK;
 }
@@ -745,7 +478,6 @@ void smj_preload_radix(void)
 {
     cudaFuncAttributes a;
     cudaFuncGetAttributes(&a, radix_pass_kernel);
-    cudaFuncGetAttributes(&a, radix_pass2_kernel);
     cudaFuncGetAttributes(&a, radix_hist_kernel);
     cudaFuncGetAttributes(&a, radix_scan_kernel);
     cudaGetLastError();
