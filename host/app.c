@@ -75,12 +75,13 @@ static void load_or_die(const char *path, smj_table_t *t)
         fseek(f, 0, SEEK_END);
         long sz = ftell(f);
         fseek(f, 0, SEEK_SET);
-        char *buf = (char *)pinned_alloc((uint64_t)sz + 1);
-        if (!buf) { fprintf(stderr, "out of pinned memory for %s\n", path); exit(EXIT_FAILURE); }
+        /* plain memory: the text crosses PCIe once, and pinning a buffer that is used once costs more than it saves */
+        char *buf = (char *)malloc((size_t)sz + 1);
+        if (!buf) { fprintf(stderr, "out of memory for %s\n", path); exit(EXIT_FAILURE); }
         size_t got = fread(buf, 1, (size_t)sz, f);
         fclose(f);
         int rc = smj_csv_parse(buf, got, t);
-        smj_host_free(buf);
+        free(buf);
         if (rc == SMJ_OK) { if (t->rows < 0) t->rows = 0; return; }
         if (rc != SMJ_EIRREGULAR) {
             fprintf(stderr, "smj_csv_parse(%s) failed: %s (%s)\n", path, smj_strerror(rc), smj_last_error());
